@@ -1,0 +1,133 @@
+/*
+ * zles.h — C ABI of the B200-native zlib codec (libzles.so).
+ *
+ * This is the drop-in boundary for zprodev/zlib.es.  The reference has no FFI of
+ * its own; its public surface is two functions,
+ *     export declare function inflate(input: Uint8Array): Uint8Array;
+ *     export declare function deflate(input: Uint8Array): Uint8Array;
+ * (/root/reference/dist/tsc/zlib.d.ts:4-5, implemented at /root/reference/src/zlib.ts:11-49),
+ * plus synchronous `throw new Error(msg)` with five fixed messages.  The entry
+ * points below are what an N-API / ctypes binding for that surface binds; the
+ * binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * zlib.es_b200/node/addon.c (N-API) and zlib.es_b200/_capi.py (ctypes).
+ *
+ * Conventions: plain pointers and sizes, no exceptions, int status (0 = ok),
+ * caller owns every buffer.  "host" functions take host pointers and do the
+ * host<->device copies themselves; "dev" functions take device pointers (the
+ * data is already in HBM) and run on the handle's stream.  There is no CPU
+ * fallback: every call fails with ZLES_E_CUDA when no usable GPU is present.
+ */
+#ifndef ZLES_H
+#define ZLES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..5 carry the reference's exact Error messages (zles_strerror). */
+enum {
+  ZLES_OK = 0,
+  ZLES_E_NOT_DEFLATE = 1,  /* 'Not compressed by deflate'    /root/reference/src/zlib.ts:15 */
+  ZLES_E_BTYPE3 = 2,       /* 'Not supported BTYPE : 3'      /root/reference/src/inflate.ts:32 */
+  ZLES_E_INSUFFICIENT = 3, /* 'Data length is insufficient'  /root/reference/src/inflate.ts:35 */
+  ZLES_E_CORRUPTED = 4,    /* 'Data is corrupted'            /root/reference/src/inflate.ts:50,88,166,247,276 */
+  ZLES_E_LACK = 5,         /* 'Lack of data length'          /root/reference/src/utils/BitReadStream.ts:15 */
+  ZLES_E_OUTPUT_FULL = 16, /* output buffer too small; *out_len holds the size needed */
+  ZLES_E_CUDA = 17,        /* CUDA runtime error (zles_last_cuda_error) */
+  ZLES_E_ARG = 18,
+  ZLES_E_NOMEM = 19
+};
+
+typedef struct zles_ctx zles_ctx;
+
+/* Library / error helpers. */
+const char *zles_version(void);
+const char *zles_strerror(int code);
+const char *zles_last_cuda_error(void);
+
+/* One context per (device, stream); calls on one context are serialised by the caller. */
+int zles_ctx_create(int device, zles_ctx **ctx);
+void zles_ctx_destroy(zles_ctx *ctx);
+/* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
+int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
+/* Encoder search depth; defaults mirror /root/reference/src/lz77.ts:7-9 scaled for an
+ * all-positions search: max_checks, min_checks (once good_len is reached), good_len, lazy. */
+int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
+/* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
+uint64_t zles_ctx_launches(const zles_ctx *ctx);
+
+/* ---- the drop-in pair: host buffers in, host buffers out ----------------------
+ * zles_deflate   replaces zlib.deflate  (/root/reference/src/zlib.ts:25-49)
+ * zles_inflate   replaces zlib.inflate  (/root/reference/src/zlib.ts:11-23)
+ * Both use a process-wide default context on device 0 when ctx is NULL. */
+size_t zles_deflate_bound(size_t n);
+int zles_deflate(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_inflate(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+/* inflate with a library-allocated result (the reference's return-a-new-array shape); free with zles_free. */
+int zles_inflate_alloc(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+void zles_free(void *p);
+/* calcAdler32 >>> 0 (/root/reference/src/adler32.ts:1-10). */
+int zles_adler32(zles_ctx *ctx, const uint8_t *in, size_t n, uint32_t *adler);
+
+/* ---- batches of independent buffers (BASELINE config 3: 262,144 x 4 KiB) --------
+ * Buffer i is in[in_off[i] .. in_off[i+1]); its result is written at out + out_off[i]
+ * (capacity out_off[i+1] - out_off[i]) and its length to out_len[i]; status[i] gets
+ * the per-buffer code.  Host pointers. Returns the first non-zero status. */
+int zles_deflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
+                       const uint64_t *out_off, uint64_t *out_len, int32_t *status);
+int zles_inflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
+                       const uint64_t *out_off, uint64_t *out_len, int32_t *status);
+
+/* ---- device-resident forms (inputs and outputs already in HBM) -------------------
+ * Same results as the host forms, no host<->device payload copies. */
+int zles_dev_deflate(zles_ctx *ctx, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t cap, size_t *out_len);
+int zles_dev_inflate(zles_ctx *ctx, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t cap, size_t *out_len);
+int zles_dev_adler32(zles_ctx *ctx, const uint8_t *d_in, size_t n, uint32_t *adler);
+int zles_dev_deflate_batch(zles_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint32_t count, uint8_t *d_out,
+                           const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status);
+int zles_dev_inflate_batch(zles_ctx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint32_t count, uint8_t *d_out,
+                           const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status);
+
+/* ---- sharded deflate: one stream, chunks split over the GPUs of a node -----------
+ * Rank r compresses a contiguous shard (a multiple of 128 KiB except on the last
+ * rank).  Phase 1 runs the match finder, code construction and layout and reports
+ * the shard's compressed size and Adler-32 partial sums; the ranks exchange those
+ * (NCCL all-gather in zlib.es_b200/dist.py); phase 2 writes the shard's bytes at
+ * its global offset — d_dst may be a peer-mapped pointer (zles_ipc_*), so the
+ * segments are stored straight into the final stream over NVLink. */
+typedef struct {
+  uint64_t comp_bytes;   /* compressed size of the shard (no zlib header/trailer) */
+  uint64_t raw_bytes;    /* shard length */
+  uint64_t adler_a;      /* sum of bytes mod 65521 */
+  uint64_t adler_b;      /* sum of (raw_bytes - i) * byte[i] mod 65521 */
+  uint64_t n_chunks;     /* 128 KiB chunks in the shard */
+} zles_shard_info;
+int zles_dev_deflate_phase1(zles_ctx *ctx, const uint8_t *d_in, size_t n, int is_last_shard, zles_shard_info *info);
+/* per-chunk compressed sizes of the last phase 1 (device pointer to n_chunks+1 uint64 offsets) */
+int zles_dev_deflate_chunk_offsets(zles_ctx *ctx, const uint64_t **d_offsets);
+int zles_dev_deflate_phase2(zles_ctx *ctx, uint8_t *d_dst);
+/* Combine the per-shard sums of all ranks (in rank order) into the stream's Adler-32. */
+uint32_t zles_adler32_combine_shards(const zles_shard_info *infos, uint32_t count);
+/* Inflate `n` bytes of marker-delimited chunks that start at a chunk boundary (no zlib header). */
+int zles_dev_inflate_segment(zles_ctx *ctx, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
+                             size_t *out_len);
+
+/* CUDA IPC helpers so that another process can map a device buffer (64-byte handles). */
+int zles_ipc_export(const void *d_ptr, uint8_t handle[64]);
+int zles_ipc_open(const uint8_t handle[64], void **d_ptr);
+int zles_ipc_close(void *d_ptr);
+
+/* Synthetic corpora of BASELINE.json / SURVEY.md §8d, generated in HBM (kind: 0 text,
+ * 1 structured binary, 2 random, 3 mixed); `offset` is the absolute byte offset of the
+ * first byte so that shards of one corpus can be generated independently. */
+int zles_dev_corpus(zles_ctx *ctx, int kind, uint64_t offset, uint8_t *d_out, size_t n);
+/* Same bytes on the host (single thread; for tests and the CPU baseline sample). */
+int zles_host_corpus(int kind, uint64_t offset, uint8_t *out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

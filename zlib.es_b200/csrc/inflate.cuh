@@ -1,0 +1,513 @@
+// inflate.cuh — kernels K6/K7: warp-per-segment table-driven Huffman decode with
+// LZ77 back-reference copy, and the sync-marker scan that finds the independent
+// segments our own deflate emits.
+//
+// Replaces /root/reference/src/inflate.ts:16-292 (bit-serial canonical decode, one
+// `read()` per code bit, byte-serial copy), src/huffman.ts:8-53 (decode tables),
+// src/utils/BitReadStream.ts and src/utils/Uint8WriteStream.ts.
+//
+// A "segment" is a run of deflate blocks that starts on a byte boundary and ends
+// with the final block or with an empty stored block (the 00 00 FF FF sync
+// marker).  Our encoder ends every independent 128 KiB chunk with that marker,
+// so the segments of one of our streams decode in parallel, one warp each;
+// streams from other encoders (zlib.es itself, system zlib, the reference's
+// test/data/compressed.bin) are a single segment and decode on one warp.
+// A segment is accepted only through k_inf_check / the chain walk in capi: it
+// must start where the previous one ended, decode without error, and never
+// reach back before its own start.
+//
+// Roofline: HBM-bound in principle (algorithmic bytes = C read + U written),
+// in practice bound by the serial decode chain of each warp; see DESIGN.md.
+#pragma once
+#include "zles_dev.h"
+
+namespace zles {
+
+constexpr int INF_WARPS = 4;
+constexpr int INF_THREADS = INF_WARPS * 32;
+constexpr int LL_ROOT = 10;
+constexpr int D_ROOT = 8;
+constexpr int CL_ROOT = 7;
+
+// status codes of a segment (the error values equal the ZLES_E_* codes of include/zles.h)
+constexpr u32 SEG_SYNC = 100;      // ended on an empty stored block
+constexpr u32 SEG_FINAL = 101;     // ended with BFINAL
+constexpr u32 SEG_E_BTYPE3 = 2;    // 'Not supported BTYPE : 3'        src/inflate.ts:32
+constexpr u32 SEG_E_INSUFF = 3;    // 'Data length is insufficient'    src/inflate.ts:35
+constexpr u32 SEG_E_CORRUPT = 4;   // 'Data is corrupted'              src/inflate.ts:50,88,166,247,276
+constexpr u32 SEG_E_LACK = 5;      // 'Lack of data length'            src/utils/BitReadStream.ts:15
+constexpr u32 SEGF_HISTORY = 1;    // a distance reached before the segment start
+constexpr u32 SEGF_OVERFLOW = 2;   // output did not fit (out_len is still the true length)
+
+struct InfRes {
+  u64 end_pos;  // byte position (in the stream) just after the segment
+  u64 out_len;  // bytes this segment decodes to
+  u32 status;
+  u32 flags;
+};
+
+struct InfTab {  // canonical description of one code, in shared memory
+  u32 first[16];
+  u16 cnt[16];
+  u16 off[16];
+};
+
+struct InfWarpSmem {
+  u16 lut_ll[1 << LL_ROOT];
+  u16 lut_d[1 << D_ROOT];  // doubles as the code-length-code LUT while a header is parsed
+  u16 sorted_ll[288];
+  u16 sorted_d[32];
+  InfTab tab_ll, tab_d;
+  u16 cur[16];
+  u8 lens[320];  // [0,288) literal/length code lengths, [288,320) distance code lengths
+  u8 cl_lens[32];
+};
+constexpr int INF_SMEM = (int)(sizeof(InfWarpSmem) + sizeof(InfRes)) * INF_WARPS;  // per-warp tables | per-warp result (batch kernel)
+
+// ---- bit reader: warp-uniform state, input fetched 128 B per warp at a time ----
+struct InfReader {
+  const u8 *in;   // stream base
+  u64 n;          // stream length in bytes
+  const u32 *words;  // `in` rounded down to 4 bytes
+  u32 skew;          // in - words, in bytes
+  u64 widx;          // next word to consume
+  u64 win_base;      // word index held by lane 0 of `win`
+  u32 win, win_next;
+  u64 bb;
+  u32 bc;
+  u32 overrun;
+
+  __device__ __forceinline__ u32 load_word(u64 wi) const {
+    // word wi covers stream bytes [4*wi - skew, 4*wi - skew + 4); bytes outside [0, n) read as 0
+    // (/root/reference/src/utils/BitReadStream.ts:33-35 reads `undefined << k === 0` past the end)
+    long long lo = (long long)(wi << 2) - (long long)skew;
+    if (lo >= 0 && (u64)lo + 4 <= n) return __ldg(words + wi);
+    u32 v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      long long b = lo + k;
+      if (b >= 0 && (u64)b < n) v |= (u32)in[b] << (8 * k);
+    }
+    return v;
+  }
+  __device__ __forceinline__ u32 next_word() {
+    if (widx - win_base >= 32) {
+      win_base += 32;
+      win = win_next;
+      win_next = load_word(win_base + 32 + lane_id());
+    }
+    u32 w = __shfl_sync(ZLES_FULL, win, (int)(widx & 31));
+    if (((widx << 2) > n + skew + 8)) overrun = 1;
+    widx++;
+    return w;
+  }
+  __device__ __forceinline__ void init(const u8 *in_, u64 n_, u64 byte_pos) {
+    in = in_; n = n_;
+    skew = (u32)((uintptr_t)in_ & 3);
+    words = reinterpret_cast<const u32 *>(in_ - skew);
+    overrun = 0;
+    u64 a = byte_pos + skew;
+    widx = a >> 2;
+    win_base = widx & ~(u64)31;
+    win = load_word(win_base + lane_id());
+    win_next = load_word(win_base + 32 + lane_id());
+    u32 sh = (u32)(a & 3) * 8;
+    bb = (u64)(next_word() >> sh);
+    bc = 32 - sh;
+    refill();
+  }
+  __device__ __forceinline__ void refill() {
+    if (bc <= 32) {
+      bb |= (u64)next_word() << bc;
+      bc += 32;
+    }
+  }
+  __device__ __forceinline__ u32 peek(u32 k) const { return (u32)bb & ((1u << k) - 1); }
+  __device__ __forceinline__ void skip(u32 k) { bb >>= k; bc -= k; }
+  __device__ __forceinline__ u32 take(u32 k) { u32 v = peek(k); skip(k); return v; }
+  // bit position (from stream byte 0) of the next unread bit
+  __device__ __forceinline__ u64 bitpos() const { return (widx << 5) - bc - ((u64)skew << 3); }
+};
+
+// Builds the canonical arrays and the root LUT of one code from its lengths
+// (same assignment as generateHuffmanTable, /root/reference/src/huffman.ts:8-39:
+// by length, then ascending symbol; code <<= 1 per length).  n is a multiple of 32.
+__device__ __forceinline__ void inf_build(const u8 *lens, int n, int root, u16 *lut, u16 *sorted, InfTab *t, u16 *cur) {
+  const u32 lane = lane_id();
+  if (lane < 16) t->cnt[lane] = 0;
+  __syncwarp();
+  for (int g = 0; g < n; g += 32) {
+    u32 l = lens[g + lane];
+    u32 m = __match_any_sync(ZLES_FULL, l);
+    if (l && lane == (u32)(__ffs((int)m) - 1)) t->cnt[l] = (u16)(t->cnt[l] + __popc(m));
+    __syncwarp();
+  }
+  if (lane == 0) {
+    u32 code = 0, o = 0;
+    t->first[0] = 0; t->off[0] = 0; cur[0] = 0;
+    for (int l = 1; l < 16; l++) {
+      t->first[l] = code;
+      t->off[l] = (u16)o;
+      cur[l] = (u16)o;
+      o += t->cnt[l];
+      code = (code + t->cnt[l]) << 1;
+    }
+  }
+  __syncwarp();
+  for (int g = 0; g < n; g += 32) {
+    u32 l = lens[g + lane];
+    u32 m = __match_any_sync(ZLES_FULL, l);
+    u32 base = cur[l];
+    __syncwarp();
+    if (l) {
+      sorted[base + __popc(m & lanemask_lt())] = (u16)(g + lane);
+      if (lane == (u32)(__ffs((int)m) - 1)) cur[l] = (u16)(base + __popc(m));
+    }
+    __syncwarp();
+  }
+  for (u32 i = lane; i < (1u << root); i += 32) {
+    u32 code = 0, e = 0;
+    for (int l = 1; l <= root; l++) {
+      code = (code << 1) | ((i >> (l - 1)) & 1);
+      u32 d = code - t->first[l];
+      if (code >= t->first[l] && d < t->cnt[l]) {
+        e = ((u32)sorted[t->off[l] + d] << 4) | (u32)l;
+        break;
+      }
+    }
+    lut[i] = (u16)e;
+  }
+  __syncwarp();
+}
+
+// Canonical decode without the LUT (codes longer than the root, or invalid): tries
+// lengths in increasing order like the lookup loop at /root/reference/src/inflate.ts:238-252.
+__device__ __forceinline__ bool inf_slow(u64 bb, const InfTab *t, const u16 *sorted, u32 &sym, u32 &len) {
+  u32 code = 0;
+  for (int l = 1; l < 16; l++) {
+    code = (code << 1) | (u32)((bb >> (l - 1)) & 1);
+    u32 d = code - t->first[l];
+    if (code >= t->first[l] && d < t->cnt[l]) {
+      sym = sorted[t->off[l] + d];
+      len = (u32)l;
+      return true;
+    }
+  }
+  return false;
+}
+
+__device__ __forceinline__ bool inf_decode(InfReader &r, const u16 *lut, int root, const InfTab *t, const u16 *sorted, u32 &sym) {
+  u32 e = lut[r.peek((u32)root)];
+  u32 l = e & 15;
+  sym = e >> 4;
+  if (l == 0 && !inf_slow(r.bb, t, sorted, sym, l)) return false;
+  r.skip(l);
+  return true;
+}
+
+// Decodes one segment on one warp.  Returns through *res (lane 0 writes).
+__device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n, u64 in_pos, u8 *out, u64 out_off, u64 cap,
+                                            bool stop_at_sync, InfRes *res) {
+  const u32 lane = lane_id();
+  InfReader r;
+  r.init(in, n, in_pos);
+  const u64 obase = out_off;
+  u64 opos = out_off;
+  u32 status = 0, flags = 0;
+  u64 end_pos = 0;
+
+  for (;;) {  // blocks, /root/reference/src/inflate.ts:22-37
+    r.refill();
+    if (r.overrun) { status = SEG_E_LACK; break; }
+    if (r.bitpos() >= (n << 3)) { status = SEG_E_INSUFF; break; }
+    const u32 bfinal = r.take(1);
+    const u32 btype = r.take(2);
+    if (btype == 3) { status = SEG_E_BTYPE3; break; }
+    if (btype == 0) {  // stored, src/inflate.ts:42-55
+      r.skip((u32)((0 - r.bitpos()) & 7));
+      r.refill();
+      const u32 LEN = r.take(16);
+      r.refill();
+      const u32 NLEN = r.take(16);
+      if (LEN + NLEN != 65535) { status = SEG_E_CORRUPT; break; }
+      const u64 q = r.bitpos() >> 3;
+      for (u32 i = lane; i < LEN; i += 32) {
+        u8 v = (q + i < n) ? in[q + i] : (u8)0;
+        if (opos + i < cap) out[opos + i] = v;
+      }
+      opos += LEN;
+      if (q + LEN > n) { status = SEG_E_LACK; break; }
+      if (bfinal) { status = SEG_FINAL; end_pos = q + LEN; break; }
+      if (LEN == 0 && stop_at_sync) { status = SEG_SYNC; end_pos = q; break; }
+      r.init(in, n, q + LEN);
+      continue;
+    }
+    if (btype == 1) {  // fixed, src/huffman.ts:41-53, src/inflate.ts:57-118
+      for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+      __syncwarp();
+    } else {  // dynamic header, src/inflate.ts:121-202
+      const u32 HLIT = r.take(5) + 257;
+      const u32 HDIST = r.take(5) + 1;
+      const u32 HCLEN = r.take(4) + 4;
+      S->cl_lens[lane] = 0;
+      for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
+      __syncwarp();
+      for (u32 i = 0; i < HCLEN; i++) {
+        r.refill();
+        u32 v = r.take(3);
+        if (lane == 0) S->cl_lens[c_cl_order[i]] = (u8)v;
+      }
+      __syncwarp();
+      inf_build(S->cl_lens, 32, CL_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+      const u32 total = HLIT + HDIST;
+      u32 prev = 0;
+      bool bad = false;
+      for (u32 i = 0; i < total;) {
+        r.refill();
+        if (r.overrun) { bad = true; status = SEG_E_LACK; break; }
+        u32 sym;
+        if (!inf_decode(r, S->lut_d, CL_ROOT, &S->tab_d, S->sorted_d, sym)) { bad = true; status = SEG_E_CORRUPT; break; }
+        u32 rep = 1, val = sym;
+        if (sym == 16) { rep = 3 + r.take(2); val = prev; }
+        else if (sym == 17) { rep = 3 + r.take(3); val = 0; prev = 0; }
+        else if (sym == 18) { rep = 11 + r.take(7); val = 0; prev = 0; }
+        else prev = sym;
+        if (val) {
+          for (u32 k = lane; k < rep; k += 32) {
+            u32 j = i + k;
+            if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
+            else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
+          }
+        }
+        i += rep;
+      }
+      if (bad) break;
+      __syncwarp();
+    }
+    inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
+    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+
+    // symbol loop, src/inflate.ts:76-117 / 237-291
+    for (;;) {
+      r.refill();
+      if (r.overrun) { status = SEG_E_LACK; break; }
+      u32 sym;
+      if (!inf_decode(r, S->lut_ll, LL_ROOT, &S->tab_ll, S->sorted_ll, sym)) { status = SEG_E_CORRUPT; break; }
+      if (sym < 256) {
+        if (lane == 0 && opos < cap) out[opos] = (u8)sym;
+        opos++;
+        continue;
+      }
+      if (sym == 256) break;
+      const u32 ls = sym - 257;
+      if (ls >= 29) { status = SEG_E_CORRUPT; break; }
+      const u32 len = c_len_base[ls] + r.take(c_len_extra[ls]);
+      r.refill();
+      u32 ds;
+      if (!inf_decode(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, ds)) { status = SEG_E_CORRUPT; break; }
+      if (ds >= 30) { status = SEG_E_CORRUPT; break; }
+      r.refill();
+      const u32 dist = c_dist_base[ds] + r.take(c_dist_extra[ds]);
+      // back-reference copy, src/inflate.ts:287-290; bytes before the start read as 0
+      const long long src = (long long)opos - (long long)dist;
+      if (src < (long long)obase) flags |= SEGF_HISTORY;
+      __syncwarp();
+      if (dist >= len) {
+        for (u32 i = lane; i < len; i += 32) {
+          long long s = src + i;
+          u8 v = (s >= (long long)obase && (u64)s < cap) ? out[s] : (u8)0;
+          if (opos + i < cap) out[opos + i] = v;
+        }
+      } else {  // overlapping: the output is periodic with period dist
+        for (u32 i = lane; i < len; i += 32) {
+          long long s = src + (i % dist);
+          u8 v = (s >= (long long)obase && (u64)s < cap) ? out[s] : (u8)0;
+          if (opos + i < cap) out[opos + i] = v;
+        }
+      }
+      opos += len;
+      __syncwarp();
+    }
+    if (status) break;
+    if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
+  }
+  if (opos > cap) flags |= SEGF_OVERFLOW;
+  if (lane == 0) {
+    res->end_pos = end_pos;
+    res->out_len = opos - obase;
+    res->status = status;
+    res->flags = flags;
+  }
+}
+
+// Grid of persistent warps; each takes segment indices from a global counter.
+// in_pos[j] = start byte of segment j; out_off == nullptr means "segment j writes
+// at j * CHUNK" (the optimistic placement that is right for our own streams).
+__global__ void __launch_bounds__(INF_THREADS)
+k_inflate(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ in_pos, const u64 *__restrict__ out_off,
+          const u32 *__restrict__ nseg_ptr, u32 nseg_cap, u8 *out, u64 cap, int stop_at_sync, InfRes *res, u32 *counter) {
+  ZLES_SMEM_DECL(smem_raw);
+  InfWarpSmem *S = reinterpret_cast<InfWarpSmem *>(smem_raw) + warp_id();
+  const u32 nseg = umin(*nseg_ptr, nseg_cap);
+  for (;;) {
+    u32 j = 0;
+    if (lane_id() == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(ZLES_FULL, j, 0);
+    if (j >= nseg) break;
+    u64 oo = out_off ? out_off[j] : (u64)j * CHUNK;
+    inf_segment(S, in, n, in_pos[j], out, oo, cap, stop_at_sync != 0, res + j);
+    __syncwarp();
+  }
+}
+
+// ---- sync-marker scan -------------------------------------------------------
+// A candidate segment start is a byte position c with in[c-4..c) == 00 00 FF FF.
+// Pass 1 counts candidates per 4 KiB tile; pass 2 (after a scan of the counts)
+// writes their positions in ascending order.  cand[0] is always `first`.
+constexpr int MARK_THREADS = 256;
+constexpr u32 MARK_TILE = MARK_THREADS * 16;
+
+__device__ __forceinline__ u32 mark_mask16(const u8 *__restrict__ in, u64 n, u64 first, u64 v) {
+  // bit k set <=> position c = 16 v + k is a candidate
+  u64 c0 = v << 4;
+  if (c0 >= n) return 0;
+  u32 m = 0;
+  if (c0 >= 4 && c0 + 16 <= n && (((uintptr_t)in & 3) == 0)) {
+    const u32 *w = reinterpret_cast<const u32 *>(in + c0 - 4);
+    u32 W[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) W[k] = __ldg(w + k);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      u32 x = (k & 3) ? __funnelshift_r(W[k >> 2], W[(k >> 2) + 1], (k & 3) * 8) : W[k >> 2];
+      if (x == 0xFFFF0000u) m |= 1u << k;
+    }
+  } else {
+    for (int k = 0; k < 16; k++) {
+      u64 c = c0 + k;
+      if (c >= 4 && c < n && in[c - 4] == 0 && in[c - 3] == 0 && in[c - 2] == 0xFF && in[c - 1] == 0xFF) m |= 1u << k;
+    }
+  }
+  // a candidate must leave at least one byte to decode and lie after the first segment start
+  for (int k = 0; k < 16; k++)
+    if ((m >> k) & 1) {
+      u64 c = c0 + k;
+      if (c <= first || c >= n) m &= ~(1u << k);
+    }
+  return m;
+}
+
+__global__ void __launch_bounds__(MARK_THREADS) k_mark_count(const u8 *__restrict__ in, u64 n, u64 first, u32 *tile_cnt) {
+  ZLES_SMEM_DECL(smem_raw);
+  u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
+  u64 v = (u64)blockIdx.x * MARK_THREADS + threadIdx.x;
+  u32 c = (u32)__popc(mark_mask16(in, n, first, v));
+  u32 total;
+  block_exscan(c, scratch, &total);
+  if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of tile counts in place; writes *ncand = 1 + total (cand[0] = first)
+__global__ void __launch_bounds__(1024) k_mark_scan(u32 *tile_cnt, u32 ntiles, u32 *ncand) {
+  ZLES_SMEM_DECL(smem_raw);
+  u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
+  u32 carry = 1;
+  for (u32 base = 0; base < ntiles; base += 1024) {
+    u32 i = base + threadIdx.x;
+    u32 c = i < ntiles ? tile_cnt[i] : 0;
+    u32 total;
+    u32 ex = block_exscan(c, scratch, &total);
+    if (i < ntiles) tile_cnt[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) *ncand = carry;
+}
+
+__global__ void __launch_bounds__(MARK_THREADS)
+k_mark_emit(const u8 *__restrict__ in, u64 n, u64 first, const u32 *tile_base, u64 *cand, u32 cand_cap) {
+  ZLES_SMEM_DECL(smem_raw);
+  u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
+  u64 v = (u64)blockIdx.x * MARK_THREADS + threadIdx.x;
+  u32 m = mark_mask16(in, n, first, v);
+  u32 total;
+  u32 ex = block_exscan((u32)__popc(m), scratch, &total);
+  u32 o = tile_base[blockIdx.x] + ex;
+  while (m) {
+    int k = __ffs((int)m) - 1;
+    m &= m - 1;
+    if (o < cand_cap) cand[o] = (v << 4) + k;
+    o++;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) cand[0] = first;
+}
+
+// stream too short to hold a marker: the only candidate is `first`
+__global__ void k_mark_none(u64 first, u64 *cand, u32 *ncand) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { cand[0] = first; *ncand = 1; }
+}
+
+// ---- acceptance of the optimistic parallel decode -----------------------------
+// problems[0] stays 0 only if every segment j ended on the marker that starts
+// segment j+1, needed no history, produced exactly CHUNK bytes (the last one:
+// <= CHUNK and BFINAL).  Bit 1 (value 2) alone = all of that holds but the output
+// buffer was too small; bit 0 = anything else, and the host walks the chain
+// (zles.cu).  total[0] = sum of out_len.
+__global__ void __launch_bounds__(256)
+k_inf_check(const InfRes *res, const u64 *cand, const u32 *nseg_ptr, u32 nseg_cap, u32 *problems, unsigned long long *total) {
+  const u32 nseg_all = *nseg_ptr;
+  const u32 nseg = umin(nseg_all, nseg_cap);
+  u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 bad = 0;
+  u64 len = 0;
+  if (j == 0 && nseg_all > nseg_cap) bad |= 1;
+  if (j < nseg) {
+    InfRes r = res[j];
+    len = r.out_len;
+    bool good;
+    if (j + 1 < nseg) good = r.status == SEG_SYNC && r.end_pos == cand[j + 1] && r.out_len == CHUNK;
+    else good = r.status == SEG_FINAL && r.out_len <= CHUNK;
+    if ((r.flags & SEGF_HISTORY) && j > 0) good = false;
+    if (!good) bad |= 1;
+    if (r.flags & SEGF_OVERFLOW) bad |= 2;
+  }
+  if (bad) atomicOr(problems, bad);
+  if (len) atomicAdd(total, (unsigned long long)len);
+}
+
+// ---- batches of independent zlib streams: one warp per stream, sequential inside ----------
+__global__ void __launch_bounds__(INF_THREADS)
+k_inflate_batch(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 count, u8 *out, const u64 *__restrict__ out_off,
+                u64 *out_len, int32_t *status, u32 *counter, u32 *first_err) {
+  ZLES_SMEM_DECL(smem_raw);
+  InfWarpSmem *S = reinterpret_cast<InfWarpSmem *>(smem_raw) + warp_id();
+  InfRes *s_res = reinterpret_cast<InfRes *>(smem_raw + sizeof(InfWarpSmem) * INF_WARPS);
+  for (;;) {
+    u32 j = 0;
+    if (lane_id() == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(ZLES_FULL, j, 0);
+    if (j >= count) break;
+    const u8 *sin = in + in_off[j];
+    const u64 sn = in_off[j + 1] - in_off[j];
+    u32 code = 0;
+    u64 olen = 0;
+    if (((sn ? sin[0] : 0) & 15) != 8) {
+      code = 1;  // 'Not compressed by deflate', /root/reference/src/zlib.ts:13-16
+    } else {
+      InfRes *r = &s_res[warp_id()];
+      inf_segment(S, sin, sn, 2, out, out_off[j], out_off[j + 1], false, r);
+      __syncwarp();
+      olen = r->out_len;
+      if (r->status != SEG_FINAL) code = r->status;
+      else if (r->flags & SEGF_OVERFLOW) code = 16;  // ZLES_E_OUTPUT_FULL
+      __syncwarp();
+    }
+    if (lane_id() == 0) {
+      out_len[j] = olen;
+      status[j] = (int32_t)code;
+      if (code) atomicMax(first_err, code);
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace zles

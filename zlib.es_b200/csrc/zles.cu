@@ -1,0 +1,952 @@
+// zles.cu — host side of libzles.so: the C ABI of include/zles.h over the sm_100a
+// kernels in this directory.
+//
+// Replaces, for callers, zlib.deflate / zlib.inflate of the reference
+// (/root/reference/src/zlib.ts:11-49).  The zlib framing (CMF/FLG header, Adler-32
+// trailer, /root/reference/src/zlib.ts:28-46) is done here on the host; everything
+// else runs on the GPU.  There is no CPU fallback: without a usable device every
+// entry point returns ZLES_E_CUDA.
+//
+// The same file builds with -DZLES_EMU against tests/emu (CPU thread emulator,
+// tests only).
+#include "../../include/zles.h"
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "zles_rt.h"
+// kernels
+#include "adler32.cuh"
+#include "corpus.cuh"
+#include "corpus_text.h"
+#include "huffman.cuh"
+#include "inflate.cuh"
+#include "lz77.cuh"
+#include "pack.cuh"
+
+using namespace zles;
+
+#define ZLES_VERSION_STR "zles-b200 0.1.0 (sm_100a)"
+
+static thread_local std::string g_cuda_err;
+
+static int cuda_fail(zrt_err_t e, const char *what) {
+  g_cuda_err = std::string(what) + ": " + zrt_err_str(e);
+  return ZLES_E_CUDA;
+}
+#define CK(expr)                                          \
+  do {                                                    \
+    zrt_err_t e_ = (expr);                                \
+    if (e_ != ZRT_OK) return cuda_fail(e_, #expr);        \
+  } while (0)
+#define RET(expr)            \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_) return rc_;     \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) zrt_free(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    zrt_err_t e = zrt_malloc(&p, want);
+    if (e != ZRT_OK) {
+      p = nullptr;
+      e = zrt_malloc(&p, bytes);
+      if (e != ZRT_OK) { p = nullptr; zrt_last_error(); return cuda_fail(e, "device allocation"); }
+      want = bytes;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) zrt_free(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// small pinned block for results read back from the device
+struct HostMail {
+  u64 summary[4];       // deflate: total bytes, adler a, adler b
+  u32 ok;               // batch calls: largest per-buffer status
+  u32 ncand;
+  unsigned long long total;
+  u32 adler;
+  u8 head[8];           // zlib header / trailer staging
+  InfRes res0;
+};
+
+}  // namespace
+
+struct zles_ctx {
+  int device = 0;
+  zrt_stream_t stream{};
+  bool own_stream = false;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  // encoder search depth (see zles_ctx_set_level)
+  u32 max_checks = 48, min_checks = 8, good_len = 16, lazy = 1;
+  // deflate workspace
+  DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_bitoff, chunk_off, summary;
+  // inflate workspace
+  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off;
+  // adler / misc
+  DevBuf acc;
+  // staging for the host forms
+  DevBuf d_in, d_out, d_off_in, d_off_out, d_len, d_status;
+  HostMail *mail = nullptr;  // pinned
+  CorpusTable *d_corpus = nullptr;
+  // state between phase 1 and phase 2 of a deflate
+  bool p1_valid = false;
+  u64 p1_n = 0;
+  u32 p1_nblocks = 0, p1_nchunks = 0;
+  int p1_final = 0;
+  u64 p1_comp = 0;
+};
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                        \
+  do {                                                                   \
+    ZLES_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);    \
+    (ctx)->launches++;                                                   \
+  } while (0)
+
+// ---- library / context ----------------------------------------------------------------
+
+extern "C" const char *zles_version(void) { return ZLES_VERSION_STR; }
+
+extern "C" const char *zles_strerror(int code) {
+  switch (code) {
+    case ZLES_OK: return "";
+    case ZLES_E_NOT_DEFLATE: return "Not compressed by deflate";      // src/zlib.ts:15
+    case ZLES_E_BTYPE3: return "Not supported BTYPE : 3";             // src/inflate.ts:32
+    case ZLES_E_INSUFFICIENT: return "Data length is insufficient";   // src/inflate.ts:35
+    case ZLES_E_CORRUPTED: return "Data is corrupted";                // src/inflate.ts:50,88,166,247,276
+    case ZLES_E_LACK: return "Lack of data length";                   // src/utils/BitReadStream.ts:15
+    case ZLES_E_OUTPUT_FULL: return "output buffer too small";
+    case ZLES_E_CUDA: return "CUDA error";
+    case ZLES_E_ARG: return "invalid argument";
+    case ZLES_E_NOMEM: return "out of memory";
+  }
+  return "unknown error";
+}
+
+extern "C" const char *zles_last_cuda_error(void) { return g_cuda_err.c_str(); }
+
+
+static int set_kernel_attrs(int device) {
+  // opt in to > 48 KiB dynamic shared memory where needed
+  zrt_err_t e = zrt_set_smem(k_lz, (int)LZ_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_lz)");
+  e = zrt_set_smem(k_huff, HUF_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff)");
+  e = zrt_set_smem(k_inflate, INF_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
+  e = zrt_set_smem(k_inflate_batch, INF_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate_batch)");
+  (void)device;
+  return 0;
+}
+
+extern "C" int zles_ctx_create(int device, zles_ctx **out) {
+  if (!out || device < 0) return ZLES_E_ARG;
+  *out = nullptr;
+  CK(zrt_set_device(device));
+  zles_ctx *c = new (std::nothrow) zles_ctx();
+  if (!c) return ZLES_E_NOMEM;
+  c->device = device;
+  zrt_err_t e = zrt_stream_create(&c->stream);
+  if (e != ZRT_OK) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+  c->own_stream = true;
+  c->sm_count = zrt_sm_count(device);
+  void *m = nullptr;
+  e = zrt_host_alloc(&m, sizeof(HostMail));
+  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
+  c->mail = reinterpret_cast<HostMail *>(m);
+  memset(c->mail, 0, sizeof(HostMail));
+  int rc = set_kernel_attrs(device);
+  if (rc) { zles_ctx_destroy(c); return rc; }
+  *out = c;
+  return 0;
+}
+
+extern "C" void zles_ctx_destroy(zles_ctx *c) {
+  if (!c) return;
+  zrt_set_device(c->device);
+  zrt_sync(c->stream);
+  DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_bitoff,
+                    &c->chunk_off, &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off,
+                    &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
+  for (DevBuf *b : bufs) b->release();
+  if (c->d_corpus) zrt_free(c->d_corpus);
+  if (c->mail) zrt_host_free(c->mail);
+  if (c->own_stream) zrt_stream_destroy(c->stream);
+  delete c;
+}
+
+extern "C" int zles_ctx_set_stream(zles_ctx *c, void *cuda_stream) {
+  if (!c) return ZLES_E_ARG;
+  CK(zrt_sync(c->stream));
+  if (c->own_stream) zrt_stream_destroy(c->stream);
+  c->stream = (zrt_stream_t)cuda_stream;
+  c->own_stream = false;
+  return 0;
+}
+
+extern "C" int zles_ctx_set_level(zles_ctx *c, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy) {
+  if (!c || max_checks == 0) return ZLES_E_ARG;
+  c->max_checks = max_checks;
+  c->min_checks = min_checks ? min_checks : 1;
+  c->good_len = good_len;
+  c->lazy = lazy ? 1 : 0;
+  return 0;
+}
+
+extern "C" uint64_t zles_ctx_launches(const zles_ctx *c) { return c ? c->launches : 0; }
+
+static std::mutex g_default_mu;
+static zles_ctx *g_default_ctx = nullptr;
+
+static int resolve_ctx(zles_ctx *&c) {
+  if (c) {
+    CK(zrt_set_device(c->device));
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(g_default_mu);
+  if (!g_default_ctx) RET(zles_ctx_create(0, &g_default_ctx));
+  c = g_default_ctx;
+  CK(zrt_set_device(c->device));
+  return 0;
+}
+
+extern "C" void zles_free(void *p) { free(p); }
+
+// ---- Adler-32 (K8) -----------------------------------------------------------------------
+
+static int dev_adler32(zles_ctx *c, const u8 *d_in, size_t n, uint32_t *adler) {
+  RET(c->acc.reserve(64));
+  unsigned long long *acc = c->acc.as<unsigned long long>();
+  CK(zrt_memset(acc, 0, 16, c->stream));
+  if (n) {
+    u64 nvec = (n >> 4) + 1;
+    u64 want = (nvec + ADLER_THREADS * 4 - 1) / (ADLER_THREADS * 4);
+    u32 grid = (u32)umin64(want, (u64)c->sm_count * 8);
+    if (grid == 0) grid = 1;
+    LAUNCH(c, k_adler_partial, grid, ADLER_THREADS, ADLER_SMEM, d_in, (u64)n, acc);
+  }
+  LAUNCH(c, k_adler_final, 1, 32, 0, acc, (u64)n, reinterpret_cast<u32 *>(acc + 2));
+  CK(zrt_last_error());
+  CK(zrt_d2h(&c->mail->adler, acc + 2, 4, c->stream));
+  CK(zrt_sync(c->stream));
+  *adler = c->mail->adler;
+  return 0;
+}
+
+extern "C" int zles_dev_adler32(zles_ctx *c, const uint8_t *d_in, size_t n, uint32_t *adler) {
+  if (!adler || (!d_in && n)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  return dev_adler32(c, d_in, n, adler);
+}
+
+extern "C" int zles_adler32(zles_ctx *c, const uint8_t *in, size_t n, uint32_t *adler) {
+  if (!adler || (!in && n)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  RET(c->d_in.reserve(n + 16));
+  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  return dev_adler32(c, c->d_in.as<u8>(), n, adler);
+}
+
+// ---- deflate (K1..K5) --------------------------------------------------------------------
+
+extern "C" size_t zles_deflate_bound(size_t n) {
+  // every 32 KiB block: <= 3 + 14 + 19*3 + 316*7 header bits and <= 9 bits per literal
+  // (length-limited codes never beat a flat code by less); every 128 KiB chunk: 5 marker bytes.
+  size_t nblocks = (n + SUB - 1) / SUB;
+  if (nblocks == 0) nblocks = 1;
+  size_t nchunks = (nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+  return 6 + n + (n >> 3) + nblocks * 320 + nchunks * 8 + 64;
+}
+
+static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info) {
+  c->p1_valid = false;
+  if (!is_last && (n == 0 || (n % CHUNK) != 0)) return ZLES_E_ARG;
+  u64 nb64 = ((u64)n + SUB - 1) / SUB;
+  if (nb64 == 0) nb64 = 1;
+  if (nb64 > 0x7fffffffull / LZ_NSYM) return ZLES_E_ARG;
+  const u32 nblocks = (u32)nb64;
+  const u32 nchunks = (nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+  const u32 grid_lz = (u32)umin64((u64)nblocks, (u64)c->sm_count);
+
+  RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
+  RET(c->ntok.reserve((size_t)nblocks * 4));
+  RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
+  RET(c->scratch.reserve((size_t)grid_lz * SUB * 4));
+  RET(c->adler_part.reserve((size_t)nblocks * 16));
+  RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
+  RET(c->blk_bits.reserve((size_t)nblocks * 4));
+  RET(c->blk_bitoff.reserve((size_t)nblocks * 4));
+  RET(c->chunk_off.reserve(((size_t)nchunks + 1) * 8));
+  RET(c->summary.reserve(64));
+
+  LzParams lp;
+  lp.in = d_in;
+  lp.n = n;
+  lp.nblocks = nblocks;
+  lp.tokens = c->tokens.as<u32>();
+  lp.ntok = c->ntok.as<u32>();
+  lp.hist = c->hist.as<u32>();
+  lp.scratch = c->scratch.as<u32>();
+  lp.adler_part = c->adler_part.as<u64>();
+  lp.max_checks = c->max_checks;
+  lp.min_checks = c->min_checks;
+  lp.good_len = c->good_len;
+  lp.lazy = c->lazy;
+  LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
+
+  LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), nblocks,
+         c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+
+  LayoutParams yp;
+  yp.blk_bits = c->blk_bits.as<u32>();
+  yp.nblocks = nblocks;
+  yp.nchunks = nchunks;
+  yp.last_is_final = is_last ? 1u : 0u;
+  yp.n = n;
+  yp.adler_part = c->adler_part.as<u64>();
+  yp.chunk_off = c->chunk_off.as<u64>();
+  yp.blk_bitoff = c->blk_bitoff.as<u32>();
+  yp.summary = c->summary.as<u64>();
+  LAUNCH(c, k_layout, 1, 1024, LAYOUT_SMEM, yp);
+  CK(zrt_last_error());
+
+  CK(zrt_d2h(c->mail->summary, c->summary.p, 24, c->stream));
+  CK(zrt_sync(c->stream));
+  c->p1_valid = true;
+  c->p1_n = n;
+  c->p1_nblocks = nblocks;
+  c->p1_nchunks = nchunks;
+  c->p1_final = is_last;
+  c->p1_comp = c->mail->summary[0];
+  if (info) {
+    info->comp_bytes = c->mail->summary[0];
+    info->raw_bytes = n;
+    info->adler_a = c->mail->summary[1];
+    info->adler_b = c->mail->summary[2];
+    info->n_chunks = nchunks;
+  }
+  return 0;
+}
+
+static int deflate_phase2(zles_ctx *c, u8 *d_dst) {
+  if (!c->p1_valid) return ZLES_E_ARG;
+  PackParams pp;
+  pp.tokens = c->tokens.as<u32>();
+  pp.ntok = c->ntok.as<u32>();
+  pp.codes = c->codes.as<BlockCodes>();
+  pp.blk_bits = c->blk_bits.as<u32>();
+  pp.chunk_off = c->chunk_off.as<u64>();
+  pp.nblocks = c->p1_nblocks;
+  pp.nchunks = c->p1_nchunks;
+  pp.last_is_final = c->p1_final ? 1u : 0u;
+  pp.out = d_dst;
+  LAUNCH(c, k_pack, c->p1_nchunks, PACK_THREADS, PACK_SMEM, pp);
+  CK(zrt_last_error());
+  return 0;
+}
+
+extern "C" uint32_t zles_adler32_combine_shards(const zles_shard_info *infos, uint32_t count) {
+  // stream d[0..N) = shard 0 | shard 1 | ...; shard s at offset o_s of length m_s with
+  // A_s = sum d, B_s = sum (m_s - j) d[j]:  s1 = 1 + sum A_s,  s2 = N + sum (B_s + (N - o_s - m_s) A_s)
+  u64 N = 0;
+  for (uint32_t i = 0; i < count; i++) N += infos[i].raw_bytes;
+  u64 s1 = 1, s2 = N % ADLER_MOD, o = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    const u64 A = infos[i].adler_a % ADLER_MOD, B = infos[i].adler_b % ADLER_MOD;
+    const u64 after = (N - o - infos[i].raw_bytes) % ADLER_MOD;
+    s1 = (s1 + A) % ADLER_MOD;
+    s2 = (s2 + B + after * A) % ADLER_MOD;
+    o += infos[i].raw_bytes;
+  }
+  return (uint32_t)((s2 << 16) | s1);
+}
+
+static void put_zlib_header(u8 *p) {
+  // CMF: CM = 8, CINFO = 7; FLG: FCHECK = 28, FDICT = 0, FLEVEL = 2  (src/zlib.ts:28-34) -> 78 9C
+  p[0] = 0x78;
+  p[1] = 0x9C;
+}
+static void put_be32(u8 *p, u32 v) {  // src/zlib.ts:37-40
+  p[0] = (u8)(v >> 24);
+  p[1] = (u8)(v >> 16);
+  p[2] = (u8)(v >> 8);
+  p[3] = (u8)v;
+}
+
+extern "C" int zles_dev_deflate_phase1(zles_ctx *c, const uint8_t *d_in, size_t n, int is_last_shard, zles_shard_info *info) {
+  if (!d_in && n) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  return deflate_phase1(c, d_in, n, is_last_shard, info);
+}
+extern "C" int zles_dev_deflate_chunk_offsets(zles_ctx *c, const uint64_t **d_offsets) {
+  if (!c || !d_offsets || !c->p1_valid) return ZLES_E_ARG;
+  *d_offsets = c->chunk_off.as<u64>();
+  return 0;
+}
+extern "C" int zles_dev_deflate_phase2(zles_ctx *c, uint8_t *d_dst) {
+  if (!c || !d_dst) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  RET(deflate_phase2(c, d_dst));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
+
+extern "C" int zles_dev_deflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t cap, size_t *out_len) {
+  if ((!d_in && n) || !out_len) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  zles_shard_info info;
+  RET(deflate_phase1(c, d_in, n, 1, &info));
+  const size_t need = (size_t)info.comp_bytes + 6;
+  *out_len = need;
+  if (!d_out || cap < need) return ZLES_E_OUTPUT_FULL;
+  RET(deflate_phase2(c, d_out + 2));
+  put_zlib_header(c->mail->head);
+  put_be32(c->mail->head + 2, zles_adler32_combine_shards(&info, 1));
+  CK(zrt_h2d(d_out, c->mail->head, 2, c->stream));
+  CK(zrt_h2d(d_out + need - 4, c->mail->head + 2, 4, c->stream));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
+
+extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  RET(c->d_in.reserve(n + 16));
+  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  zles_shard_info info;
+  RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info));
+  const size_t need = (size_t)info.comp_bytes + 6;
+  *out_len = need;
+  if (!out || cap < need) return ZLES_E_OUTPUT_FULL;
+  RET(c->d_out.reserve(need + 16));
+  RET(deflate_phase2(c, c->d_out.as<u8>() + 2));
+  CK(zrt_d2h(out + 2, c->d_out.as<u8>() + 2, info.comp_bytes, c->stream));
+  put_zlib_header(out);
+  put_be32(out + need - 4, zles_adler32_combine_shards(&info, 1));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
+
+// ---- inflate (K6/K7) ---------------------------------------------------------------------
+
+static int seg_status_to_code(u32 st) {
+  switch (st) {
+    case SEG_E_BTYPE3: return ZLES_E_BTYPE3;
+    case SEG_E_INSUFF: return ZLES_E_INSUFFICIENT;
+    case SEG_E_CORRUPT: return ZLES_E_CORRUPTED;
+    case SEG_E_LACK: return ZLES_E_LACK;
+  }
+  return ZLES_E_CORRUPTED;
+}
+
+// control block in device memory
+struct InfCtl {
+  u32 ncand;
+  u32 counter;
+  u32 ok;
+  u32 pad;
+  unsigned long long total;
+};
+
+static u32 inflate_grid(const zles_ctx *c, u64 nseg) {
+  u64 want = (nseg + INF_WARPS - 1) / INF_WARPS;
+  u64 cap = (u64)c->sm_count * 16;
+  if (want < 1) want = 1;
+  return (u32)(want < cap ? want : cap);
+}
+
+// Decodes the raw deflate data that starts at byte `first` of d_in[0..n).  On success *out_len = decoded size.
+// ZLES_E_OUTPUT_FULL: *out_len = size needed.
+static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
+  // 1. candidate segment starts: `first` and every position that follows a 00 00 FF FF marker
+  const u64 nvec = ((u64)n + 15) >> 4;
+  const u32 ntiles = (u32)((nvec + MARK_THREADS - 1) / MARK_THREADS);
+  RET(c->ctl.reserve(sizeof(InfCtl)));
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  RET(c->tile_cnt.reserve(((size_t)ntiles + 1) * 4));
+  // Our own streams have one marker per 128 KiB of input (>= ~100 B of stream even for zeros).  Streams
+  // with more candidates than n / 64 are somebody else's and take the sequential path below.
+  const u64 cand_cap64 = (u64)n / 64 + 64;
+  if (cand_cap64 > 0x7fffffffull) return ZLES_E_ARG;
+  const u32 cand_cap = (u32)cand_cap64;
+  RET(c->cand.reserve((size_t)cand_cap * 8));
+  RET(c->res.reserve((size_t)cand_cap * sizeof(InfRes)));
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  u32 *d_ncand = &ctl->ncand;
+  if (ntiles) {
+    LAUNCH(c, k_mark_count, ntiles, MARK_THREADS, 64 * 4, d_in, (u64)n, first, c->tile_cnt.as<u32>());
+    LAUNCH(c, k_mark_scan, 1, 1024, 64 * 4, c->tile_cnt.as<u32>(), ntiles, d_ncand);
+    LAUNCH(c, k_mark_emit, ntiles, MARK_THREADS, 64 * 4, d_in, (u64)n, first, (const u32 *)c->tile_cnt.as<u32>(), c->cand.as<u64>(),
+           cand_cap);
+  } else {
+    LAUNCH(c, k_mark_none, 1, 32, 0, first, c->cand.as<u64>(), d_ncand);
+  }
+  // 2. optimistic parallel decode: segment j writes at j * CHUNK
+  const u64 guess_seg = (u64)n / 2048 + 1;  // launch width only; the kernel reads the real count
+  LAUNCH(c, k_inflate, inflate_grid(c, guess_seg), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(),
+         (const u64 *)nullptr, (const u32 *)d_ncand, cand_cap, d_out, (u64)cap, 1, c->res.as<InfRes>(), &ctl->counter);
+  LAUNCH(c, k_inf_check, (cand_cap + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(),
+         (const u32 *)d_ncand, cand_cap, &ctl->ok, &ctl->total);
+  CK(zrt_last_error());
+  InfCtl h;
+  CK(zrt_d2h(&c->mail->summary[0], ctl, sizeof(InfCtl), c->stream));
+  CK(zrt_sync(c->stream));
+  memcpy(&h, &c->mail->summary[0], sizeof(InfCtl));
+  if (h.ok == 0) {  // InfCtl::ok collects problem bits (k_inf_check)
+    *out_len = (size_t)h.total;
+    return 0;
+  }
+  if (h.ok == 2) {  // everything consistent, only the output did not fit
+    *out_len = (size_t)h.total;
+    return ZLES_E_OUTPUT_FULL;
+  }
+
+  // 3. the optimistic layout was wrong (false marker, foreign stream, error).  Walk the chain of
+  //    segments on the host: segment 0 is real; the segment after it starts where it ended.
+  const u32 ncand = h.ncand < cand_cap ? h.ncand : cand_cap;
+  bool chain_ok = h.ncand <= cand_cap;
+  std::vector<InfRes> res(ncand);
+  std::vector<u64> cand(ncand);
+  CK(zrt_d2h(res.data(), c->res.p, (size_t)ncand * sizeof(InfRes), c->stream));
+  CK(zrt_d2h(cand.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+  CK(zrt_sync(c->stream));
+  std::vector<u64> pos, off;
+  u64 total = 0;
+  if (chain_ok) {
+    size_t j = 0;
+    for (;;) {
+      const InfRes &r = res[j];
+      if ((r.flags & SEGF_HISTORY) && j != 0) { chain_ok = false; break; }
+      if (r.status != SEG_SYNC && r.status != SEG_FINAL) { chain_ok = false; break; }
+      pos.push_back(cand[j]);
+      off.push_back(total);
+      total += r.out_len;
+      if (r.status == SEG_FINAL) break;
+      // next real segment: the candidate equal to this segment's end
+      size_t lo = j + 1, hi = ncand;
+      while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if (cand[mid] < r.end_pos) lo = mid + 1; else hi = mid;
+      }
+      if (lo >= ncand || cand[lo] != r.end_pos) { chain_ok = false; break; }
+      j = lo;
+    }
+  }
+  if (chain_ok) {
+    *out_len = (size_t)total;
+    if (total > cap) return ZLES_E_OUTPUT_FULL;
+    const u32 nseg = (u32)pos.size();
+    RET(c->seg_pos.reserve((size_t)nseg * 8));
+    RET(c->seg_off.reserve((size_t)nseg * 8));
+    CK(zrt_h2d(c->seg_pos.p, pos.data(), (size_t)nseg * 8, c->stream));
+    CK(zrt_h2d(c->seg_off.p, off.data(), (size_t)nseg * 8, c->stream));
+    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+    CK(zrt_h2d(&ctl->ncand, &nseg, 4, c->stream));
+    CK(zrt_sync(c->stream));  // pos/off/nseg are stack or heap memory
+    LAUNCH(c, k_inflate, inflate_grid(c, nseg), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->seg_pos.as<u64>(),
+           (const u64 *)c->seg_off.as<u64>(), (const u32 *)d_ncand, nseg, d_out, (u64)cap, 1, c->res.as<InfRes>(), &ctl->counter);
+    CK(zrt_last_error());
+    CK(zrt_sync(c->stream));
+    return 0;
+  }
+
+  // 4. sequential decode of the whole stream on one warp: exactly the reference's order of
+  //    events (src/inflate.ts:22-37), used for foreign streams and for error reporting.
+  {
+    const u32 one = 1;
+    const u64 zero = 0;
+    RET(c->seg_pos.reserve(8));
+    RET(c->seg_off.reserve(8));
+    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+    CK(zrt_h2d(&ctl->ncand, &one, 4, c->stream));
+    CK(zrt_h2d(c->seg_pos.p, &first, 8, c->stream));
+    CK(zrt_h2d(c->seg_off.p, &zero, 8, c->stream));
+    CK(zrt_sync(c->stream));
+    LAUNCH(c, k_inflate, 1, INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->seg_pos.as<u64>(), (const u64 *)c->seg_off.as<u64>(),
+           (const u32 *)d_ncand, 1u, d_out, (u64)cap, 0, c->res.as<InfRes>(), &ctl->counter);
+    CK(zrt_last_error());
+    CK(zrt_d2h(&c->mail->res0, c->res.p, sizeof(InfRes), c->stream));
+    CK(zrt_sync(c->stream));
+    const InfRes r = c->mail->res0;
+    if (r.status != SEG_FINAL) return seg_status_to_code(r.status);
+    *out_len = (size_t)r.out_len;
+    if (r.flags & SEGF_OVERFLOW) return ZLES_E_OUTPUT_FULL;
+    return 0;
+  }
+}
+
+// header check of zlib.inflate (src/zlib.ts:12-16): only CM is looked at.
+static int check_zlib_header(const u8 *h, size_t n) {
+  const u32 b0 = n ? h[0] : 0;  // reading past the end yields 0 bits
+  if ((b0 & 15) != 8) return ZLES_E_NOT_DEFLATE;
+  return 0;
+}
+
+extern "C" int zles_dev_inflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t cap, size_t *out_len) {
+  if ((!d_in && n) || !out_len || (!d_out && cap)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  c->mail->head[0] = 0;
+  if (n) {
+    CK(zrt_d2h(c->mail->head, d_in, 1, c->stream));
+    CK(zrt_sync(c->stream));
+  }
+  RET(check_zlib_header(c->mail->head, n));
+  return inflate_body(c, d_in, n, 2, d_out, cap, out_len);
+}
+
+extern "C" int zles_dev_inflate_segment(zles_ctx *c, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
+                                        size_t *out_len) {
+  if ((!d_in && n) || !out_len) return ZLES_E_ARG;
+  (void)has_final;
+  RET(resolve_ctx(c));
+  return inflate_body(c, d_in, n, 0, d_out, cap, out_len);
+}
+
+extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
+  RET(check_zlib_header(in, n));
+  RET(resolve_ctx(c));
+  RET(c->d_in.reserve(n + 16));
+  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  RET(c->d_out.reserve(cap + 16));
+  int rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, out_len);
+  if (rc) return rc;
+  if (*out_len) CK(zrt_d2h(out, c->d_out.p, *out_len, c->stream));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
+
+extern "C" int zles_inflate_alloc(zles_ctx *c, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
+  if ((!in && n) || !out || !out_len) return ZLES_E_ARG;
+  *out = nullptr;
+  *out_len = 0;
+  RET(check_zlib_header(in, n));
+  RET(resolve_ctx(c));
+  RET(c->d_in.reserve(n + 16));
+  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  // first guess: the reference's own initial capacity, 10 x input (src/inflate.ts:17); retry once with the exact size
+  size_t cap = n * 10 + CHUNK;
+  size_t need = 0;
+  RET(c->d_out.reserve(cap + 16));
+  int rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, &need);
+  if (rc == ZLES_E_OUTPUT_FULL) {
+    cap = need;
+    RET(c->d_out.reserve(cap + 16));
+    rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, &need);
+  }
+  if (rc) return rc;
+  u8 *buf = (u8 *)malloc(need ? need : 1);
+  if (!buf) return ZLES_E_NOMEM;
+  if (need) {
+    zrt_err_t e = zrt_d2h(buf, c->d_out.p, need, c->stream);
+    if (e == ZRT_OK) e = zrt_sync(c->stream);
+    if (e != ZRT_OK) { free(buf); return cuda_fail(e, "copy to host"); }
+  }
+  *out = buf;
+  *out_len = need;
+  return 0;
+}
+
+// ---- batches of independent buffers --------------------------------------------------------
+
+static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, const u64 *h_in_off, u32 count, u8 *d_out,
+                             const u64 *d_out_off, u64 *d_out_len, int32_t *d_status);
+
+extern "C" int zles_dev_inflate_batch(zles_ctx *c, const uint8_t *d_in, const uint64_t *d_in_off, uint32_t count, uint8_t *d_out,
+                                      const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status) {
+  if (!count) return 0;
+  if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  RET(c->ctl.reserve(sizeof(InfCtl)));
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  LAUNCH(c, k_inflate_batch, inflate_grid(c, count), INF_THREADS, INF_SMEM, d_in, d_in_off, count, d_out, d_out_off, d_out_len, d_status,
+         &ctl->counter, &ctl->ok);
+  CK(zrt_last_error());
+  CK(zrt_d2h(&c->mail->ok, &ctl->ok, 4, c->stream));
+  CK(zrt_sync(c->stream));
+  return (int)c->mail->ok;  // first (lowest) non-zero status, 0 if none
+}
+
+extern "C" int zles_inflate_batch(zles_ctx *c, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
+                                  const uint64_t *out_off, uint64_t *out_len, int32_t *status) {
+  if (!count) return 0;
+  if (!in || !in_off || !out || !out_off || !out_len || !status) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  const size_t nin = in_off[count] - in_off[0], nout = out_off[count] - out_off[0];
+  RET(c->d_in.reserve(nin + 16));
+  RET(c->d_out.reserve(nout + 16));
+  RET(c->d_off_in.reserve(((size_t)count + 1) * 8));
+  RET(c->d_off_out.reserve(((size_t)count + 1) * 8));
+  RET(c->d_len.reserve((size_t)count * 8));
+  RET(c->d_status.reserve((size_t)count * 4));
+  std::vector<u64> oi(count + 1), oo(count + 1);
+  for (u32 i = 0; i <= count; i++) { oi[i] = in_off[i] - in_off[0]; oo[i] = out_off[i] - out_off[0]; }
+  CK(zrt_h2d(c->d_in.p, in + in_off[0], nin, c->stream));
+  CK(zrt_h2d(c->d_off_in.p, oi.data(), ((size_t)count + 1) * 8, c->stream));
+  CK(zrt_h2d(c->d_off_out.p, oo.data(), ((size_t)count + 1) * 8, c->stream));
+  CK(zrt_sync(c->stream));
+  int rc = zles_dev_inflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), count, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
+                                  c->d_len.as<u64>(), c->d_status.as<int32_t>());
+  if (rc == ZLES_E_CUDA || rc == ZLES_E_ARG) return rc;
+  CK(zrt_d2h(out + out_off[0], c->d_out.p, nout, c->stream));
+  CK(zrt_d2h(out_len, c->d_len.p, (size_t)count * 8, c->stream));
+  CK(zrt_d2h(status, c->d_status.p, (size_t)count * 4, c->stream));
+  CK(zrt_sync(c->stream));
+  return rc;
+}
+
+extern "C" int zles_dev_deflate_batch(zles_ctx *c, const uint8_t *d_in, const uint64_t *d_in_off, uint32_t count, uint8_t *d_out,
+                                      const uint64_t *d_out_off, uint64_t *d_out_len, int32_t *d_status) {
+  if (!count) return 0;
+  if (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_status) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  return dev_deflate_batch(c, d_in, d_in_off, nullptr, count, d_out, d_out_off, d_out_len, d_status);
+}
+
+extern "C" int zles_deflate_batch(zles_ctx *c, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
+                                  const uint64_t *out_off, uint64_t *out_len, int32_t *status) {
+  if (!count) return 0;
+  if (!in || !in_off || !out || !out_off || !out_len || !status) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  const size_t nin = in_off[count] - in_off[0], nout = out_off[count] - out_off[0];
+  RET(c->d_in.reserve(nin + 16));
+  RET(c->d_out.reserve(nout + 16));
+  RET(c->d_off_in.reserve(((size_t)count + 1) * 8));
+  RET(c->d_off_out.reserve(((size_t)count + 1) * 8));
+  RET(c->d_len.reserve((size_t)count * 8));
+  RET(c->d_status.reserve((size_t)count * 4));
+  std::vector<u64> oi(count + 1), oo(count + 1);
+  for (u32 i = 0; i <= count; i++) { oi[i] = in_off[i] - in_off[0]; oo[i] = out_off[i] - out_off[0]; }
+  if (nin) CK(zrt_h2d(c->d_in.p, in + in_off[0], nin, c->stream));
+  CK(zrt_h2d(c->d_off_in.p, oi.data(), ((size_t)count + 1) * 8, c->stream));
+  CK(zrt_h2d(c->d_off_out.p, oo.data(), ((size_t)count + 1) * 8, c->stream));
+  CK(zrt_sync(c->stream));
+  int rc = dev_deflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), oi.data(), count, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
+                             c->d_len.as<u64>(), c->d_status.as<int32_t>());
+  if (rc == ZLES_E_CUDA || rc == ZLES_E_ARG) return rc;
+  CK(zrt_d2h(out + out_off[0], c->d_out.p, nout, c->stream));
+  CK(zrt_d2h(out_len, c->d_len.p, (size_t)count * 8, c->stream));
+  CK(zrt_d2h(status, c->d_status.p, (size_t)count * 4, c->stream));
+  CK(zrt_sync(c->stream));
+  return rc;
+}
+
+// Batch deflate: every buffer is its own zlib stream (header, blocks, Adler-32 trailer all
+// written on the device so that one launch sequence serves the whole batch).
+static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, const u64 *h_in_off, u32 count, u8 *d_out,
+                             const u64 *d_out_off, u64 *d_out_len, int32_t *d_status) {
+  (void)h_in_off;
+  RET(c->ctl.reserve(sizeof(InfCtl)));
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  // per-buffer block counts -> block table
+  RET(c->seg_pos.reserve(((size_t)count + 1) * 8));
+  u64 *d_blk_first = c->seg_pos.as<u64>();  // [count + 1] first block index of each buffer
+  LAUNCH(c, k_batch_count, 1, 1024, 64 * 4, d_in_off, count, d_blk_first);
+  CK(zrt_last_error());
+  CK(zrt_d2h(&c->mail->total, d_blk_first + count, 8, c->stream));
+  CK(zrt_sync(c->stream));
+  const u64 nb64 = c->mail->total;
+  if (nb64 > 0x7fffffffull / LZ_NSYM) return ZLES_E_ARG;
+  const u32 nblocks = (u32)nb64;
+  const u32 grid_lz = (u32)umin64((u64)nblocks, (u64)c->sm_count);
+  RET(c->seg_off.reserve((size_t)nblocks * sizeof(BatchBlk)));
+  BatchBlk *d_tab = c->seg_off.as<BatchBlk>();
+  RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
+  RET(c->ntok.reserve((size_t)nblocks * 4));
+  RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
+  RET(c->scratch.reserve((size_t)grid_lz * SUB * 4));
+  RET(c->adler_part.reserve((size_t)nblocks * 16));
+  RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
+  RET(c->blk_bits.reserve((size_t)nblocks * 4));
+  c->p1_valid = false;
+  LAUNCH(c, k_batch_table, (count + 255) / 256, 256, 0, d_in_off, count, (const u64 *)d_blk_first, d_tab);
+
+  LzParams lp;
+  lp.in = d_in;
+  lp.n = 0;
+  lp.nblocks = nblocks;
+  lp.tokens = c->tokens.as<u32>();
+  lp.ntok = c->ntok.as<u32>();
+  lp.hist = c->hist.as<u32>();
+  lp.scratch = c->scratch.as<u32>();
+  lp.adler_part = c->adler_part.as<u64>();
+  lp.max_checks = c->max_checks;
+  lp.min_checks = c->min_checks;
+  lp.good_len = c->good_len;
+  lp.lazy = c->lazy;
+  lp.table = d_tab;
+  LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
+  LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), nblocks,
+         c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+  BatchPackParams bp;
+  bp.tokens = c->tokens.as<u32>();
+  bp.ntok = c->ntok.as<u32>();
+  bp.codes = c->codes.as<BlockCodes>();
+  bp.blk_bits = c->blk_bits.as<u32>();
+  bp.adler_part = c->adler_part.as<u64>();
+  bp.table = d_tab;
+  bp.blk_first = d_blk_first;
+  bp.in_off = d_in_off;
+  bp.out_off = d_out_off;
+  bp.count = count;
+  bp.out = d_out;
+  bp.out_len = d_out_len;
+  bp.status = d_status;
+  bp.first_err = &ctl->ok;
+  LAUNCH(c, k_pack_batch, count, PACK_THREADS, PACK_SMEM, bp);
+  CK(zrt_last_error());
+  CK(zrt_d2h(&c->mail->ok, &ctl->ok, 4, c->stream));
+  CK(zrt_sync(c->stream));
+  return (int)c->mail->ok;
+}
+
+// ---- CUDA IPC (peer-mapped destination of the sharded deflate) ----------------------------------
+
+extern "C" int zles_ipc_export(const void *d_ptr, uint8_t handle[64]) {
+#ifdef ZLES_EMU
+  (void)d_ptr; (void)handle;
+  return ZLES_E_CUDA;
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!d_ptr || !handle) return ZLES_E_ARG;
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+  memcpy(handle, &h, 64);
+  return 0;
+#endif
+}
+extern "C" int zles_ipc_open(const uint8_t handle[64], void **d_ptr) {
+#ifdef ZLES_EMU
+  (void)handle; (void)d_ptr;
+  return ZLES_E_CUDA;
+#else
+  if (!d_ptr || !handle) return ZLES_E_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+#endif
+}
+extern "C" int zles_ipc_close(void *d_ptr) {
+#ifdef ZLES_EMU
+  (void)d_ptr;
+  return ZLES_E_CUDA;
+#else
+  if (!d_ptr) return ZLES_E_ARG;
+  CK(cudaIpcCloseMemHandle(d_ptr));
+  return 0;
+#endif
+}
+
+// ---- synthetic corpora ------------------------------------------------------------------------
+
+static std::once_flag g_corpus_once;
+static CorpusTable *g_corpus_host = nullptr;
+
+static int corpus_sym_of(int ch) {
+  if (ch >= 'a' && ch <= 'z') return ch - 'a';
+  if (ch >= 'A' && ch <= 'Z') return 26 + ch - 'A';
+  switch (ch) {
+    case ' ': return 52;
+    case ',': return 53;
+    case '.': return 54;
+    case ';': return 55;
+    case '\'': return 56;
+    case '-': return 57;
+    case '\n': return 58;
+  }
+  return -1;
+}
+
+static void corpus_build_host() {
+  CorpusTable *T = new CorpusTable();
+  static const char alpha[] = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ ,.;'-\n";
+  memset(T->alphabet, ' ', sizeof(T->alphabet));
+  for (u32 i = 0; i < CORPUS_NSYM; i++) T->alphabet[i] = (u8)alpha[i];
+  std::vector<u32> c2((size_t)CORPUS_NSYM * CORPUS_NSYM * CORPUS_NSYM, 0), c1((size_t)CORPUS_NSYM * CORPUS_NSYM, 0), c0(CORPUS_NSYM, 0);
+  int s1 = 4, s2 = 52;
+  for (const char *p = ZLES_CORPUS_PROSE; *p; p++) {
+    int s = corpus_sym_of((unsigned char)*p);
+    if (s < 0) continue;
+    c2[((size_t)s1 * CORPUS_NSYM + s2) * CORPUS_NSYM + s]++;
+    c1[(size_t)s2 * CORPUS_NSYM + s]++;
+    c0[s]++;
+    s1 = s2;
+    s2 = s;
+  }
+  for (u32 st = 0; st < CORPUS_NSYM * CORPUS_NSYM; st++) {
+    const u32 *cnt = &c2[(size_t)st * CORPUS_NSYM];
+    u64 tot = 0;
+    for (u32 k = 0; k < CORPUS_NSYM; k++) tot += cnt[k];
+    if (tot == 0) {  // unseen pair: back off to the order-1, then the order-0 statistics
+      cnt = &c1[(size_t)(st % CORPUS_NSYM) * CORPUS_NSYM];
+      for (u32 k = 0; k < CORPUS_NSYM; k++) tot += cnt[k];
+      if (tot == 0) {
+        cnt = c0.data();
+        for (u32 k = 0; k < CORPUS_NSYM; k++) tot += cnt[k];
+      }
+    }
+    u64 cum = 0;
+    for (u32 k = 0; k < 64; k++) {
+      if (k < CORPUS_NSYM) cum += cnt[k];
+      u64 v = tot ? (cum * 65536ull) / tot : 65535;
+      T->cdf[st][k] = (u16)(v > 65535 ? 65535 : v);
+    }
+  }
+  g_corpus_host = T;
+}
+
+static const CorpusTable *corpus_host_table() {
+  std::call_once(g_corpus_once, corpus_build_host);
+  return g_corpus_host;
+}
+
+extern "C" int zles_host_corpus(int kind, uint64_t offset, uint8_t *out, size_t n) {
+  if (kind < 0 || kind > 3 || (!out && n)) return ZLES_E_ARG;
+  const CorpusTable *T = corpus_host_table();
+  if (!n) return 0;
+  const u64 p0 = offset / CORPUS_PAGE, p1 = (offset + n + CORPUS_PAGE - 1) / CORPUS_PAGE;
+  for (u64 p = p0; p < p1; p++) corpus_page(T, kind, p, offset, offset + n, out);
+  return 0;
+}
+
+extern "C" int zles_dev_corpus(zles_ctx *c, int kind, uint64_t offset, uint8_t *d_out, size_t n) {
+  if (kind < 0 || kind > 3 || (!d_out && n)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  if (!c->d_corpus) {
+    void *p = nullptr;
+    CK(zrt_malloc(&p, sizeof(CorpusTable)));
+    c->d_corpus = reinterpret_cast<CorpusTable *>(p);
+    CK(zrt_h2d(c->d_corpus, corpus_host_table(), sizeof(CorpusTable), c->stream));
+    CK(zrt_sync(c->stream));
+  }
+  if (!n) return 0;
+  const u64 p0 = offset / CORPUS_PAGE, p1 = (offset + n + CORPUS_PAGE - 1) / CORPUS_PAGE;
+  const u32 grid = (u32)((p1 - p0 + 31) / 32);
+  LAUNCH(c, k_corpus, grid, 32, 0, (const CorpusTable *)c->d_corpus, kind, (u64)offset, d_out, (u64)n);
+  CK(zrt_last_error());
+  CK(zrt_sync(c->stream));
+  return 0;
+}

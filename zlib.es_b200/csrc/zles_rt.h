@@ -1,0 +1,65 @@
+// zles_rt.h — host-side runtime shim: CUDA runtime in the product build, libc in the
+// emulator build used by the tests (tests/emu).  Keeps zles.cu free of #ifdefs.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef ZLES_EMU
+#include "cuda_emu.h"
+typedef void *zrt_stream_t;
+typedef int zrt_err_t;
+#define ZRT_OK 0
+static inline zrt_err_t zrt_set_device(int) { return 0; }
+static inline zrt_err_t zrt_stream_create(zrt_stream_t *s) { *s = nullptr; return 0; }
+static inline zrt_err_t zrt_stream_destroy(zrt_stream_t) { return 0; }
+static inline zrt_err_t zrt_malloc(void **p, size_t n) {
+  n = (n + 255) & ~(size_t)255;
+  *p = aligned_alloc(256, n ? n : 256);
+  if (*p) memset(*p, 0xA5, n ? n : 256);  // device memory starts undefined
+  return *p ? 0 : 2;
+}
+static inline zrt_err_t zrt_free(void *p) { free(p); return 0; }
+static inline zrt_err_t zrt_host_alloc(void **p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
+static inline zrt_err_t zrt_host_free(void *p) { free(p); return 0; }
+static inline zrt_err_t zrt_h2d(void *d, const void *s, size_t n, zrt_stream_t) { memcpy(d, s, n); return 0; }
+static inline zrt_err_t zrt_d2h(void *d, const void *s, size_t n, zrt_stream_t) { memcpy(d, s, n); return 0; }
+static inline zrt_err_t zrt_memset(void *d, int v, size_t n, zrt_stream_t) { memset(d, v, n); return 0; }
+static inline zrt_err_t zrt_sync(zrt_stream_t) { return 0; }
+static inline zrt_err_t zrt_last_error() { return 0; }
+static inline const char *zrt_err_str(zrt_err_t) { return "emulator"; }
+template <typename K>
+static inline zrt_err_t zrt_set_smem(K, int) { return 0; }
+static inline int zrt_sm_count(int) { return 4; }
+#define ZLES_LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+typedef cudaStream_t zrt_stream_t;
+typedef cudaError_t zrt_err_t;
+#define ZRT_OK cudaSuccess
+static inline zrt_err_t zrt_set_device(int d) { return cudaSetDevice(d); }
+static inline zrt_err_t zrt_stream_create(zrt_stream_t *s) { return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking); }
+static inline zrt_err_t zrt_stream_destroy(zrt_stream_t s) { return cudaStreamDestroy(s); }
+static inline zrt_err_t zrt_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 256); }
+static inline zrt_err_t zrt_free(void *p) { return cudaFree(p); }
+static inline zrt_err_t zrt_host_alloc(void **p, size_t n) { return cudaMallocHost(p, n ? n : 1); }
+static inline zrt_err_t zrt_host_free(void *p) { return cudaFreeHost(p); }
+static inline zrt_err_t zrt_h2d(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st); }
+static inline zrt_err_t zrt_d2h(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st); }
+static inline zrt_err_t zrt_memset(void *d, int v, size_t n, zrt_stream_t st) { return cudaMemsetAsync(d, v, n, st); }
+static inline zrt_err_t zrt_sync(zrt_stream_t st) { return cudaStreamSynchronize(st); }
+static inline zrt_err_t zrt_last_error() { return cudaGetLastError(); }
+static inline const char *zrt_err_str(zrt_err_t e) { return cudaGetErrorString(e); }
+template <typename K>
+static inline zrt_err_t zrt_set_smem(K kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+static inline int zrt_sm_count(int dev) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  return n;
+}
+#define ZLES_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#endif

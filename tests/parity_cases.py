@@ -1,0 +1,97 @@
+"""Parity cases shared by the GPU tests (tests/test_gpu_*.py, through libzles.so on a B200)
+and the emulator tests (tests/test_emu_*.py, same sources on the CPU thread emulator,
+small sizes only).  Every function takes a ``zles.Codec``.
+
+They restate /root/reference/test/index.js in pytest form: the 4 inflate known-answer
+vectors, and round trips of deflate output through (a) our inflate, (b) the oracle's
+restatement of the reference's inflate and (c) system zlib (the stand-in for Node's
+zlib.inflateSync, test/index.js:68,83,105), plus the size bound against the oracle.
+"""
+import zlib
+
+import oracle as O
+import vectors as T
+
+SIZE_SLACK = 1.03  # BASELINE.json north_star: compressed size within 3 % of the reference's
+
+
+def inflate_kats(c):
+    for name in ("UNCOMPRESSED", "FIXED", "DYNAMIC"):  # test/index.js:15-35
+        assert c.inflate(getattr(T, name)) == T.RAW, name
+
+
+def inflate_fixture(c):  # test/index.js:37-42
+    assert c.inflate(T.fixture_compressed()) == T.fixture_raw()
+
+
+def adler_kats(c):
+    assert c.adler32(T.RAW) == 0x2B23056C
+    assert c.adler32(b"") == 1
+    assert c.adler32(b"\x00") == O.adler32(b"\x00")
+
+
+def roundtrip(c, data: bytes, check_size: bool = True, oracle_decode: bool = True):
+    """deflate(data) decodes to data under all three decoders; size <= 1.03 x oracle's."""
+    z = c.deflate(data)
+    assert z[:2] == b"\x78\x9c"  # src/zlib.ts:28-34
+    assert int.from_bytes(z[-4:], "big") == zlib.adler32(data)  # src/zlib.ts:36-40
+    assert zlib.decompress(z) == data  # Node's inflateSync stand-in (verifies the trailer too)
+    if oracle_decode:
+        assert O.inflate(z) == data
+    assert c.inflate(z) == data
+    if check_size:
+        try:
+            ref = O.deflate(data)
+        except O.OracleError:
+            ref = None  # the reference throws on this length; nothing to compare
+        if ref is not None:
+            assert len(z) <= SIZE_SLACK * len(ref) + 8, (len(z), len(ref))
+    return z
+
+
+def inflate_matches_oracle(c, stream: bytes):
+    """Same bytes or the same error as the reference's inflate."""
+    try:
+        want = O.inflate(stream)
+    except O.OracleError as e:
+        want = e
+    try:
+        got = c.inflate(stream)
+    except Exception as e:  # ZlesError
+        got = e
+    if isinstance(want, Exception):
+        assert isinstance(got, Exception), "reference throws %r, we returned %d bytes" % (str(want), len(got))
+        assert str(got) == str(want)
+    else:
+        assert not isinstance(got, Exception), "we raise %r, reference returns %d bytes" % (str(got), len(want))
+        assert got == want
+
+
+def lenient_like_reference(c):
+    # src/zlib.ts:22 — the Adler-32 trailer is never read
+    z = bytearray(zlib.compress(b"hello hello hello hello"))
+    z[-1] ^= 0xFF
+    assert c.inflate(bytes(z)) == b"hello hello hello hello"
+    # trailer absent / trailing garbage
+    z = zlib.compress(b"hello hello hello hello")
+    assert c.inflate(z[:-4]) == b"hello hello hello hello"
+    assert c.inflate(z + b"garbage") == b"hello hello hello hello"
+    # src/inflate.ts:287-290 — a distance before the start of the output yields zeros
+    co = zlib.compressobj(wbits=-15, zdict=b"abcdefgh")
+    body = co.compress(b"abcdefghabcdefgh") + co.flush()
+    inflate_matches_oracle(c, b"\x78\x9c" + body)
+    # FDICT / FCHECK ignored (src/zlib.ts:17-20)
+    inflate_matches_oracle(c, b"\x78\xff" + zlib.compress(b"abc" * 50)[2:])
+
+
+def error_strings(c):
+    for stream, msg in [(b"\x77\x9c\x03\x00", "Not compressed by deflate"),   # src/zlib.ts:15
+                        (b"", "Not compressed by deflate"),
+                        (b"\x78\x9c\x07\x00\x00\x00\x00\x00", "Not supported BTYPE : 3"),  # src/inflate.ts:32
+                        (b"\x78\x9c\x01\x05\x00\x00\x00hello", "Data is corrupted")]:    # src/inflate.ts:50
+        try:
+            c.inflate(stream)
+        except Exception as e:
+            assert str(e) == msg, (stream, str(e))
+        else:
+            raise AssertionError("no error for %r" % stream)

@@ -13,9 +13,13 @@
 //   together with the preceding 32 KiB of the same chunk (the window), by TMA;
 //   S2  the positions are radix-sorted (stable, 2 x 8 bit) by a 16-bit hash of their
 //       3-byte key: one run of the sorted array == one position list of the reference;
-//   S3  every position of the block looks up its own matches in parallel by walking
-//       backwards through its run (most recent first, same stop rules as
-//       src/lz77.ts:66-69,86-92, depth configurable);
+//   S3  every position of the block finds its matches in parallel.  A warp sweeps its slice of the
+//       sorted array 32 entries at a time; each entry's next 7 bytes go into a per-warp ring, and
+//       every lane compares its own 7 bytes with those of the <= 32 entries before it in its run
+//       (nearest first, inside the window — the candidate order of src/lz77.ts:64-93).  That
+//       gives the exact match length up to 6 for all 32 candidates at ~13 instructions each with
+//       no divergence; only candidates that match on all 7 bytes are extended byte-wise
+//       (up to `deep` of them).  Longest wins, ties keep the nearest (src/lz77.ts:86-92);
 //   S4  the greedy parse (src/lz77.ts:39-115, nowIndex += repeatLengthMax) is a serial
 //       chain; 64 walkers parse 512-position ranges speculatively and a short serial
 //       pass stitches them (a walk re-synchronises with the speculative one within a
@@ -29,8 +33,8 @@
 // longer one).
 //
 // Shared memory: 64 KiB+pad data | 128 KiB sorted positions (u16) reused for the
-// per-position match results (u32) | 16 KiB sort histograms reused for the token
-// bitmap and the symbol histograms | 4 KiB warp queues | 1 KiB misc  = 213.4 KiB.
+// per-position match results (u32) | 16 KiB sort histograms reused for the candidate
+// rings, then the token bitmap and the symbol histograms | 1 KiB misc  = 209.4 KiB.
 #pragma once
 #include "tma.cuh"
 #include "zles_dev.h"
@@ -48,9 +52,10 @@ constexpr u32 LZ_NSYM = 320;  // [0,288) literal/length symbols, [288,320) dista
 constexpr u32 LZ_OFF_DATA = 0;
 constexpr u32 LZ_OFF_X = 65536 + 384;                       // 65920
 constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256] | bitmap u32[1024] + hist u32[8*320]
-constexpr u32 LZ_OFF_WQ = LZ_OFF_WH + 16384;                // u16[LZ_WARPS][64]
-constexpr u32 LZ_OFF_MISC = LZ_OFF_WQ + 4096;               // scratch u32[40] | specexit u32[64] | mbarrier
-constexpr u32 LZ_SMEM = LZ_OFF_MISC + 1024;                 // 218496 B
+constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 16384;              // scratch u32[40] | specexit u32[64] | mbarrier
+constexpr u32 LZ_SMEM = LZ_OFF_MISC + 1024;                 // 214400 B
+constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (ring = 2 x 32 entries)
+static_assert(LZ_WARPS * 64 * 8 <= 16384, "candidate rings overlay the sort histograms");
 
 struct LzParams {
   const u8 *in;       // this shard's input
@@ -61,9 +66,9 @@ struct LzParams {
   u32 *hist;          // [nblocks][LZ_NSYM]
   u32 *scratch;       // [gridDim.x][SUB] u32: sort pass buffer (as u16[65536]), then match results
   u64 *adler_part;    // [nblocks][2]: sum d, sum (len - j) d[j] over the block's own bytes
-  u32 max_checks;     // FAST_INDEX_CHECK_MAX   (reference: 128, src/lz77.ts:7)
-  u32 min_checks;     // FAST_INDEX_CHECK_MIN   (reference: 16,  src/lz77.ts:8)
-  u32 good_len;       // FAST_REPEAT_LENGTH     (reference: 8,   src/lz77.ts:9)
+  u32 max_checks;     // candidates compared per position, <= LZ_SCAN   (reference: FAST_INDEX_CHECK_MAX = 128, src/lz77.ts:7)
+  u32 min_checks;     // of those, how many >= 7-byte candidates are extended (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
+  u32 good_len;       // reserved (reference: FAST_REPEAT_LENGTH = 8, src/lz77.ts:9)
   u32 lazy;           // 1: defer a match by one literal when the next position has a longer one
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
 };
@@ -152,37 +157,13 @@ __device__ __forceinline__ void lz_sort_pass(const u8 *data, const u16 *src, Out
   __syncthreads();
 }
 
-// S3: best earlier match of position p = X[k] (one thread).  Returns (len << 16) | dist, or 0.
-__device__ __forceinline__ u32 lz_find(const u8 *data, const u16 *X, u32 k, u32 L, const LzParams &P) {
-  const u32 p = X[k];
-  const u32 maxlen = umin(MAX_MATCH, L - p);
-  if (maxlen < MIN_MATCH) return 0;
-  const u32 kp = lz_key3(data, p);
-  const u32 hp = lz_hash16(kp);
-  u32 best = 2, bdist = 0, checks = 0, skips = 0;
-  for (u32 j = k; j-- > 0;) {
-    const u32 c = X[j];
-    const u32 kc = lz_key3(data, c);
-    if (kc != kp) {
-      if (lz_hash16(kc) != hp || ++skips > 64) break;  // left the run of this hash
-      continue;                                        // hash collision inside the run
-    }
-    if (p - c > WINDOW) break;  // runs are ascending: everything further left is older (src/lz77.ts:49)
-    checks++;
-    // src/lz77.ts:72-76: a candidate that cannot beat the best is rejected from its far end first
-    if (best < maxlen && data[c + best] == data[p + best]) {
-      u32 len = lz_match_len(data, c, p, maxlen);
-      if (len > best) {  // strictly longer wins, ties keep the nearest (src/lz77.ts:86-92)
-        best = len;
-        bdist = p - c;
-        if (len >= maxlen) break;
-      }
-    }
-    if (checks >= P.max_checks || (best >= P.good_len && checks >= P.min_checks)) break;  // src/lz77.ts:66-69
-  }
-  if (best < MIN_MATCH) return 0;
-  if (best == MIN_MATCH && bdist > 4096) return 0;  // costs more than three literals
-  return (best << 16) | bdist;
+// bytes d[p .. p+6] as (lo = bytes 0-3, hi = bytes 4-6); unaligned shared-memory read
+__device__ __forceinline__ void lz_ld56(const u8 *d, u32 p, u32 &lo, u32 &hi) {
+  const u32 *w = reinterpret_cast<const u32 *>(d + (p & ~3u));
+  const u32 sh = (p & 3) * 8;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = __funnelshift_r(w1, w2, sh) & 0x00ffffffu;
 }
 
 // match length the parse uses at own-relative position pos (0 = literal)
@@ -210,7 +191,6 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u16 *wh = reinterpret_cast<u16 *>(smem + LZ_OFF_WH);
   u32 *bm = reinterpret_cast<u32 *>(smem + LZ_OFF_WH);          // [1024]
   u32 *hcopies = reinterpret_cast<u32 *>(smem + LZ_OFF_WH) + 1024;  // [LZ_HCOPIES][LZ_NSYM]
-  u16 *wq = reinterpret_cast<u16 *>(smem + LZ_OFF_WQ);
   u32 *scratch = reinterpret_cast<u32 *>(smem + LZ_OFF_MISC);       // [40]
   u32 *specexit = scratch + 40;                                      // [64]
   u64 *mbar = reinterpret_cast<u64 *>(scratch + 40 + 64);           // 8-byte aligned: (40+64)*4 = 416
@@ -277,32 +257,97 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     lz_sort_pass<u16>(data, nullptr, Y, wh, scratch, N, per, 0);
     lz_sort_pass<u16>(data, Y, X, wh, scratch, N, per, 8);
 
-    // S3: per-position match search, own positions only, compacted through a warp queue
+    // S3: per-position match search.  Warp w owns sorted entries [kbeg, kend).
     {
-      u16 *q = wq + w * 64;
-      u32 qn = 0;
-      for (u32 base = w * 32; base < N; base += LZ_THREADS) {
-        const u32 k = base + lane;
-        const bool own = k < N && X[k] >= hist_len;
-        const u32 bal = __ballot_sync(ZLES_FULL, own);
-        if (own) q[qn + __popc(bal & lanemask_lt())] = (u16)k;
-        qn += __popc(bal);
-        __syncwarp();
-        if (qn >= 32) {
-          const u32 kk = q[lane];
-          R[(u32)X[kk] - hist_len] = lz_find(data, X, kk, L, P);
-          __syncwarp();
-          u16 t = 0;
-          if (lane < qn - 32) t = q[32 + lane];
-          __syncwarp();
-          if (lane < qn - 32) q[lane] = t;
-          qn -= 32;
-          __syncwarp();
-        }
+      uint2 *ring = reinterpret_cast<uint2 *>(smem + LZ_OFF_WH) + w * 64;
+      const u32 kbeg = umin(w * per, N), kend = umin(kbeg + per, N);
+      const u32 scan = umin(P.max_checks, LZ_SCAN);
+      u32 Bprev = 0, hprev = 0xffffffffu;
+      if (kbeg > 0 && kbeg < kend) {  // the 32 entries before the slice are candidates of its first ones (kbeg is a multiple of 32)
+        const u32 j = kbeg - 32 + lane;
+        const u32 pj = X[j];
+        u32 lo, hi;
+        lz_ld56(data, pj, lo, hi);
+        ring[j & 63] = make_uint2(lo, hi);
+        const u32 hj = lz_hash16(lo & 0xffffffu);
+        u32 hl = __shfl_up_sync(ZLES_FULL, hj, 1);
+        if (lane == 0) hl = 0xffffffffu;  // whether entry kbeg-32 starts a run never matters (see rrun below)
+        Bprev = __ballot_sync(ZLES_FULL, hj != hl);
+        hprev = __shfl_sync(ZLES_FULL, hj, 31);
       }
-      if (lane < qn) {
-        const u32 kk = q[lane];
-        R[(u32)X[kk] - hist_len] = lz_find(data, X, kk, L, P);
+      for (u32 kb = kbeg; kb < kend; kb += 32) {
+        const u32 k = kb + lane;
+        const bool valid = k < kend;
+        u32 p = 0, lo = 0, hi = 0, h = 0x10000u + lane;
+        if (valid) {
+          p = X[k];
+          lz_ld56(data, p, lo, hi);
+          h = lz_hash16(lo & 0xffffffu);
+        }
+        ring[k & 63] = make_uint2(lo, hi);
+        u32 hl = __shfl_up_sync(ZLES_FULL, h, 1);
+        if (lane == 0) hl = hprev;
+        const u32 B = __ballot_sync(ZLES_FULL, h != hl);  // bit l: entry kb+l starts a run of equal hashes
+        hprev = __shfl_sync(ZLES_FULL, h, 31);
+        __syncwarp();
+        // rrun = how many entries before k belong to k's run (capped at the scan width)
+        const bool own = valid && p >= hist_len;
+        u32 rrun = 0;
+        if (own) {
+          const u64 t = ((((u64)B) << 32) | Bprev) << (31 - lane);  // bit 63 = entry k, bit 62 = entry k-1, ...
+          rrun = t ? (u32)__clzll((long long)t) : 64u;
+          rrun = umin(rrun, scan);
+          if (rrun && p > WINDOW && (u32)X[k - rrun] < p - WINDOW) {
+            // candidates older than the window (src/lz77.ts:49): positions ascend inside a run, so
+            // binary-search the largest r with X[k-r] >= p - WINDOW
+            const u32 lim = p - WINDOW;
+            u32 a = 0, b = rrun;  // X[k-a] in window (a = 0: k itself), X[k-b] not
+            while (b - a > 1) {
+              const u32 m = (a + b) >> 1;
+              if ((u32)X[k - m] >= lim) a = m; else b = m;
+            }
+            rrun = a;
+          }
+        }
+        const u32 rmax = __reduce_max_sync(ZLES_FULL, rrun);
+        u32 best = 0, full = 0;
+        for (u32 r = 1; r <= rmax; r++) {
+          if (r <= rrun) {
+            const uint2 ce = ring[(k - r) & 63];
+            const u32 xl = lo ^ ce.x, xh = hi ^ ce.y;
+            if ((xl & 0xffffffu) == 0) {               // same 3-byte key (src/lz77.ts:40)
+              const u32 v = (xl >> 24) | (xh << 8);    // bytes 3..6
+              if (v == 0) full |= 1u << (r - 1);
+              else best = umax(best, ((3 + ((u32)(__ffs((int)v) - 1) >> 3)) << 8) | (64 - r));
+            }
+          }
+        }
+        if (own) {
+          const u32 maxlen = umin(MAX_MATCH, L - p);
+          u32 len = 0, dist = 0;
+          if (full) {  // candidates equal on 7 bytes: extend, nearest first
+            u32 m = full, n = 0;
+            while (m && n < P.min_checks) {
+              const u32 r = (u32)__ffs((int)m);
+              m &= m - 1;
+              n++;
+              const u32 c = X[k - r];
+              const u32 l = maxlen > 7 ? 7 + lz_match_len(data, c + 7, p + 7, maxlen - 7) : maxlen;
+              if (l > len) {  // strictly longer wins, ties keep the nearest (src/lz77.ts:86-92)
+                len = l;
+                dist = p - c;
+                if (l >= maxlen) break;
+              }
+            }
+          } else if (best) {
+            len = umin(best >> 8, maxlen);
+            dist = p - (u32)X[k - (64 - (best & 255))];
+          }
+          if (len == MIN_MATCH && dist > 4096) len = 0;  // costs more than three literals
+          R[p - hist_len] = len >= MIN_MATCH ? (len << 16) | dist : 0;
+        }
+        Bprev = B;
+        __syncwarp();  // the next batch overwrites the older half of the ring
       }
       // positions without a full 3-byte key (the last two of the window+block) have no match
       if (tid < 2 && own_len > tid) R[own_len - 1 - tid] = 0;

@@ -97,21 +97,24 @@ int zles_dev_inflate_batch(zles_ctx *ctx, const uint8_t *d_in, const uint64_t *d
  * the shard's compressed size and Adler-32 partial sums; the ranks exchange those
  * (NCCL all-gather in zlib.es_b200/dist.py); phase 2 writes the shard's bytes at
  * its global offset — d_dst may be a peer-mapped pointer (zles_ipc_*), so the
- * segments are stored straight into the final stream over NVLink. */
+ * blocks are stored straight into the final stream over NVLink.  Every block is
+ * byte aligned (it ends with an empty stored block), which is what lets shards
+ * be written independently and lets inflate decode blocks in parallel. */
 typedef struct {
   uint64_t comp_bytes;   /* compressed size of the shard (no zlib header/trailer) */
   uint64_t raw_bytes;    /* shard length */
   uint64_t adler_a;      /* sum of bytes mod 65521 */
   uint64_t adler_b;      /* sum of (raw_bytes - i) * byte[i] mod 65521 */
-  uint64_t n_chunks;     /* 128 KiB chunks in the shard */
+  uint64_t n_blocks;     /* 32 KiB deflate blocks in the shard */
 } zles_shard_info;
 int zles_dev_deflate_phase1(zles_ctx *ctx, const uint8_t *d_in, size_t n, int is_last_shard, zles_shard_info *info);
-/* per-chunk compressed sizes of the last phase 1 (device pointer to n_chunks+1 uint64 offsets) */
-int zles_dev_deflate_chunk_offsets(zles_ctx *ctx, const uint64_t **d_offsets);
+/* byte offsets of the shard's blocks after the last phase 1 (device pointer to n_blocks+1 uint64) */
+int zles_dev_deflate_block_offsets(zles_ctx *ctx, const uint64_t **d_offsets);
 int zles_dev_deflate_phase2(zles_ctx *ctx, uint8_t *d_dst);
 /* Combine the per-shard sums of all ranks (in rank order) into the stream's Adler-32. */
 uint32_t zles_adler32_combine_shards(const zles_shard_info *infos, uint32_t count);
-/* Inflate `n` bytes of marker-delimited chunks that start at a chunk boundary (no zlib header). */
+/* Inflate `n` bytes of marker-delimited blocks that start at a 128 KiB chunk boundary of the
+ * original data (no zlib header); used by the sharded inflate. */
 int zles_dev_inflate_segment(zles_ctx *ctx, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
                              size_t *out_len);
 

@@ -3,22 +3,17 @@
 // The container that builds this repo has no GPU, and GPU time is rationed, so
 // the kernels under zlib.es_b200/csrc are written against a small portability
 // shim (zles_dev.h).  Compiled with -DZLES_EMU the same sources run here: one
-// OS thread per CUDA thread, __syncthreads() = a CTA barrier, warp intrinsics =
+// fiber per CUDA thread, __syncthreads() = a CTA barrier, warp intrinsics =
 // a per-warp rendezvous keyed by the participation mask.  This is a debugging
-// aid for logic errors, races (it runs under -fsanitize=thread/address) and
-// deadlocks.  It is never loaded by the product: zlib.es_b200/_capi.py only
+// aid for logic errors (indexing, barrier placement, warp votes) and deadlocks.  It is never loaded by the product: zlib.es_b200/_capi.py only
 // opens libzles.so (the nvcc build) and raises if that is missing.
 #pragma once
 #include <atomic>
-#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
-#include <map>
-#include <mutex>
-#include <thread>
 #include <vector>
 
 #define __global__
@@ -42,94 +37,100 @@ static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 
 namespace emu {
 
-struct Slot {
+// One CUDA thread = one fiber (user-level context).  All fibers of a CTA run on one OS
+// thread under a round-robin scheduler, so __syncthreads(), warp collectives and
+// spin-waits are plain loops around yield() — no locks, deterministic, and fast enough
+// to run whole kernels.  Several CTAs run in parallel on several OS threads.
+struct Fiber {
+  void *sp = nullptr;      // saved stack pointer
+  void *stack = nullptr;
+  bool done = false;
+  uint3 tid{0, 0, 0};
+};
+struct WarpSlot {          // rendezvous state of one warp collective
   uint64_t vals[32];
   uint64_t out[32];
-  int arrived = 0;
-  int gen = 0;
-  int readers_left = 0;
-};
-struct WarpRv {
-  std::mutex m;
-  std::condition_variable cv;
-  std::map<uint32_t, Slot> slots;
+  uint32_t mask = 0;       // participation mask of the collective in flight (0 = idle)
+  uint32_t arrived = 0;
+  uint32_t pending_read = 0;
+  uint32_t gen = 0;
 };
 struct BlockCtx {
   unsigned nthreads = 0;
-  std::mutex bm;
-  std::condition_variable bcv;
-  unsigned barrived = 0;
-  unsigned bgen = 0;
-  std::vector<WarpRv> warps;
+  std::vector<Fiber> fibers;
+  std::vector<WarpSlot> warps;
+  unsigned barrier_arrived = 0;
+  unsigned barrier_gen = 0;
   uint8_t *smem = nullptr;
+  uint3 bid{0, 0, 0};
+  dim3 bdim, gdim;
+  unsigned cur = 0;        // running fiber
+  void *sched_sp = nullptr;
+  const std::function<void()> *body = nullptr;
 };
 
 extern thread_local BlockCtx *g_blk;
-extern thread_local uint3 g_tid, g_bid;
-extern thread_local dim3 g_bdim, g_gdim;
 
 inline uint8_t *dyn_smem() { return g_blk->smem; }
+void yield();              // back to the scheduler; returns when this fiber is picked again
 
 inline void block_barrier() {
   BlockCtx *b = g_blk;
-  std::unique_lock<std::mutex> lk(b->bm);
-  unsigned gen = b->bgen;
-  if (++b->barrived == b->nthreads) {
-    b->barrived = 0;
-    b->bgen++;
-    b->bcv.notify_all();
-  } else {
-    b->bcv.wait(lk, [&] { return b->bgen != gen; });
+  const unsigned gen = b->barrier_gen;
+  if (++b->barrier_arrived == b->nthreads) {
+    b->barrier_arrived = 0;
+    b->barrier_gen++;
+    return;
   }
+  while (b->barrier_gen == gen) yield();
 }
 
 // Every participating lane publishes v and receives the values of all lanes in mask.
 inline void warp_exchange(uint32_t mask, uint64_t v, uint64_t out[32]) {
-  unsigned lane = g_tid.x & 31;
+  BlockCtx *b = g_blk;
+  const unsigned t = b->cur, lane = t & 31;
   if (!((mask >> lane) & 1)) {
     fprintf(stderr, "emu: lane %u not in mask %08x\n", lane, mask);
     abort();
   }
-  WarpRv &w = g_blk->warps[g_tid.x >> 5];
-  int cnt = __builtin_popcount(mask);
-  std::unique_lock<std::mutex> lk(w.m);
-  Slot &s = w.slots[mask];
-  w.cv.wait(lk, [&] { return s.readers_left == 0; });
+  WarpSlot &s = b->warps[t >> 5];
+  while (s.pending_read || (s.mask && s.mask != mask)) yield();  // previous collective still being read / another in flight
+  s.mask = mask;
   s.vals[lane] = v;
-  if (++s.arrived == cnt) {
+  s.arrived |= 1u << lane;
+  if (s.arrived == mask) {
     memcpy(s.out, s.vals, sizeof(s.out));
-    s.readers_left = cnt;
+    s.pending_read = mask;
     s.arrived = 0;
+    s.mask = 0;
     s.gen++;
-    w.cv.notify_all();
   } else {
-    int gen = s.gen;
-    w.cv.wait(lk, [&] { return s.gen != gen; });
+    const uint32_t gen = s.gen;
+    while (s.gen == gen) yield();
   }
   memcpy(out, s.out, sizeof(s.out));
-  if (--s.readers_left == 0) w.cv.notify_all();
+  s.pending_read &= ~(1u << lane);
 }
 
-// Runs `body` once per CUDA thread.  Blocks run one after another (a few host
-// threads each would only add noise); threads of a block are real OS threads.
+// Runs `body` once per CUDA thread.
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
 
 }  // namespace emu
 
-#define threadIdx (emu::g_tid)
-#define blockIdx (emu::g_bid)
-#define blockDim (emu::g_bdim)
-#define gridDim (emu::g_gdim)
+#define threadIdx (emu::g_blk->fibers[emu::g_blk->cur].tid)
+#define blockIdx (emu::g_blk->bid)
+#define blockDim (emu::g_blk->bdim)
+#define gridDim (emu::g_blk->gdim)
 
 static inline void __syncthreads() { emu::block_barrier(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   uint64_t o[32];
   emu::warp_exchange(mask, 0, o);
 }
-static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
-static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
 static inline void __trap() { fprintf(stderr, "emu: __trap()\n"); abort(); }
-static inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+static inline void __nanosleep(unsigned) { emu::yield(); }
 
 template <typename T>
 static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {

@@ -23,7 +23,7 @@ c_vp = ctypes.c_void_p
 class ShardInfo(ctypes.Structure):
     """zles_shard_info"""
     _fields_ = [("comp_bytes", ctypes.c_uint64), ("raw_bytes", ctypes.c_uint64), ("adler_a", ctypes.c_uint64),
-                ("adler_b", ctypes.c_uint64), ("n_chunks", ctypes.c_uint64)]
+                ("adler_b", ctypes.c_uint64), ("n_blocks", ctypes.c_uint64)]
 
 
 # name -> (restype, argtypes); every symbol include/zles.h declares
@@ -50,7 +50,7 @@ PROTOTYPES = {
     "zles_dev_deflate_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "zles_dev_inflate_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "zles_dev_deflate_phase1": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ShardInfo)]),
-    "zles_dev_deflate_chunk_offsets": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "zles_dev_deflate_block_offsets": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "zles_dev_deflate_phase2": (ctypes.c_int, [c_vp, c_vp]),
     "zles_adler32_combine_shards": (ctypes.c_uint32, [ctypes.POINTER(ShardInfo), ctypes.c_uint32]),
     "zles_dev_inflate_segment": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, c_vp, ctypes.c_size_t, c_szp]),

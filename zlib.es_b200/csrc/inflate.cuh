@@ -205,6 +205,49 @@ __device__ __forceinline__ bool inf_decode(InfReader &r, const u16 *lut, int roo
   return true;
 }
 
+// Dynamic block header (/root/reference/src/inflate.ts:121-202): HLIT/HDIST/HCLEN, the code-length
+// code, then the run-length coded literal/length and distance code lengths into S->lens.
+// Returns false with `status` set on error.  Warp-uniform.
+__device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSmem *S, u32 &status) {
+  const u32 lane = lane_id();
+  const u32 HLIT = r.take(5) + 257;
+  const u32 HDIST = r.take(5) + 1;
+  const u32 HCLEN = r.take(4) + 4;
+  S->cl_lens[lane] = 0;
+  for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
+  __syncwarp();
+  for (u32 i = 0; i < HCLEN; i++) {
+    r.refill();
+    u32 v = r.take(3);
+    if (lane == 0) S->cl_lens[c_cl_order[i]] = (u8)v;
+  }
+  __syncwarp();
+  inf_build(S->cl_lens, 32, CL_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+  const u32 total = HLIT + HDIST;
+  u32 prev = 0;
+  for (u32 i = 0; i < total;) {
+    r.refill();
+    if (r.overrun) { status = SEG_E_LACK; return false; }
+    u32 sym;
+    if (!inf_decode(r, S->lut_d, CL_ROOT, &S->tab_d, S->sorted_d, sym)) { status = SEG_E_CORRUPT; return false; }
+    u32 rep = 1, val = sym;
+    if (sym == 16) { rep = 3 + r.take(2); val = prev; }
+    else if (sym == 17) { rep = 3 + r.take(3); val = 0; prev = 0; }
+    else if (sym == 18) { rep = 11 + r.take(7); val = 0; prev = 0; }
+    else prev = sym;
+    if (val) {
+      for (u32 k = lane; k < rep; k += 32) {
+        u32 j = i + k;
+        if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
+        else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
+      }
+    }
+    i += rep;
+  }
+  __syncwarp();
+  return true;
+}
+
 // Decodes one segment on one warp.  Returns through *res (lane 0 writes).
 __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n, u64 in_pos, u8 *out, u64 out_off, u64 cap,
                                             bool stop_at_sync, InfRes *res) {
@@ -246,43 +289,7 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
       for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
       __syncwarp();
     } else {  // dynamic header, src/inflate.ts:121-202
-      const u32 HLIT = r.take(5) + 257;
-      const u32 HDIST = r.take(5) + 1;
-      const u32 HCLEN = r.take(4) + 4;
-      S->cl_lens[lane] = 0;
-      for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
-      __syncwarp();
-      for (u32 i = 0; i < HCLEN; i++) {
-        r.refill();
-        u32 v = r.take(3);
-        if (lane == 0) S->cl_lens[c_cl_order[i]] = (u8)v;
-      }
-      __syncwarp();
-      inf_build(S->cl_lens, 32, CL_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
-      const u32 total = HLIT + HDIST;
-      u32 prev = 0;
-      bool bad = false;
-      for (u32 i = 0; i < total;) {
-        r.refill();
-        if (r.overrun) { bad = true; status = SEG_E_LACK; break; }
-        u32 sym;
-        if (!inf_decode(r, S->lut_d, CL_ROOT, &S->tab_d, S->sorted_d, sym)) { bad = true; status = SEG_E_CORRUPT; break; }
-        u32 rep = 1, val = sym;
-        if (sym == 16) { rep = 3 + r.take(2); val = prev; }
-        else if (sym == 17) { rep = 3 + r.take(3); val = 0; prev = 0; }
-        else if (sym == 18) { rep = 11 + r.take(7); val = 0; prev = 0; }
-        else prev = sym;
-        if (val) {
-          for (u32 k = lane; k < rep; k += 32) {
-            u32 j = i + k;
-            if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
-            else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
-          }
-        }
-        i += rep;
-      }
-      if (bad) break;
-      __syncwarp();
+      if (!inf_read_dynamic_header(r, S, status)) break;
     }
     inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
     inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
@@ -441,6 +448,204 @@ k_mark_emit(const u8 *__restrict__ in, u64 n, u64 first, const u32 *tile_base, u
   if (blockIdx.x == 0 && threadIdx.x == 0) cand[0] = first;
 }
 
+// ---- K7 fast path for OUR streams: two phases ------------------------------------------------
+// Our encoder ends every 32 KiB block with a sync marker and a block only references data of
+// its own 128 KiB chunk.  Huffman decoding is a serial chain per block but independent between
+// blocks; the LZ77 copies depend on earlier output but are cheap.  So:
+//   phase A  k_inf_tokens   one warp per candidate segment: decode the symbols into a token
+//                           list (literal byte | match length + distance), no output yet.
+//                           Where a segment ends and how many bytes it stands for do not
+//                           depend on anything outside it, so false candidates are harmless.
+//   (check)  k_inf_check    every candidate must end where the next one starts and stand for
+//                           exactly SUB bytes; otherwise the host filters the list (zles.cu).
+//   phase B  k_inf_resolve  one warp per 128 KiB chunk (4 segments, in order): a warp-wide scan
+//                           of the token lengths gives every token its output offset, literals
+//                           are stored at once, and matches are copied lane-parallel, a batch
+//                           of 32 tokens at a time, in rounds that respect their dependencies.
+// Tokens use the encoder's format (lz77.cuh): literal = byte value; match = bit31 | (len-3)<<16 | (dist-1).
+constexpr u32 SEGF_BADREF = 4;            // a distance reached before the start of the chunk
+
+__device__ __forceinline__ void inf_segment_tokens(InfWarpSmem *S, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out) {
+  const u32 lane = lane_id();
+  InfReader r;
+  r.init(in, n, in_pos);
+  u32 o = 0, nt = 0, mytok = 0;
+  u32 status = 0, flags = 0;
+  u64 end_pos = 0;
+#define ZLES_EMIT(t)                                         \
+  do {                                                       \
+    if ((nt & 31) == lane) mytok = (t);                      \
+    nt++;                                                    \
+    if ((nt & 31) == 0) tok[nt - 32 + lane] = mytok;         \
+  } while (0)
+  for (;;) {
+    r.refill();
+    if (r.overrun) { status = SEG_E_LACK; break; }
+    const u32 bfinal = r.take(1);
+    const u32 btype = r.take(2);
+    if (btype == 3) { status = SEG_E_BTYPE3; break; }
+    if (btype == 0) {
+      r.skip((u32)((0 - r.bitpos()) & 7));
+      r.refill();
+      const u32 LEN = r.take(16);
+      r.refill();
+      const u32 NLEN = r.take(16);
+      if (LEN + NLEN != 65535) { status = SEG_E_CORRUPT; break; }
+      if (LEN != 0) { status = SEG_E_CORRUPT; break; }  // stored data: not one of our streams, sequential path
+      end_pos = r.bitpos() >> 3;
+      status = bfinal ? SEG_FINAL : SEG_SYNC;
+      break;
+    }
+    if (btype == 1) {
+      for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+      __syncwarp();
+    } else {
+      if (!inf_read_dynamic_header(r, S, status)) break;
+    }
+    inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
+    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+    for (;;) {
+      r.refill();
+      if (r.overrun) { status = SEG_E_LACK; break; }
+      u32 sym;
+      if (!inf_decode(r, S->lut_ll, LL_ROOT, &S->tab_ll, S->sorted_ll, sym)) { status = SEG_E_CORRUPT; break; }
+      if (sym < 256) {
+        if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+        ZLES_EMIT(sym);
+        o++;
+        continue;
+      }
+      if (sym == 256) break;
+      const u32 ls = sym - 257;
+      if (ls >= 29) { status = SEG_E_CORRUPT; break; }
+      const u32 len = c_len_base[ls] + r.take(c_len_extra[ls]);
+      r.refill();
+      u32 ds;
+      if (!inf_decode(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, ds)) { status = SEG_E_CORRUPT; break; }
+      if (ds >= 30) { status = SEG_E_CORRUPT; break; }
+      r.refill();
+      const u32 dist = c_dist_base[ds] + r.take(c_dist_extra[ds]);
+      if (o + len > SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+      ZLES_EMIT(0x80000000u | ((len - 3) << 16) | (dist - 1));
+      o += len;
+    }
+    if (status) break;
+    if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
+  }
+#undef ZLES_EMIT
+  if (lane < (nt & 31)) tok[(nt & ~31u) + lane] = mytok;
+  if (lane == 0) {
+    res->end_pos = end_pos;
+    res->out_len = o;
+    res->status = status;
+    res->flags = flags;
+    *ntok_out = nt;
+  }
+}
+
+// phase A: persistent warps take segment indices from a counter.  Segment j's tokens go to
+// tokens[j * SUB ...]; candidates beyond tok_segs (more than the output could hold) are not decoded.
+__global__ void __launch_bounds__(INF_THREADS)
+k_inf_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res,
+             u32 *counter) {
+  ZLES_SMEM_DECL(smem_raw);
+  InfWarpSmem *S = reinterpret_cast<InfWarpSmem *>(smem_raw) + warp_id();
+  for (;;) {
+    u32 j = 0;
+    if (lane_id() == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(ZLES_FULL, j, 0);
+    if (j >= nseg) break;
+    inf_segment_tokens(S, in, n, seg_pos[j], tokens + (size_t)j * SUB, res + j, ntok + j);
+    __syncwarp();
+  }
+}
+
+// phase B: one warp per chunk.  seg_list (or identity when null) names the real segments in
+// stream order; chunk c is made of entries [4c, 4c+4) and is written at out + c * CHUNK.
+constexpr int RES_WARPS = 4;
+constexpr int RES_THREADS = RES_WARPS * 32;
+constexpr u32 RES_LONG = 24;  // matches at least this long are copied by the whole warp
+
+__global__ void __launch_bounds__(RES_THREADS)
+k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg, u8 *out, u64 cap,
+              u32 *problems) {
+  const u32 lane = lane_id();
+  const u32 c = blockIdx.x * RES_WARPS + warp_id();
+  if (c * SUBS_PER_CHUNK >= nseg) return;
+  u8 *base = out + (u64)c * CHUNK;
+  const u64 room64 = (u64)c * CHUNK >= cap ? 0 : cap - (u64)c * CHUNK;
+  const u32 room = (u32)umin64(room64, (u64)CHUNK);  // bytes of this chunk that fit in the output
+  u32 o = 0, bad = 0;
+  for (u32 k = 0; k < SUBS_PER_CHUNK && !bad; k++) {
+    const u32 e = c * SUBS_PER_CHUNK + k;
+    if (e >= nseg) break;
+    const u32 sidx = seg_list ? seg_list[e] : e;
+    const u32 nt = umin(ntok[sidx], SUB);
+    const u32 *tok = tokens + (size_t)sidx * SUB;
+    for (u32 b0 = 0; b0 < nt; b0 += 32) {
+      const bool valid = b0 + lane < nt;
+      const u32 t = valid ? __ldg(tok + b0 + lane) : 0;
+      const bool isM = valid && (t >> 31);
+      const u32 len = !valid ? 0 : (isM ? ((t >> 16) & 255) + 3 : 1);
+      const u32 dist = (t & 0x7fff) + 1;
+      u32 inc = len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u32 v = __shfl_up_sync(ZLES_FULL, inc, d);
+        if (lane >= (u32)d) inc += v;
+      }
+      const u32 pos = o + inc - len;            // chunk-relative offset of this token's first byte
+      const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
+      if (o + total > CHUNK) { bad |= 1; break; }
+      if (o + total > room) { bad |= 2; break; }  // output buffer too small: nothing of this batch is written
+      if (valid && !isM) base[pos] = (u8)t;
+      const bool badref = isM && dist > pos;     // before the start of the chunk
+      if (__any_sync(ZLES_FULL, badref)) { bad |= 1; break; }
+      const u32 src = pos - dist;
+      const u32 send = umin(src + len, pos);      // bytes [src, send) must be final before this match is copied
+      // dep = earlier matches of this batch whose output overlaps [src, send)
+      u32 dep = 0;
+      const u32 mmask = __ballot_sync(ZLES_FULL, isM);
+      if (__any_sync(ZLES_FULL, isM && send > o)) {
+        const u32 pend = pos + len;
+        u32 m = mmask;
+        while (m) {
+          const int j = __ffs((int)m) - 1;
+          m &= m - 1;
+          const u32 pj = __shfl_sync(ZLES_FULL, pos, j), ej = __shfl_sync(ZLES_FULL, pend, j);
+          if ((u32)j < lane && src < ej && send > pj) dep |= 1u << j;
+        }
+      }
+      __syncwarp();
+      u32 done = ~mmask;
+      while (done != 0xffffffffu) {
+        const bool ready = isM && !((done >> lane) & 1) && (dep & ~done) == 0;
+        const u32 rmask = __ballot_sync(ZLES_FULL, ready);
+        const u32 lmask = __ballot_sync(ZLES_FULL, ready && len >= RES_LONG);
+        if (ready && len < RES_LONG) {
+          for (u32 q = 0; q < len; q++) base[pos + q] = base[src + q];  // byte-serial: right for overlapping copies too
+        }
+        u32 m = lmask;
+        while (m) {  // long matches: the whole warp copies one at a time
+          const int j = __ffs((int)m) - 1;
+          m &= m - 1;
+          const u32 pj = __shfl_sync(ZLES_FULL, pos, j), sj = __shfl_sync(ZLES_FULL, src, j), lj = __shfl_sync(ZLES_FULL, len, j);
+          const u32 dj = pj - sj;
+          if (dj >= lj) {
+            for (u32 q = lane; q < lj; q += 32) base[pj + q] = base[sj + q];
+          } else {  // overlapping: the output is periodic with period dj
+            for (u32 q = lane; q < lj; q += 32) base[pj + q] = base[sj + (q % dj)];
+          }
+        }
+        done |= rmask;
+        __syncwarp();
+      }
+      o += total;
+    }
+  }
+  if (bad && lane == 0) atomicOr(problems, bad);
+}
+
 // stream too short to hold a marker: the only candidate is `first`
 __global__ void k_mark_none(u64 first, u64 *cand, u32 *ncand) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { cand[0] = first; *ncand = 1; }
@@ -448,27 +653,20 @@ __global__ void k_mark_none(u64 first, u64 *cand, u32 *ncand) {
 
 // ---- acceptance of the optimistic parallel decode -----------------------------
 // problems[0] stays 0 only if every segment j ended on the marker that starts
-// segment j+1, needed no history, produced exactly CHUNK bytes (the last one:
-// <= CHUNK and BFINAL).  Bit 1 (value 2) alone = all of that holds but the output
-// buffer was too small; bit 0 = anything else, and the host walks the chain
-// (zles.cu).  total[0] = sum of out_len.
+// segment j+1 and stands for exactly SUB bytes (the last one: <= SUB and BFINAL);
+// otherwise the host walks the chain (zles.cu).  total[0] = sum of out_len.
 __global__ void __launch_bounds__(256)
-k_inf_check(const InfRes *res, const u64 *cand, const u32 *nseg_ptr, u32 nseg_cap, u32 *problems, unsigned long long *total) {
-  const u32 nseg_all = *nseg_ptr;
-  const u32 nseg = umin(nseg_all, nseg_cap);
+k_inf_check(const InfRes *res, const u64 *cand, u32 nseg, u32 *problems, unsigned long long *total) {
   u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   u32 bad = 0;
   u64 len = 0;
-  if (j == 0 && nseg_all > nseg_cap) bad |= 1;
   if (j < nseg) {
     InfRes r = res[j];
     len = r.out_len;
     bool good;
-    if (j + 1 < nseg) good = r.status == SEG_SYNC && r.end_pos == cand[j + 1] && r.out_len == CHUNK;
-    else good = r.status == SEG_FINAL && r.out_len <= CHUNK;
-    if ((r.flags & SEGF_HISTORY) && j > 0) good = false;
+    if (j + 1 < nseg) good = r.status == SEG_SYNC && r.end_pos == cand[j + 1] && r.out_len == SUB;
+    else good = r.status == SEG_FINAL && r.out_len <= SUB;
     if (!good) bad |= 1;
-    if (r.flags & SEGF_OVERFLOW) bad |= 2;
   }
   if (bad) atomicOr(problems, bad);
   if (len) atomicAdd(total, (unsigned long long)len);

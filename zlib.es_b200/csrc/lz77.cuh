@@ -310,17 +310,23 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
           }
         }
         const u32 rmax = __reduce_max_sync(ZLES_FULL, rrun);
+        // Branch-free body: candidate r is entry k-r of the ring; ml = bytes equal from offset 0 (3..7).
         u32 best = 0, full = 0;
+        const u8 *rbase = reinterpret_cast<const u8 *>(ring);
+        u32 off = ((k - 1) & 63) * 8, rkey = 0x340u - 1, bit = 1;  // rkey = 0x300 + (64 - r), bit = 1 << (r - 1)
+#pragma unroll 4
         for (u32 r = 1; r <= rmax; r++) {
-          if (r <= rrun) {
-            const uint2 ce = ring[(k - r) & 63];
-            const u32 xl = lo ^ ce.x, xh = hi ^ ce.y;
-            if ((xl & 0xffffffu) == 0) {               // same 3-byte key (src/lz77.ts:40)
-              const u32 v = (xl >> 24) | (xh << 8);    // bytes 3..6
-              if (v == 0) full |= 1u << (r - 1);
-              else best = umax(best, ((3 + ((u32)(__ffs((int)v) - 1) >> 3)) << 8) | (64 - r));
-            }
-          }
+          const uint2 ce = *reinterpret_cast<const uint2 *>(rbase + off);
+          const u32 xl = lo ^ ce.x, xh = hi ^ ce.y;
+          const u32 v = __funnelshift_r(xl, xh, 24);              // bytes 3..6
+          const bool ok = ((xl & 0xffffffu) == 0) & (r <= rrun);  // same 3-byte key (src/lz77.ts:40), inside run and window
+          const u32 tz = (u32)__clz((int)__brev(v));              // 32 when bytes 3..6 are all equal
+          const u32 key = ((tz << 5) & 0x700u) + rkey;            // (3 + tz / 8) << 8 | (64 - r)
+          if (ok) best = umax(best, key);
+          if (ok & (v == 0)) full |= bit;
+          off = (off - 8) & 511;
+          rkey--;
+          bit <<= 1;
         }
         if (own) {
           const u32 maxlen = umin(MAX_MATCH, L - p);

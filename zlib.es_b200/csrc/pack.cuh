@@ -6,16 +6,18 @@
 // emit loops of deflateDynamicBlock (/root/reference/src/deflate.ts:150-226) plus the block
 // loop of deflate (/root/reference/src/deflate.ts:20-38).
 //
-// Layout of one chunk in the stream (byte aligned, so chunks are written
-// independently — to local memory or straight into a peer GPU's buffer):
-//   [block 0][block 1][block 2][block 3]   dynamic blocks, bit-concatenated, BFINAL=0
-//   000 + pad to byte + 00 00 FF FF        empty stored block = sync marker
-// The last chunk of the stream sets BFINAL on its last block and has no marker.
+// Layout of one deflate block ("segment") in the stream.  Every block is byte aligned, so
+// blocks are written independently — to local memory or straight into a peer GPU's buffer —
+// and can be located and decoded in parallel by inflate.cuh:
+//   [dynamic block, BFINAL=0]  000 + pad to byte + 00 00 FF FF   (empty stored block = sync marker)
+// The last block of the stream sets BFINAL, is padded to a byte (src/deflate.ts:35-37) and has
+// no marker.  A block of chunk-relative index 1..3 may reference the 32 KiB before it (same
+// chunk); index 0 references nothing outside itself.
 //
 // K5 computes every token's code + extra bits (<= 48 bits), a block-wide exclusive
 // scan of the bit lengths gives each token its bit offset, tokens are OR-ed into a
 // shared-memory staging window and the window is written out with aligned,
-// coalesced 32-bit... 128-bit stores (head/tail bytes of a chunk with byte stores).
+// coalesced 32-bit stores (head/tail bytes of a block with byte stores).
 #pragma once
 #include "huffman.cuh"
 #include "zles_dev.h"
@@ -31,14 +33,16 @@ constexpr u32 PACK_SMEM = PACK_STAGE_WORDS * 4 + 320 * 4 + 40 * 4 + 48 * 8;  // 
 struct LayoutParams {
   const u32 *blk_bits;   // [nblocks]
   u32 nblocks;
-  u32 nchunks;
   u32 last_is_final;     // this shard ends the stream
   u64 n;                 // shard length in bytes
   const u64 *adler_part; // [nblocks][2]
-  u64 *chunk_off;        // [nchunks + 1] byte offsets relative to the shard's first byte; [nchunks] = total
-  u32 *blk_bitoff;       // [nblocks] bit offset of the block inside its chunk
+  u64 *blk_off;          // [nblocks + 1] byte offsets relative to the shard's first byte; [nblocks] = total
   u64 *summary;          // [0]=total bytes, [1]=sum d mod p, [2]=sum (n - i) d[i] mod p (i local to the shard)
 };
+
+__host__ __device__ __forceinline__ u32 seg_bytes(u32 bits, bool final_block) {
+  return final_block ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4;
+}
 
 // single CTA
 __global__ void __launch_bounds__(1024) k_layout(const LayoutParams P) {
@@ -47,29 +51,20 @@ __global__ void __launch_bounds__(1024) k_layout(const LayoutParams P) {
   u64 *red = reinterpret_cast<u64 *>(smem_raw + 256);
   u64 carry = 0;
   u64 sa = 0, sb = 0;
-  for (u32 base = 0; base < P.nchunks; base += 1024) {
-    const u32 c = base + threadIdx.x;
+  for (u32 base = 0; base < P.nblocks; base += 1024) {
+    const u32 b = base + threadIdx.x;
     u32 bytes = 0;
-    if (c < P.nchunks) {
-      u32 bits = 0;
-      for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
-        u32 b = c * SUBS_PER_CHUNK + k;
-        if (b < P.nblocks) {
-          P.blk_bitoff[b] = bits;
-          bits += P.blk_bits[b];
-          const u64 off = (u64)b * SUB;
-          const u64 len = umin64((u64)SUB, P.n - off);
-          const u64 A = P.adler_part[2 * (size_t)b], B = P.adler_part[2 * (size_t)b + 1];
-          sa += A;
-          sb += (B + ((P.n - off - len) % ADLER_MOD) * (A % ADLER_MOD)) % ADLER_MOD;
-        }
-      }
-      const bool final_chunk = P.last_is_final && c + 1 == P.nchunks;
-      bytes = final_chunk ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4;
+    if (b < P.nblocks) {
+      bytes = seg_bytes(P.blk_bits[b], P.last_is_final && b + 1 == P.nblocks);
+      const u64 off = (u64)b * SUB;
+      const u64 len = umin64((u64)SUB, P.n - off);
+      const u64 A = P.adler_part[2 * (size_t)b], B = P.adler_part[2 * (size_t)b + 1];
+      sa += A;
+      sb += (B + ((P.n - off - len) % ADLER_MOD) * (A % ADLER_MOD)) % ADLER_MOD;
     }
     u32 total;
     u32 ex = block_exscan(bytes, scratch, &total);
-    if (c < P.nchunks) P.chunk_off[c] = carry + ex;
+    if (b < P.nblocks) P.blk_off[b] = carry + ex;
     carry += total;
   }
 #pragma unroll
@@ -83,7 +78,7 @@ __global__ void __launch_bounds__(1024) k_layout(const LayoutParams P) {
   if (threadIdx.x == 0) {
     u64 ta = 0, tb = 0;
     for (int w = 0; w < 32; w++) { ta += red[w]; tb += red[32 + w]; }
-    P.chunk_off[P.nchunks] = carry;
+    P.blk_off[P.nblocks] = carry;
     P.summary[0] = carry;
     P.summary[1] = ta % ADLER_MOD;
     P.summary[2] = tb % ADLER_MOD;
@@ -96,8 +91,8 @@ struct PackParams {
   const u32 *ntok;         // [nblocks]
   const BlockCodes *codes; // [nblocks]
   const u32 *blk_bits;     // [nblocks]
-  const u64 *chunk_off;    // [nchunks + 1]
-  u32 nblocks, nchunks;
+  const u64 *blk_off;      // [nblocks + 1]
+  u32 nblocks;
   u32 last_is_final;
   u8 *out;                 // destination of this shard's first byte (local or peer memory)
 };
@@ -171,8 +166,8 @@ __device__ __forceinline__ void pack_finish(PackState &st) {
   }
 }
 
-// Appends deflate blocks [b0, b1) — one chunk — and then either the final pad
-// (src/deflate.ts:35-37) or the empty stored block that separates independent chunks.
+// Appends deflate blocks [b0, b1) bit-concatenated and then either the final pad
+// (src/deflate.ts:35-37) or the empty stored block that makes the next block byte aligned.
 __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *tokens, const u32 *ntok, const BlockCodes *codes,
                                            u32 b0, u32 b1, bool final_chunk) {
   const u32 tid = threadIdx.x;
@@ -258,14 +253,11 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(const PackParams P) {
   u32 *stage = reinterpret_cast<u32 *>(smem_raw);
   u32 *ctab = stage + PACK_STAGE_WORDS;  // [320]
   u32 *scratch = ctab + 320;
-  const u32 c = blockIdx.x;
-  if (c >= P.nchunks) return;
+  const u32 b = blockIdx.x;
+  if (b >= P.nblocks) return;
   PackState st;
-  pack_begin(st, stage, scratch, P.out + P.chunk_off[c]);
-  const bool final_chunk = P.last_is_final && c + 1 == P.nchunks;
-  const u32 b0 = c * SUBS_PER_CHUNK;
-  const u32 b1 = umin(b0 + SUBS_PER_CHUNK, P.nblocks);
-  pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b0, b1, final_chunk);
+  pack_begin(st, stage, scratch, P.out + P.blk_off[b]);
+  pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, P.last_is_final && b + 1 == P.nblocks);
   pack_finish(st);
 }
 
@@ -336,23 +328,15 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_batch(const BatchPackPara
   if (i >= P.count) return;
   const u64 len = P.in_off[i + 1] - P.in_off[i];
   const u32 b0 = (u32)P.blk_first[i], b1 = (u32)P.blk_first[i + 1];
-  const u32 nchunks = (b1 - b0 + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
 
   // size of the stream and Adler-32 sums of the buffer
   u64 bytes = 0, sa = 0, sb = 0;
-  for (u32 c = tid; c < nchunks; c += PACK_THREADS) {
-    u64 bits = 0;
-    for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
-      const u32 b = b0 + c * SUBS_PER_CHUNK + k;
-      if (b < b1) {
-        bits += P.blk_bits[b];
-        const u64 off = (u64)(c * SUBS_PER_CHUNK + k) * SUB;
-        const u64 A = P.adler_part[2 * (size_t)b], B = P.adler_part[2 * (size_t)b + 1];
-        sa += A;
-        sb += (B + ((len - off - P.table[b].own_len) % ADLER_MOD) * (A % ADLER_MOD)) % ADLER_MOD;
-      }
-    }
-    bytes += (c + 1 == nchunks) ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4;
+  for (u32 b = b0 + tid; b < b1; b += PACK_THREADS) {
+    const u64 off = (u64)(b - b0) * SUB;
+    const u64 A = P.adler_part[2 * (size_t)b], B = P.adler_part[2 * (size_t)b + 1];
+    sa += A;
+    sb += (B + ((len - off - P.table[b].own_len) % ADLER_MOD) * (A % ADLER_MOD)) % ADLER_MOD;
+    bytes += seg_bytes(P.blk_bits[b], b + 1 == b1);
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
@@ -384,10 +368,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_batch(const BatchPackPara
   for (int k = 0; k < PACK_ITEMS; k++) { bits[k] = 0; nb[k] = 0; }
   if (tid == 0) { bits[0] = 0x9C78u; nb[0] = 16; }  // CMF = 78, FLG = 9C (src/zlib.ts:28-34)
   pack_emit(st, bits, nb);
-  for (u32 c = 0; c < nchunks; c++) {
-    const u32 cb0 = b0 + c * SUBS_PER_CHUNK;
-    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, cb0, umin(cb0 + SUBS_PER_CHUNK, b1), c + 1 == nchunks);
-  }
+  for (u32 b = b0; b < b1; b++) pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, b + 1 == b1);
   nb[0] = 0;
   if (tid == 0) {  // big-endian Adler-32 (src/zlib.ts:36-40)
     bits[0] = ((adler >> 24) & 0xff) | ((adler >> 8) & 0xff00) | ((adler << 8) & 0xff0000) | (adler << 24);

@@ -99,7 +99,7 @@ struct zles_ctx {
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 4, good_len = 8, lazy = 1;
   // deflate workspace
-  DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_bitoff, chunk_off, summary;
+  DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
   DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off;
   // adler / misc
@@ -153,6 +153,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff)");
   e = zrt_set_smem(k_inflate, INF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
+  e = zrt_set_smem(k_inf_tokens, INF_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens)");
   e = zrt_set_smem(k_inflate_batch, INF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate_batch)");
   (void)device;
@@ -185,8 +187,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   if (!c) return;
   zrt_set_device(c->device);
   zrt_sync(c->stream);
-  DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_bitoff,
-                    &c->chunk_off, &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off,
+  DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
   if (c->d_corpus) zrt_free(c->d_corpus);
@@ -270,12 +272,11 @@ extern "C" int zles_adler32(zles_ctx *c, const uint8_t *in, size_t n, uint32_t *
 // ---- deflate (K1..K5) --------------------------------------------------------------------
 
 extern "C" size_t zles_deflate_bound(size_t n) {
-  // every 32 KiB block: <= 3 + 14 + 19*3 + 316*7 header bits and <= 9 bits per literal
-  // (length-limited codes never beat a flat code by less); every 128 KiB chunk: 5 marker bytes.
+  // every 32 KiB block: <= 3 + 14 + 19*3 + 316*7 header bits, <= 9 bits per literal
+  // (an optimal length-limited code is never worse than a flat 8/9-bit one) and 5 marker bytes.
   size_t nblocks = (n + SUB - 1) / SUB;
   if (nblocks == 0) nblocks = 1;
-  size_t nchunks = (nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
-  return 6 + n + (n >> 3) + nblocks * 320 + nchunks * 8 + 64;
+  return 6 + n + (n >> 3) + nblocks * 328 + 64;
 }
 
 static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info) {
@@ -295,8 +296,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   RET(c->adler_part.reserve((size_t)nblocks * 16));
   RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
   RET(c->blk_bits.reserve((size_t)nblocks * 4));
-  RET(c->blk_bitoff.reserve((size_t)nblocks * 4));
-  RET(c->chunk_off.reserve(((size_t)nchunks + 1) * 8));
+  RET(c->blk_off.reserve(((size_t)nblocks + 1) * 8));
   RET(c->summary.reserve(64));
 
   LzParams lp;
@@ -320,12 +320,10 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   LayoutParams yp;
   yp.blk_bits = c->blk_bits.as<u32>();
   yp.nblocks = nblocks;
-  yp.nchunks = nchunks;
   yp.last_is_final = is_last ? 1u : 0u;
   yp.n = n;
   yp.adler_part = c->adler_part.as<u64>();
-  yp.chunk_off = c->chunk_off.as<u64>();
-  yp.blk_bitoff = c->blk_bitoff.as<u32>();
+  yp.blk_off = c->blk_off.as<u64>();
   yp.summary = c->summary.as<u64>();
   LAUNCH(c, k_layout, 1, 1024, LAYOUT_SMEM, yp);
   CK(zrt_last_error());
@@ -343,7 +341,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     info->raw_bytes = n;
     info->adler_a = c->mail->summary[1];
     info->adler_b = c->mail->summary[2];
-    info->n_chunks = nchunks;
+    info->n_blocks = nblocks;
   }
   return 0;
 }
@@ -355,12 +353,11 @@ static int deflate_phase2(zles_ctx *c, u8 *d_dst) {
   pp.ntok = c->ntok.as<u32>();
   pp.codes = c->codes.as<BlockCodes>();
   pp.blk_bits = c->blk_bits.as<u32>();
-  pp.chunk_off = c->chunk_off.as<u64>();
+  pp.blk_off = c->blk_off.as<u64>();
   pp.nblocks = c->p1_nblocks;
-  pp.nchunks = c->p1_nchunks;
   pp.last_is_final = c->p1_final ? 1u : 0u;
   pp.out = d_dst;
-  LAUNCH(c, k_pack, c->p1_nchunks, PACK_THREADS, PACK_SMEM, pp);
+  LAUNCH(c, k_pack, c->p1_nblocks, PACK_THREADS, PACK_SMEM, pp);
   CK(zrt_last_error());
   return 0;
 }
@@ -398,9 +395,9 @@ extern "C" int zles_dev_deflate_phase1(zles_ctx *c, const uint8_t *d_in, size_t 
   RET(resolve_ctx(c));
   return deflate_phase1(c, d_in, n, is_last_shard, info);
 }
-extern "C" int zles_dev_deflate_chunk_offsets(zles_ctx *c, const uint64_t **d_offsets) {
+extern "C" int zles_dev_deflate_block_offsets(zles_ctx *c, const uint64_t **d_offsets) {
   if (!c || !d_offsets || !c->p1_valid) return ZLES_E_ARG;
-  *d_offsets = c->chunk_off.as<u64>();
+  *d_offsets = c->blk_off.as<u64>();
   return 0;
 }
 extern "C" int zles_dev_deflate_phase2(zles_ctx *c, uint8_t *d_dst) {
@@ -463,8 +460,8 @@ static int seg_status_to_code(u32 st) {
 struct InfCtl {
   u32 ncand;
   u32 counter;
-  u32 ok;
-  u32 pad;
+  u32 ok;        // problem bits of k_inf_check
+  u32 ok_res;    // problem bits of k_inf_resolve
   unsigned long long total;
 };
 
@@ -475,99 +472,118 @@ static u32 inflate_grid(const zles_ctx *c, u64 nseg) {
   return (u32)(want < cap ? want : cap);
 }
 
-// Decodes the raw deflate data that starts at byte `first` of d_in[0..n).  On success *out_len = decoded size.
-// ZLES_E_OUTPUT_FULL: *out_len = size needed.
-static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
-  // 1. candidate segment starts: `first` and every position that follows a 00 00 FF FF marker
+// Step 1 of inflate: candidate segment starts = `first` and every position that follows a
+// 00 00 FF FF marker.  Leaves them in c->cand (device) and returns their number; *cand_cap is the
+// list capacity (more candidates than that: not one of our streams).
+static int inflate_scan(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 *ncand_all, u32 *cand_cap_out) {
   const u64 nvec = ((u64)n + 15) >> 4;
   const u32 ntiles = (u32)((nvec + MARK_THREADS - 1) / MARK_THREADS);
   RET(c->ctl.reserve(sizeof(InfCtl)));
   InfCtl *ctl = c->ctl.as<InfCtl>();
   RET(c->tile_cnt.reserve(((size_t)ntiles + 1) * 4));
-  // Our own streams have one marker per 128 KiB of input (>= ~100 B of stream even for zeros).  Streams
-  // with more candidates than n / 64 are somebody else's and take the sequential path below.
-  const u64 cand_cap64 = (u64)n / 64 + 64;
+  // Our own streams have one marker per 32 KiB of input (>= ~40 B of stream even for zeros).  Streams
+  // with more candidates than n / 32 are somebody else's and take the sequential path.
+  const u64 cand_cap64 = (u64)n / 32 + 64;
   if (cand_cap64 > 0x7fffffffull) return ZLES_E_ARG;
   const u32 cand_cap = (u32)cand_cap64;
   RET(c->cand.reserve((size_t)cand_cap * 8));
-  RET(c->res.reserve((size_t)cand_cap * sizeof(InfRes)));
   CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
-  u32 *d_ncand = &ctl->ncand;
   if (ntiles) {
     LAUNCH(c, k_mark_count, ntiles, MARK_THREADS, 64 * 4, d_in, (u64)n, first, c->tile_cnt.as<u32>());
-    LAUNCH(c, k_mark_scan, 1, 1024, 64 * 4, c->tile_cnt.as<u32>(), ntiles, d_ncand);
+    LAUNCH(c, k_mark_scan, 1, 1024, 64 * 4, c->tile_cnt.as<u32>(), ntiles, &ctl->ncand);
     LAUNCH(c, k_mark_emit, ntiles, MARK_THREADS, 64 * 4, d_in, (u64)n, first, (const u32 *)c->tile_cnt.as<u32>(), c->cand.as<u64>(),
            cand_cap);
   } else {
-    LAUNCH(c, k_mark_none, 1, 32, 0, first, c->cand.as<u64>(), d_ncand);
+    LAUNCH(c, k_mark_none, 1, 32, 0, first, c->cand.as<u64>(), &ctl->ncand);
   }
-  // 2. optimistic parallel decode: segment j writes at j * CHUNK
-  const u64 guess_seg = (u64)n / 2048 + 1;  // launch width only; the kernel reads the real count
-  LAUNCH(c, k_inflate, inflate_grid(c, guess_seg), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(),
-         (const u64 *)nullptr, (const u32 *)d_ncand, cand_cap, d_out, (u64)cap, 1, c->res.as<InfRes>(), &ctl->counter);
-  LAUNCH(c, k_inf_check, (cand_cap + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(),
-         (const u32 *)d_ncand, cand_cap, &ctl->ok, &ctl->total);
   CK(zrt_last_error());
-  InfCtl h;
-  CK(zrt_d2h(&c->mail->summary[0], ctl, sizeof(InfCtl), c->stream));
+  CK(zrt_d2h(&c->mail->ncand, &ctl->ncand, 4, c->stream));
   CK(zrt_sync(c->stream));
-  memcpy(&h, &c->mail->summary[0], sizeof(InfCtl));
-  if (h.ok == 0) {  // InfCtl::ok collects problem bits (k_inf_check)
-    *out_len = (size_t)h.total;
-    return 0;
-  }
-  if (h.ok == 2) {  // everything consistent, only the output did not fit
-    *out_len = (size_t)h.total;
-    return ZLES_E_OUTPUT_FULL;
-  }
+  *ncand_all = c->mail->ncand;
+  *cand_cap_out = cand_cap;
+  return 0;
+}
 
-  // 3. the optimistic layout was wrong (false marker, foreign stream, error).  Walk the chain of
-  //    segments on the host: segment 0 is real; the segment after it starts where it ended.
-  const u32 ncand = h.ncand < cand_cap ? h.ncand : cand_cap;
-  bool chain_ok = h.ncand <= cand_cap;
-  std::vector<InfRes> res(ncand);
-  std::vector<u64> cand(ncand);
-  CK(zrt_d2h(res.data(), c->res.p, (size_t)ncand * sizeof(InfRes), c->stream));
-  CK(zrt_d2h(cand.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+static int read_ctl(zles_ctx *c, InfCtl *h) {
+  CK(zrt_d2h(&c->mail->summary[0], c->ctl.p, sizeof(InfCtl), c->stream));
   CK(zrt_sync(c->stream));
-  std::vector<u64> pos, off;
-  u64 total = 0;
-  if (chain_ok) {
-    size_t j = 0;
-    for (;;) {
-      const InfRes &r = res[j];
-      if ((r.flags & SEGF_HISTORY) && j != 0) { chain_ok = false; break; }
-      if (r.status != SEG_SYNC && r.status != SEG_FINAL) { chain_ok = false; break; }
-      pos.push_back(cand[j]);
-      off.push_back(total);
-      total += r.out_len;
-      if (r.status == SEG_FINAL) break;
-      // next real segment: the candidate equal to this segment's end
-      size_t lo = j + 1, hi = ncand;
-      while (lo < hi) {
-        size_t mid = (lo + hi) >> 1;
-        if (cand[mid] < r.end_pos) lo = mid + 1; else hi = mid;
-      }
-      if (lo >= ncand || cand[lo] != r.end_pos) { chain_ok = false; break; }
-      j = lo;
-    }
+  memcpy(h, &c->mail->summary[0], sizeof(InfCtl));
+  return 0;
+}
+
+// Steps 2.. of inflate.  On success *out_len = decoded size.  ZLES_E_OUTPUT_FULL: *out_len = size needed.
+static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 ncand_all, u32 cand_cap, u8 *d_out, size_t cap,
+                          size_t *out_len) {
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  bool fast = ncand_all >= 1 && ncand_all <= cand_cap;
+  const u32 ncand = ncand_all;
+  if (fast) {  // workspace for phase A; failing to get it only costs the fast path
+    if (c->tokens.reserve((size_t)ncand * SUB * 4) || c->ntok.reserve((size_t)ncand * 4) || c->res.reserve((size_t)ncand * sizeof(InfRes)))
+      fast = false;
   }
-  if (chain_ok) {
-    *out_len = (size_t)total;
-    if (total > cap) return ZLES_E_OUTPUT_FULL;
-    const u32 nseg = (u32)pos.size();
-    RET(c->seg_pos.reserve((size_t)nseg * 8));
-    RET(c->seg_off.reserve((size_t)nseg * 8));
-    CK(zrt_h2d(c->seg_pos.p, pos.data(), (size_t)nseg * 8, c->stream));
-    CK(zrt_h2d(c->seg_off.p, off.data(), (size_t)nseg * 8, c->stream));
-    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
-    CK(zrt_h2d(&ctl->ncand, &nseg, 4, c->stream));
-    CK(zrt_sync(c->stream));  // pos/off/nseg are stack or heap memory
-    LAUNCH(c, k_inflate, inflate_grid(c, nseg), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->seg_pos.as<u64>(),
-           (const u64 *)c->seg_off.as<u64>(), (const u32 *)d_ncand, nseg, d_out, (u64)cap, 1, c->res.as<InfRes>(), &ctl->counter);
+  if (fast) {
+    // 2. phase A on every candidate, acceptance check, and — optimistically — phase B with candidate j
+    //    taken as block j of the stream (true unless a marker pattern occurs inside compressed data)
+    LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
+           c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+    LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
+           &ctl->ok, &ctl->total);
+    const u32 nchunks = (ncand + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+    const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only
+    if (room)
+      LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, 0, (const u32 *)c->tokens.as<u32>(),
+             (const u32 *)c->ntok.as<u32>(), (const u32 *)nullptr, ncand, d_out, (u64)cap, &ctl->ok_res);
     CK(zrt_last_error());
-    CK(zrt_sync(c->stream));
-    return 0;
+    InfCtl h;
+    RET(read_ctl(c, &h));
+    if (h.ok == 0) {
+      *out_len = (size_t)h.total;
+      if (!room || h.total > cap || h.ok_res == 2) return ZLES_E_OUTPUT_FULL;
+      if (h.ok_res == 0) return 0;
+      // a reference before the start of a chunk: not ours after all -> sequential path
+    } else {
+      // 3. some candidate is not a block start.  Where a segment ends and how much it stands for do not
+      //    depend on the others, so walk the chain on the host: candidate 0 is real, the next real one
+      //    starts where it ended.
+      std::vector<InfRes> res(ncand);
+      std::vector<u64> cand(ncand);
+      CK(zrt_d2h(res.data(), c->res.p, (size_t)ncand * sizeof(InfRes), c->stream));
+      CK(zrt_d2h(cand.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+      CK(zrt_sync(c->stream));
+      std::vector<u32> list;
+      u64 total = 0;
+      bool chain_ok = true;
+      for (size_t j = 0;;) {
+        const InfRes &r = res[j];
+        if (r.status != SEG_SYNC && r.status != SEG_FINAL) { chain_ok = false; break; }
+        if (r.status == SEG_SYNC && r.out_len != SUB) { chain_ok = false; break; }
+        list.push_back((u32)j);
+        total += r.out_len;
+        if (r.status == SEG_FINAL) break;
+        size_t lo = j + 1, hi = ncand;
+        while (lo < hi) {
+          size_t mid = (lo + hi) >> 1;
+          if (cand[mid] < r.end_pos) lo = mid + 1; else hi = mid;
+        }
+        if (lo >= ncand || cand[lo] != r.end_pos) { chain_ok = false; break; }
+        j = lo;
+      }
+      if (chain_ok) {
+        *out_len = (size_t)total;
+        if (total > cap) return ZLES_E_OUTPUT_FULL;
+        const u32 nseg = (u32)list.size();
+        RET(c->seg_pos.reserve((size_t)nseg * 4));
+        CK(zrt_h2d(c->seg_pos.p, list.data(), (size_t)nseg * 4, c->stream));
+        CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+        CK(zrt_sync(c->stream));  // list is host heap memory
+        const u32 nch = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+        LAUNCH(c, k_inf_resolve, (nch + RES_WARPS - 1) / RES_WARPS, RES_THREADS, 0, (const u32 *)c->tokens.as<u32>(),
+               (const u32 *)c->ntok.as<u32>(), (const u32 *)c->seg_pos.as<u32>(), nseg, d_out, (u64)cap, &ctl->ok_res);
+        CK(zrt_last_error());
+        RET(read_ctl(c, &h));
+        if (h.ok_res == 0) return 0;
+      }
+    }
   }
 
   // 4. sequential decode of the whole stream on one warp: exactly the reference's order of
@@ -577,13 +593,14 @@ static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_
     const u64 zero = 0;
     RET(c->seg_pos.reserve(8));
     RET(c->seg_off.reserve(8));
+    RET(c->res.reserve(sizeof(InfRes)));
     CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
     CK(zrt_h2d(&ctl->ncand, &one, 4, c->stream));
     CK(zrt_h2d(c->seg_pos.p, &first, 8, c->stream));
     CK(zrt_h2d(c->seg_off.p, &zero, 8, c->stream));
     CK(zrt_sync(c->stream));
     LAUNCH(c, k_inflate, 1, INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->seg_pos.as<u64>(), (const u64 *)c->seg_off.as<u64>(),
-           (const u32 *)d_ncand, 1u, d_out, (u64)cap, 0, c->res.as<InfRes>(), &ctl->counter);
+           (const u32 *)&ctl->ncand, 1u, d_out, (u64)cap, 0, c->res.as<InfRes>(), &ctl->counter);
     CK(zrt_last_error());
     CK(zrt_d2h(&c->mail->res0, c->res.p, sizeof(InfRes), c->stream));
     CK(zrt_sync(c->stream));
@@ -593,6 +610,12 @@ static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_
     if (r.flags & SEGF_OVERFLOW) return ZLES_E_OUTPUT_FULL;
     return 0;
   }
+}
+
+static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
+  u32 ncand = 0, cand_cap = 0;
+  RET(inflate_scan(c, d_in, n, first, &ncand, &cand_cap));
+  return inflate_decode(c, d_in, n, first, ncand, cand_cap, d_out, cap, out_len);
 }
 
 // header check of zlib.inflate (src/zlib.ts:12-16): only CM is looked at.
@@ -644,11 +667,15 @@ extern "C" int zles_inflate_alloc(zles_ctx *c, const uint8_t *in, size_t n, uint
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
   if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
-  // first guess: the reference's own initial capacity, 10 x input (src/inflate.ts:17); retry once with the exact size
+  // capacity: the reference's own initial guess, 10 x input (src/inflate.ts:17), or what our own format
+  // implies (32 KiB per marker-delimited block), whichever is larger; retry once with the exact size
+  u32 ncand = 0, cand_cap = 0;
+  RET(inflate_scan(c, c->d_in.as<u8>(), n, 2, &ncand, &cand_cap));
   size_t cap = n * 10 + CHUNK;
+  if (ncand <= cand_cap && (size_t)ncand * SUB > cap) cap = (size_t)ncand * SUB;
   size_t need = 0;
   RET(c->d_out.reserve(cap + 16));
-  int rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, &need);
+  int rc = inflate_decode(c, c->d_in.as<u8>(), n, 2, ncand, cand_cap, c->d_out.as<u8>(), cap, &need);
   if (rc == ZLES_E_OUTPUT_FULL) {
     cap = need;
     RET(c->d_out.reserve(cap + 16));

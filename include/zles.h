@@ -58,6 +58,16 @@ int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
 int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);
+/* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the context's
+ * stream; zles_ctx_kernel_time returns the summed duration and launch count of one kernel
+ * (e.g. "k_lz") since timing was switched on.  Both calls synchronise the stream. */
+int zles_ctx_set_timing(zles_ctx *ctx, int on);
+int zles_ctx_kernel_time(zles_ctx *ctx, const char *kernel, double *ms_total, uint64_t *launches);
+/* Plain device memory (cudaMalloc/cudaFree), e.g. for a buffer that is exported with zles_ipc_export,
+ * and a synchronous copy between any two device / host / peer-mapped pointers. */
+int zles_dev_alloc(zles_ctx *ctx, size_t n, void **d_ptr);
+int zles_dev_free(zles_ctx *ctx, void *d_ptr);
+int zles_dev_copy(zles_ctx *ctx, void *dst, const void *src, size_t n);
 
 /* ---- the drop-in pair: host buffers in, host buffers out ----------------------
  * zles_deflate   replaces zlib.deflate  (/root/reference/src/zlib.ts:25-49)
@@ -114,7 +124,8 @@ int zles_dev_deflate_phase2(zles_ctx *ctx, uint8_t *d_dst);
 /* Combine the per-shard sums of all ranks (in rank order) into the stream's Adler-32. */
 uint32_t zles_adler32_combine_shards(const zles_shard_info *infos, uint32_t count);
 /* Inflate `n` bytes of marker-delimited blocks that start at a 128 KiB chunk boundary of the
- * original data (no zlib header); used by the sharded inflate. */
+ * original data (no zlib header); used by the sharded inflate.  has_final = 0: the bytes are a
+ * shard that ends on a block boundary before the stream's last block. */
 int zles_dev_inflate_segment(zles_ctx *ctx, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
                              size_t *out_len);
 

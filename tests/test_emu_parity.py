@@ -1,0 +1,112 @@
+"""The CUDA sources run through the CPU thread emulator (tests/emu) at small sizes.
+
+This is NOT the parity gate (that is tests/test_gpu_*.py on a B200); it keeps the kernels'
+logic — barriers, warp votes, indexing, the host-side chain walk — checked in a container
+without a GPU.  The emulator library is loaded only here (tests/emu_lib.py).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+import emu_lib
+import oracle as O
+import parity_cases as P
+import vectors as T
+
+pytestmark = pytest.mark.emu
+
+
+@pytest.fixture(scope="module")
+def c():
+    return emu_lib.codec()
+
+
+def test_inflate_kats(c):
+    P.inflate_kats(c)
+
+
+def test_inflate_fixture(c):
+    P.inflate_fixture(c)
+
+
+def test_adler(c):
+    P.adler_kats(c)
+    for n in (1, 15, 16, 17, 4095, 70001):
+        d = T.gen("G3", n)
+        assert c.adler32(d) == O.adler32(d)
+
+
+@pytest.mark.parametrize("name,n", [("RAW", 0), ("REPEAT", 0), ("G1", 0), ("G1", 1), ("G1", 2), ("G1", 3), ("G1", 4096), ("G2", 4096),
+                                    ("G3", 4096), ("G4", 4096), ("G5", 4096), ("G5", 32768), ("G5", 32769), ("G5", 70000), ("G1", 131073),
+                                    ("G5", 140000), ("G2", 200000)])
+def test_deflate_roundtrip(c, name, n):
+    data = T.gen(name, n)
+    # size bound: only where one 32 KiB block's header is not the bulk of the output (see DESIGN.md "size")
+    P.roundtrip(c, data, check_size=name in ("RAW", "REPEAT", "G3", "G5") or n <= 4096)
+
+
+def test_fixture_roundtrip_and_size(c):
+    z = P.roundtrip(c, T.fixture_raw())
+    assert len(z) <= 1.03 * T.V["fixture"]["oracle_deflate_size"] if "oracle_deflate_size" in T.V["fixture"] else True
+
+
+def test_inflate_reference_streams(c):
+    # zlib.es's own output: bit-concatenated 128 KiB blocks, no markers -> sequential path
+    for name, n in [("G5", 4096), ("G5", 140000), ("G1", 131074)]:
+        P.inflate_matches_oracle(c, O.deflate(T.gen(name, n)))
+
+
+def test_inflate_system_zlib_streams(c):
+    data = T.gen("G5", 30000) + T.fixture_raw()[:40000]
+    for level in (0, 1, 6, 9):
+        P.inflate_matches_oracle(c, zlib.compress(data, level))
+    co = zlib.compressobj(6)
+    z = co.compress(data[:20000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[20000:]) + co.flush(zlib.Z_FULL_FLUSH) + co.flush()
+    P.inflate_matches_oracle(c, z)  # markers with history across them: must not be taken for our format
+
+
+def test_lenient_and_errors(c):
+    P.lenient_like_reference(c)
+    P.error_strings(c)
+
+
+def test_false_marker_in_payload(c):
+    # the marker bytes 00 00 FF FF inside a stored block are not block boundaries
+    payload = (b"\x00\x00\xff\xff" * 50 + b"abc") * 20
+    P.inflate_matches_oracle(c, zlib.compress(payload, 0))
+
+
+def test_batch(c):
+    bufs = [T.gen("G5", 4096), b"", T.gen("G1", 100), T.gen("G3", 5000), T.gen("G5", 40000), b"x"]
+    zs = c.deflate_batch(bufs)
+    for b, z in zip(bufs, zs):
+        assert zlib.decompress(z) == b
+        assert z == c.deflate(b)  # a batch entry is exactly the single-call stream
+    assert c.inflate_batch(zs) == bufs
+    mixed = [zlib.compress(bufs[0], 6), O.deflate(bufs[3]), zs[4]]
+    assert c.inflate_batch(mixed) == [bufs[0], bufs[3], bufs[4]]
+    res = c.inflate_batch([zs[0], b"\x77\x00"], raise_on_error=False)
+    assert res[0] == bufs[0] and str(res[1]) == "Not compressed by deflate"
+
+
+def test_sharded_phases_match_single_call(c):
+    # independent chunks: compressing shards separately and concatenating gives the single-call bytes
+    import zles
+    from zles import _capi
+    data = T.gen("G5", 300000)
+    whole = c.deflate(data)
+    cuts = [0, 131072, 262144, len(data)]
+    arr = np.frombuffer(data, dtype=np.uint8)
+    infos, parts = [], []
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        seg = np.ascontiguousarray(arr[a:b])
+        info = c.dev_deflate_phase1(seg.ctypes.data, b - a, k == len(cuts) - 2)
+        out = np.zeros(info.comp_bytes + 8, dtype=np.uint8)
+        c.dev_deflate_phase2(out.ctypes.data)
+        parts.append(out[:info.comp_bytes].tobytes())
+        infos.append(info)
+    adler = zles.codec.combine_adler(infos, c.L)
+    stream = b"\x78\x9c" + b"".join(parts) + adler.to_bytes(4, "big")
+    assert stream == whole
+    assert zlib.decompress(stream) == data

@@ -1,0 +1,184 @@
+"""Parity of the CUDA path (libzles.so on a B200, through the C ABI) against the oracle.
+
+Restates /root/reference/test/index.js: the 4 inflate known-answer vectors, and deflate
+round trips through our inflate, the oracle's restatement of the reference's inflate and
+system zlib (Node's inflateSync stand-in), plus SURVEY.md §8c inputs, edge lengths, the
+lenient behaviours of the reference's inflate and the size bound (<= 1.03 x oracle).
+Bar: bit-exact (byte / integer work, no tolerance).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity_cases as P
+import vectors as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c():
+    import zles
+    return zles.Codec(0)
+
+
+def test_native_library_is_loaded(c):
+    import zles
+    assert zles._capi.LIB_PATH.endswith("zlib.es_b200/libzles.so")
+    assert c.launches == 0 or c.launches > 0
+    before = c.launches
+    c.adler32(b"abc")
+    assert c.launches > before  # kernels really launched
+
+
+def test_inflate_kats(c):
+    P.inflate_kats(c)
+
+
+def test_inflate_fixture(c):
+    P.inflate_fixture(c)
+
+
+def test_adler_kats_and_sizes(c):
+    P.adler_kats(c)
+    assert c.adler32(T.fixture_raw()) == 0x140FA15B
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 15, 16, 17, 31, 4095, 4096, 65521, 131072, 1 << 20, (1 << 24) + 13):
+        d = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        assert c.adler32(d) == zlib.adler32(d)
+    d = b"\xff" * (1 << 24)  # largest per-byte value: exercises the deferred modulo
+    assert c.adler32(d) == zlib.adler32(d)
+
+
+@pytest.mark.parametrize("row", T.V["model_table"], ids=lambda r: "%s-%d" % (r[0], r[1]))
+def test_deflate_model_table(c, row):
+    name, n = row[0], row[1]
+    data = T.gen(name, n)
+    # the 3 % size bound is checked where a 32 KiB block header is not the bulk of the output (DESIGN.md "Size")
+    degenerate = name in ("G1", "G2", "G4") and n > 4096
+    P.roundtrip(c, data, check_size=not degenerate)
+
+
+@pytest.mark.parametrize("n", [0, 1, 131073, 262145])
+def test_lengths_on_which_the_reference_throws(c, n):
+    # zlib.es throws for these; we return a valid stream (documented difference)
+    P.roundtrip(c, T.gen("G5", n), check_size=False)
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 255, 256, 257, 258, 259, 32767, 32768, 32769, 65535, 65536, 131071, 131072, 131074, 400000])
+def test_ragged_lengths(c, n):
+    P.roundtrip(c, T.gen("G5", n))
+
+
+def test_long_matches_and_overlaps(c):
+    for d in (bytes(300000), b"a" * 70000, b"ab" * 50000, b"abc" * 40000, T.repeat_input() * 40, bytes(range(256)) * 600):
+        P.roundtrip(c, d, check_size=False)
+
+
+def test_incompressible(c):
+    rng = np.random.default_rng(2)
+    d = rng.integers(0, 256, size=300001, dtype=np.uint8).tobytes()
+    z = P.roundtrip(c, d)
+    assert len(z) < len(d) * 1.01
+
+
+def test_skewed_histograms_deep_trees(c):
+    # Fibonacci-like byte frequencies force Huffman trees deeper than 15 (7 for the code-length code):
+    # the length-limited construction must still give complete codes that zlib accepts
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    rng = np.random.default_rng(3)
+    syms = np.repeat(np.arange(24, dtype=np.uint8) * 7 + 3, fib)
+    for size in (32768, 100000):
+        d = rng.permutation(np.resize(syms, size)).tobytes()
+        P.roundtrip(c, d, check_size=False)
+
+
+def test_inflate_reference_streams(c):
+    # streams made by (the restatement of) zlib.es itself: bit-concatenated blocks, no markers
+    for name, n in [("RAW", 0), ("REPEAT", 0), ("G5", 4096), ("G5", 200000), ("G1", 131074), ("G3", 65536), ("FIXTURE", 0)]:
+        P.inflate_matches_oracle(c, O.deflate(T.gen(name, n)))
+
+
+def test_inflate_system_zlib_streams(c):
+    data = T.gen("G5", 50000) + T.fixture_raw()[:150000]
+    for level in range(0, 10):
+        P.inflate_matches_oracle(c, zlib.compress(data, level))
+    co = zlib.compressobj(6)
+    z = co.compress(data[:20000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[20000:90000]) + co.flush(zlib.Z_FULL_FLUSH)
+    z += co.compress(data[90000:]) + co.flush()
+    P.inflate_matches_oracle(c, z)
+    co = zlib.compressobj(9, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)
+    P.inflate_matches_oracle(c, co.compress(data) + co.flush())  # fixed Huffman blocks only
+
+
+def test_lenient_and_errors(c):
+    P.lenient_like_reference(c)
+    P.error_strings(c)
+
+
+def test_truncated_streams_raise(c):
+    z = c.deflate(T.gen("G5", 100000))
+    for cut in (len(z) // 3, len(z) - 10):
+        with pytest.raises(Exception):
+            c.inflate(z[:cut])
+        with pytest.raises(O.OracleError):
+            O.inflate(z[:cut])
+
+
+def test_marker_bytes_inside_data(c):
+    payload = (b"\x00\x00\xff\xff" * 50 + b"abc") * 2000
+    P.inflate_matches_oracle(c, zlib.compress(payload, 0))  # stored blocks: the pattern appears verbatim
+    P.roundtrip(c, payload, check_size=False)
+    # our own stream with a marker pattern spliced between two blocks' worth of compressed bytes cannot
+    # be built by hand; instead check that removing candidates is exercised: a stream = ours + foreign tail
+    z = c.deflate(T.gen("G5", 100000))
+    assert c.inflate(z + b"\x00\x00\xff\xff" * 8) == T.gen("G5", 100000)
+
+
+def test_batch(c):
+    rng = np.random.default_rng(4)
+    bufs = [T.gen("G5", 4096), b"", T.gen("G1", 100), T.gen("G3", 5000), T.gen("G5", 140000), b"x", T.fixture_raw()[:4096 * 3]]
+    bufs += [rng.integers(0, 64, size=int(n), dtype=np.uint8).tobytes() for n in rng.integers(0, 9000, size=200)]
+    zs = c.deflate_batch(bufs)
+    assert len(zs) == len(bufs)
+    for b, z in zip(bufs[:20], zs[:20]):
+        assert zlib.decompress(z) == b and O.inflate(z) == b
+        assert z == c.deflate(b)
+    for b, z in zip(bufs, zs):
+        assert zlib.decompress(z) == b
+    assert c.inflate_batch(zs) == bufs
+    foreign = [zlib.compress(b, 6) for b in bufs[:10]] + [O.deflate(bufs[3])]
+    assert c.inflate_batch(foreign) == bufs[:10] + [bufs[3]]
+    res = c.inflate_batch([zs[0], b"\x77\x00", b"\x78\x9c\x07"], raise_on_error=False)
+    assert res[0] == bufs[0] and str(res[1]) == "Not compressed by deflate" and str(res[2]) == "Not supported BTYPE : 3"
+
+
+def test_sharded_phases_match_single_call(c):
+    import torch
+    import zles
+    data = T.fixture_raw() + T.gen("G5", 300000)
+    whole = c.deflate(data)
+    cuts = [0, 131072, 131072 * 3, len(data)]
+    src = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    infos, parts = [], []
+    for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        info = c.dev_deflate_phase1(src.data_ptr() + a, b - a, k == len(cuts) - 2)
+        out = torch.zeros(info.comp_bytes + 8, dtype=torch.uint8, device="cuda")
+        c.dev_deflate_phase2(out.data_ptr())
+        parts.append(out[:info.comp_bytes].cpu().numpy().tobytes())
+        infos.append(info)
+    adler = zles.codec.combine_adler(infos)
+    stream = b"\x78\x9c" + b"".join(parts) + adler.to_bytes(4, "big")
+    assert stream == whole
+    assert zlib.decompress(stream) == data
+    # sharded inflate: every shard decodes on its own
+    for k, part in enumerate(parts):
+        d_in = torch.frombuffer(bytearray(part), dtype=torch.uint8).cuda()
+        d_out = torch.zeros(cuts[k + 1] - cuts[k], dtype=torch.uint8, device="cuda")
+        n = c.dev_inflate_segment(d_in.data_ptr(), len(part), d_out.data_ptr(), d_out.numel(), has_final=k == len(parts) - 1)
+        assert n == cuts[k + 1] - cuts[k]
+        assert d_out.cpu().numpy().tobytes() == data[cuts[k]:cuts[k + 1]]

@@ -36,6 +36,11 @@ PROTOTYPES = {
     "zles_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "zles_ctx_set_level": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "zles_ctx_launches": (ctypes.c_uint64, [c_vp]),
+    "zles_ctx_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "zles_ctx_kernel_time": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "zles_dev_alloc": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "zles_dev_free": (ctypes.c_int, [c_vp, c_vp]),
+    "zles_dev_copy": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
     "zles_deflate_bound": (ctypes.c_size_t, [ctypes.c_size_t]),
     "zles_deflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
     "zles_inflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),

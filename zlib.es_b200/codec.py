@@ -81,6 +81,41 @@ class Codec:
     def launches(self) -> int:
         return int(self.L.zles_ctx_launches(self.h))
 
+    def set_timing(self, on: bool):
+        self._check(self.L.zles_ctx_set_timing(self.h, 1 if on else 0))
+
+    def kernel_time(self, kernel: str) -> tuple[float, int]:
+        """(summed device milliseconds, launches) of one kernel since set_timing(True)."""
+        ms = ctypes.c_double()
+        n = ctypes.c_uint64()
+        self._check(self.L.zles_ctx_kernel_time(self.h, kernel.encode(), ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, int(n.value)
+
+    def dev_alloc(self, n: int) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.L.zles_dev_alloc(self.h, n, ctypes.byref(p)))
+        return int(p.value)
+
+    def dev_free(self, ptr: int):
+        self._check(self.L.zles_dev_free(self.h, ctypes.c_void_p(ptr)))
+
+    def dev_copy(self, dst: int, src: int, n: int):
+        self._check(self.L.zles_dev_copy(self.h, ctypes.c_void_p(dst), ctypes.c_void_p(src), n))
+
+    def ipc_export(self, ptr: int) -> bytes:
+        buf = (ctypes.c_uint8 * 64)()
+        self._check(self.L.zles_ipc_export(ctypes.c_void_p(ptr), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (ctypes.c_uint8 * 64)(*handle)
+        p = ctypes.c_void_p()
+        self._check(self.L.zles_ipc_open(buf, ctypes.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self.L.zles_ipc_close(ctypes.c_void_p(ptr)))
+
     def deflate_bound(self, n: int) -> int:
         return int(self.L.zles_deflate_bound(n))
 
@@ -223,9 +258,9 @@ class Codec:
     def dev_deflate_phase2(self, d_dst: int):
         self._check(self.L.zles_dev_deflate_phase2(self.h, d_dst))
 
-    def dev_inflate_segment(self, d_in: int, n: int, d_out: int, cap: int) -> int:
+    def dev_inflate_segment(self, d_in: int, n: int, d_out: int, cap: int, has_final: bool = True) -> int:
         olen = ctypes.c_size_t()
-        self._check(self.L.zles_dev_inflate_segment(self.h, d_in, n, 1, d_out, cap, ctypes.byref(olen)))
+        self._check(self.L.zles_dev_inflate_segment(self.h, d_in, n, 1 if has_final else 0, d_out, cap, ctypes.byref(olen)))
         return olen.value
 
     def dev_corpus(self, kind: int, offset: int, d_out: int, n: int):

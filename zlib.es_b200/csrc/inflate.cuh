@@ -656,7 +656,7 @@ __global__ void k_mark_none(u64 first, u64 *cand, u32 *ncand) {
 // segment j+1 and stands for exactly SUB bytes (the last one: <= SUB and BFINAL);
 // otherwise the host walks the chain (zles.cu).  total[0] = sum of out_len.
 __global__ void __launch_bounds__(256)
-k_inf_check(const InfRes *res, const u64 *cand, u32 nseg, u32 *problems, unsigned long long *total) {
+k_inf_check(const InfRes *res, const u64 *cand, u32 nseg, u64 n, u32 has_final, u32 *problems, unsigned long long *total) {
   u32 j = blockIdx.x * blockDim.x + threadIdx.x;
   u32 bad = 0;
   u64 len = 0;
@@ -665,7 +665,8 @@ k_inf_check(const InfRes *res, const u64 *cand, u32 nseg, u32 *problems, unsigne
     len = r.out_len;
     bool good;
     if (j + 1 < nseg) good = r.status == SEG_SYNC && r.end_pos == cand[j + 1] && r.out_len == SUB;
-    else good = r.status == SEG_FINAL && r.out_len <= SUB;
+    else if (has_final) good = r.status == SEG_FINAL && r.out_len <= SUB;
+    else good = r.status == SEG_SYNC && r.end_pos == n && r.out_len == SUB;  // a shard that is not the stream's last
     if (!good) bad |= 1;
   }
   if (bad) atomicOr(problems, bad);

@@ -108,6 +108,13 @@ struct zles_ctx {
   DevBuf d_in, d_out, d_off_in, d_off_out, d_len, d_status;
   HostMail *mail = nullptr;  // pinned
   CorpusTable *d_corpus = nullptr;
+  // per-kernel timing
+  bool timing = false;
+  struct TimedLaunch { const char *name; zrt_event_t e0, e1; };
+  std::vector<TimedLaunch> timed;
+  std::vector<zrt_event_t> event_pool;
+  struct KernelTotal { std::string name; double ms; uint64_t n; };
+  std::vector<KernelTotal> totals;
   // state between phase 1 and phase 2 of a deflate
   bool p1_valid = false;
   u64 p1_n = 0;
@@ -116,11 +123,47 @@ struct zles_ctx {
   u64 p1_comp = 0;
 };
 
+// Per-kernel device timing (zles_ctx_set_timing): an event pair around every launch, read back by
+// zles_ctx_kernel_time.  Off by default; bench.py turns it on to get the dominant kernel's duration.
+static void timing_begin(zles_ctx *c, const char *name);
+static void timing_end(zles_ctx *c);
+
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                        \
   do {                                                                   \
+    if ((ctx)->timing) timing_begin((ctx), #kern);                       \
     ZLES_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);    \
+    if ((ctx)->timing) timing_end((ctx));                                \
     (ctx)->launches++;                                                   \
   } while (0)
+
+static int resolve_ctx(zles_ctx *&c);
+
+static zrt_event_t timing_event(zles_ctx *c) {
+  if (!c->event_pool.empty()) { zrt_event_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+  zrt_event_t e{};
+  zrt_event_create(&e);
+  return e;
+}
+static void timing_begin(zles_ctx *c, const char *name) {
+  zles_ctx::TimedLaunch t{name, timing_event(c), timing_event(c)};
+  zrt_event_record(t.e0, c->stream);
+  c->timed.push_back(t);
+}
+static void timing_end(zles_ctx *c) { zrt_event_record(c->timed.back().e1, c->stream); }
+static void timing_collect(zles_ctx *c) {
+  zrt_sync(c->stream);
+  for (auto &t : c->timed) {
+    float ms = 0;
+    zrt_event_elapsed(&ms, t.e0, t.e1);
+    bool found = false;
+    for (auto &k : c->totals)
+      if (k.name == t.name) { k.ms += ms; k.n++; found = true; break; }
+    if (!found) c->totals.push_back({t.name, (double)ms, 1});
+    c->event_pool.push_back(t.e0);
+    c->event_pool.push_back(t.e1);
+  }
+  c->timed.clear();
+}
 
 // ---- library / context ----------------------------------------------------------------
 
@@ -191,6 +234,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
                     &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
+  timing_collect(c);
+  for (zrt_event_t e : c->event_pool) zrt_event_destroy(e);
   if (c->d_corpus) zrt_free(c->d_corpus);
   if (c->mail) zrt_host_free(c->mail);
   if (c->own_stream) zrt_stream_destroy(c->stream);
@@ -216,6 +261,45 @@ extern "C" int zles_ctx_set_level(zles_ctx *c, uint32_t max_checks, uint32_t min
 }
 
 extern "C" uint64_t zles_ctx_launches(const zles_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int zles_ctx_set_timing(zles_ctx *c, int on) {
+  if (!c) return ZLES_E_ARG;
+  CK(zrt_set_device(c->device));
+  timing_collect(c);
+  c->totals.clear();
+  c->timing = on != 0;
+  return 0;
+}
+
+extern "C" int zles_ctx_kernel_time(zles_ctx *c, const char *kernel, double *ms_total, uint64_t *launches) {
+  if (!c || !kernel || !ms_total || !launches) return ZLES_E_ARG;
+  CK(zrt_set_device(c->device));
+  timing_collect(c);
+  *ms_total = 0;
+  *launches = 0;
+  for (auto &k : c->totals)
+    if (k.name == kernel) { *ms_total = k.ms; *launches = k.n; }
+  return 0;
+}
+
+extern "C" int zles_dev_alloc(zles_ctx *c, size_t n, void **d_ptr) {
+  if (!d_ptr) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  CK(zrt_malloc(d_ptr, n));
+  return 0;
+}
+extern "C" int zles_dev_free(zles_ctx *c, void *d_ptr) {
+  RET(resolve_ctx(c));
+  if (d_ptr) CK(zrt_free(d_ptr));
+  return 0;
+}
+extern "C" int zles_dev_copy(zles_ctx *c, void *dst, const void *src, size_t n) {
+  if ((!dst || !src) && n) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  if (n) CK(zrt_copy(dst, src, n, c->stream));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
 
 static std::mutex g_default_mu;
 static zles_ctx *g_default_ctx = nullptr;
@@ -281,7 +365,17 @@ extern "C" size_t zles_deflate_bound(size_t n) {
 
 static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info) {
   c->p1_valid = false;
-  if (!is_last && (n == 0 || (n % CHUNK) != 0)) return ZLES_E_ARG;
+  if (!is_last && (n % CHUNK) != 0) return ZLES_E_ARG;
+  if (!is_last && n == 0) {  // an empty shard in front of the last one contributes nothing
+    c->p1_valid = true;
+    c->p1_n = 0;
+    c->p1_nblocks = 0;
+    c->p1_nchunks = 0;
+    c->p1_final = 0;
+    c->p1_comp = 0;
+    if (info) memset(info, 0, sizeof(*info));
+    return 0;
+  }
   u64 nb64 = ((u64)n + SUB - 1) / SUB;
   if (nb64 == 0) nb64 = 1;
   if (nb64 > 0x7fffffffull / LZ_NSYM) return ZLES_E_ARG;
@@ -348,6 +442,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
 
 static int deflate_phase2(zles_ctx *c, u8 *d_dst) {
   if (!c->p1_valid) return ZLES_E_ARG;
+  if (c->p1_nblocks == 0) return 0;
   PackParams pp;
   pp.tokens = c->tokens.as<u32>();
   pp.ntok = c->ntok.as<u32>();
@@ -513,7 +608,7 @@ static int read_ctl(zles_ctx *c, InfCtl *h) {
 
 // Steps 2.. of inflate.  On success *out_len = decoded size.  ZLES_E_OUTPUT_FULL: *out_len = size needed.
 static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 ncand_all, u32 cand_cap, u8 *d_out, size_t cap,
-                          size_t *out_len) {
+                          size_t *out_len, bool has_final = true) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   bool fast = ncand_all >= 1 && ncand_all <= cand_cap;
   const u32 ncand = ncand_all;
@@ -527,7 +622,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
            c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
     LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
-           &ctl->ok, &ctl->total);
+           (u64)n, has_final ? 1u : 0u, &ctl->ok, &ctl->total);
     const u32 nchunks = (ncand + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
     const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only
     if (room)
@@ -559,7 +654,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
         if (r.status == SEG_SYNC && r.out_len != SUB) { chain_ok = false; break; }
         list.push_back((u32)j);
         total += r.out_len;
-        if (r.status == SEG_FINAL) break;
+        if (r.status == SEG_FINAL) { if (!has_final) chain_ok = false; break; }
+        if (!has_final && r.end_pos == n) break;
         size_t lo = j + 1, hi = ncand;
         while (lo < hi) {
           size_t mid = (lo + hi) >> 1;
@@ -588,6 +684,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
 
   // 4. sequential decode of the whole stream on one warp: exactly the reference's order of
   //    events (src/inflate.ts:22-37), used for foreign streams and for error reporting.
+  if (!has_final) return ZLES_E_CORRUPTED;  // a shard of one of our streams must have decoded above
   {
     const u32 one = 1;
     const u64 zero = 0;
@@ -612,10 +709,10 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
   }
 }
 
-static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
+static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len, bool has_final = true) {
   u32 ncand = 0, cand_cap = 0;
   RET(inflate_scan(c, d_in, n, first, &ncand, &cand_cap));
-  return inflate_decode(c, d_in, n, first, ncand, cand_cap, d_out, cap, out_len);
+  return inflate_decode(c, d_in, n, first, ncand, cand_cap, d_out, cap, out_len, has_final);
 }
 
 // header check of zlib.inflate (src/zlib.ts:12-16): only CM is looked at.
@@ -640,9 +737,9 @@ extern "C" int zles_dev_inflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint
 extern "C" int zles_dev_inflate_segment(zles_ctx *c, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
                                         size_t *out_len) {
   if ((!d_in && n) || !out_len) return ZLES_E_ARG;
-  (void)has_final;
   RET(resolve_ctx(c));
-  return inflate_body(c, d_in, n, 0, d_out, cap, out_len);
+  if (n == 0 && !has_final) { *out_len = 0; return 0; }
+  return inflate_body(c, d_in, n, 0, d_out, cap, out_len, has_final != 0);
 }
 
 extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {

@@ -32,6 +32,12 @@ static inline const char *zrt_err_str(zrt_err_t) { return "emulator"; }
 template <typename K>
 static inline zrt_err_t zrt_set_smem(K, int) { return 0; }
 static inline int zrt_sm_count(int) { return 4; }
+typedef int zrt_event_t;
+static inline zrt_err_t zrt_event_create(zrt_event_t *e) { *e = 0; return 0; }
+static inline zrt_err_t zrt_event_destroy(zrt_event_t) { return 0; }
+static inline zrt_err_t zrt_event_record(zrt_event_t, zrt_stream_t) { return 0; }
+static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t, zrt_event_t) { *ms = 0; return 0; }
+static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t) { memmove(d, s, n); return 0; }
 #define ZLES_LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
 #else
@@ -56,6 +62,13 @@ template <typename K>
 static inline zrt_err_t zrt_set_smem(K kern, int bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
+typedef cudaEvent_t zrt_event_t;
+static inline zrt_err_t zrt_event_create(zrt_event_t *e) { return cudaEventCreate(e); }
+static inline zrt_err_t zrt_event_destroy(zrt_event_t e) { return cudaEventDestroy(e); }
+static inline zrt_err_t zrt_event_record(zrt_event_t e, zrt_stream_t s) { return cudaEventRecord(e, s); }
+static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t a, zrt_event_t b) { return cudaEventElapsedTime(ms, a, b); }
+// device, host or peer-mapped pointers on either side (unified addressing)
+static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, st); }
 static inline int zrt_sm_count(int dev) {
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;

@@ -1,0 +1,157 @@
+"""Sharded deflate / inflate over the GPUs of one node (one process per GPU).
+
+The reference has no notion of more than one thread; the shape below is SURVEY.md §8(e):
+
+deflate   rank r compresses a contiguous shard of the input (a multiple of 128 KiB except on
+          the last rank) with no communication (phase 1: match finder, code construction,
+          layout).  ONE exchange: an all-gather of 5 x u64 per rank (compressed size, raw size,
+          Adler-32 partial sums, block count) over NCCL.  Every rank then knows every shard's
+          offset in the final stream and phase 2 (the bit packer) stores its blocks straight
+          into the destination buffer on the owning rank through a peer-mapped pointer
+          (CUDA IPC; NVLink P2P stores issued by k_pack itself).  The owner adds the zlib
+          header and the combined Adler-32 trailer (/root/reference/src/zlib.ts:28-46).
+inflate   rank r pulls its shard's compressed bytes from the owner (peer read), decodes them
+          (blocks are byte aligned and chunk-independent) into its local output shard.
+
+The transport that turns "a buffer on rank 0" into a pointer usable by every rank is pluggable:
+``IpcTransport`` (CUDA IPC) is the product path; the CPU tests plug in a shared-memory one.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from .codec import Codec, combine_adler
+
+CHUNK = 131072
+
+
+def shard_bounds(total: int, world: int) -> list[tuple[int, int]]:
+    """Contiguous shards, whole 128 KiB chunks each (the last one takes the ragged tail)."""
+    nchunks = (total + CHUNK - 1) // CHUNK
+    out = []
+    for r in range(world):
+        c0 = nchunks * r // world
+        c1 = nchunks * (r + 1) // world
+        a = min(total, c0 * CHUNK)
+        b = total if r == world - 1 else min(total, c1 * CHUNK)
+        out.append((a, b))
+    return out
+
+
+class IpcTransport:
+    """Destination buffer in rank 0's HBM, mapped into every rank with CUDA IPC."""
+
+    def __init__(self, codec: Codec):
+        self.codec = codec
+        self.base = 0
+        self.owner = False
+
+    def create(self, nbytes: int) -> bytes:
+        self.base = self.codec.dev_alloc(nbytes)
+        self.owner = True
+        return self.codec.ipc_export(self.base)
+
+    def open(self, handle: bytes):
+        self.base = self.codec.ipc_open(handle)
+
+    def close(self):
+        if not self.base:
+            return
+        if self.owner:
+            self.codec.dev_free(self.base)
+        else:
+            self.codec.ipc_close(self.base)
+        self.base = 0
+
+
+@dataclass
+class ShardLayout:
+    offsets: list[int]      # byte offset of each rank's blocks inside the raw deflate data
+    comp: list[int]         # compressed bytes per rank
+    raw: list[int]          # raw bytes per rank
+    total_comp: int         # whole zlib stream length (header + data + trailer)
+    adler: int
+
+
+class ShardedCodec:
+    def __init__(self, codec: Codec, transport, rank: int | None = None, world: int | None = None, group=None,
+                 comm_device: str | torch.device = "cuda"):
+        self.c = codec
+        self.t = transport
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.comm_device = torch.device(comm_device)
+        self.capacity = 0
+        self.layout: ShardLayout | None = None
+
+    # -- destination buffer -----------------------------------------------------------------
+    def setup(self, capacity: int):
+        """Allocate the final-stream buffer on rank 0 and map it everywhere (once, outside any timing)."""
+        self.capacity = capacity
+        box = [None]
+        if self.rank == 0:
+            box[0] = self.t.create(capacity)
+        dist.broadcast_object_list(box, src=0, group=self.group)
+        if self.rank != 0:
+            self.t.open(box[0])
+        dist.barrier(group=self.group)
+
+    def teardown(self):
+        dist.barrier(group=self.group)
+        if self.rank != 0:
+            self.t.close()
+        dist.barrier(group=self.group)
+        if self.rank == 0:
+            self.t.close()
+
+    # -- deflate ------------------------------------------------------------------------------
+    def deflate(self, d_in: int, n_local: int) -> ShardLayout:
+        """All ranks call this with their shard (device pointer).  Afterwards the zlib stream lies at
+        ``self.t.base`` on rank 0 (``layout.total_comp`` bytes)."""
+        info = self.c.dev_deflate_phase1(d_in, n_local, self.rank == self.world - 1)
+        mine = torch.tensor([info.comp_bytes, info.raw_bytes, info.adler_a, info.adler_b, info.n_blocks], dtype=torch.int64,
+                            device=self.comm_device)
+        allv = torch.empty(self.world * 5, dtype=torch.int64, device=self.comm_device)
+        dist.all_gather_into_tensor(allv, mine, group=self.group)  # the one exchange step of the path
+        rows = allv.cpu().view(self.world, 5).tolist()
+        infos = []
+        offsets, comp, raw = [], [], []
+        off = 0
+        for cb, rb, a, b, nb in rows:
+            si = _capi.ShardInfo()
+            si.comp_bytes, si.raw_bytes, si.adler_a, si.adler_b, si.n_blocks = int(cb), int(rb), int(a), int(b), int(nb)
+            infos.append(si)
+            offsets.append(off)
+            comp.append(int(cb))
+            raw.append(int(rb))
+            off += int(cb)
+        total = off + 6
+        if total > self.capacity:
+            raise RuntimeError("destination buffer too small: need %d, have %d" % (total, self.capacity))
+        adler = combine_adler(infos, self.c.L)
+        # phase 2: the packer stores this shard's blocks at their global offset — local memory on rank 0,
+        # peer-mapped memory (NVLink) elsewhere
+        self.c.dev_deflate_phase2(self.t.base + 2 + offsets[self.rank])
+        dist.barrier(group=self.group)
+        if self.rank == 0:  # framing stays on the host (/root/reference/src/zlib.ts:28-46)
+            frame = np.array([0x78, 0x9C, (adler >> 24) & 255, (adler >> 16) & 255, (adler >> 8) & 255, adler & 255], dtype=np.uint8)
+            self.c.dev_copy(self.t.base, frame.ctypes.data, 2)
+            self.c.dev_copy(self.t.base + total - 4, frame.ctypes.data + 2, 4)
+        self.layout = ShardLayout(offsets, comp, raw, total, adler)
+        return self.layout
+
+    # -- inflate ------------------------------------------------------------------------------
+    def inflate(self, d_stage: int, d_out: int, cap: int, layout: ShardLayout | None = None) -> int:
+        """Rank r decodes shard r of the stream at ``self.t.base`` into d_out; d_stage is local scratch of at
+        least layout.comp[rank] bytes.  Returns the decoded length."""
+        lay = layout or self.layout
+        n = lay.comp[self.rank]
+        self.c.dev_copy(d_stage, self.t.base + 2 + lay.offsets[self.rank], n)  # peer read of this shard's bytes
+        return self.c.dev_inflate_segment(d_stage, n, d_out, cap, has_final=self.rank == self.world - 1)

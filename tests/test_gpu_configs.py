@@ -16,8 +16,12 @@ KINDS = {"text": 0, "binary": 1, "random": 2, "mixed": 3}
 
 @pytest.fixture(scope="module")
 def c():
+    import torch
     import zles
-    return zles.Codec(0)
+    codec = zles.Codec(0)
+    # run on torch's current stream: the tests fill device tensors with torch right before calling the codec
+    codec.set_stream(torch.cuda.current_stream().cuda_stream)
+    return codec
 
 
 def _corpus(c, kind, n, offset=0):

@@ -20,8 +20,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def c():
+    import torch
     import zles
-    return zles.Codec(0)
+    codec = zles.Codec(0)
+    # run on torch's current stream: the tests fill device tensors with torch right before calling the codec
+    codec.set_stream(torch.cuda.current_stream().cuda_stream)
+    return codec
 
 
 def test_native_library_is_loaded(c):

@@ -278,6 +278,14 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) {
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
   return (unsigned)((((((uint64_t)hi) << 32) | lo) << (s & 31)) >> 32);
 }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) {  // clamp variant: shift = min(s, 32)
+  if (s > 32) s = 32;
+  return (unsigned)((((((uint64_t)hi) << 32) | lo) << s) >> 32);
+}
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) {
+  if (s > 32) s = 32;
+  return (unsigned)(((((uint64_t)hi) << 32) | lo) >> s);
+}
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
   for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 255) * ((b >> (8 * i)) & 255);
   return c;

@@ -465,22 +465,161 @@ k_mark_emit(const u8 *__restrict__ in, u64 n, u64 first, const u32 *tile_base, u
 // Tokens use the encoder's format (lz77.cuh): literal = byte value; match = bit31 | (len-3)<<16 | (dist-1).
 constexpr u32 SEGF_BADREF = 4;            // a distance reached before the start of the chunk
 
-__device__ __forceinline__ void inf_segment_tokens(InfWarpSmem *S, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out) {
+// Phase A uses 32-bit LUT entries so that one shared-memory load yields everything about a symbol:
+//   bits 0-3 code length (0 = longer than the root: canonical slow path) | bits 4-7 extra-bit count |
+//   bits 8-23 literal value / length base / distance base | bit 24 length | bit 25 end of block | bit 26 invalid
+constexpr u32 TK_LEN = 1u << 24, TK_EOB = 1u << 25, TK_INV = 1u << 26;
+
+struct TokWarpSmem {
+  u32 lut_ll[1 << LL_ROOT];
+  u32 lut_d[1 << D_ROOT];
+  InfWarpSmem w;  // code lengths, canonical arrays, 16-bit LUTs the 32-bit ones are expanded from
+};
+constexpr int TOK_SMEM = (int)sizeof(TokWarpSmem) * INF_WARPS;
+
+__device__ __forceinline__ u32 tk_entry_ll(u32 sym, u32 l) {
+  if (sym < 256) return (sym << 8) | l;
+  if (sym == 256) return TK_EOB | l;
+  if (sym >= 286) return TK_INV | l;
+  return TK_LEN | ((u32)c_len_base[sym - 257] << 8) | ((u32)c_len_extra[sym - 257] << 4) | l;
+}
+__device__ __forceinline__ u32 tk_entry_d(u32 sym, u32 l) {
+  if (sym >= 30) return TK_INV | l;
+  return ((u32)c_dist_base[sym] << 8) | ((u32)c_dist_extra[sym] << 4) | l;
+}
+
+// warp-uniform bit reader for phase A: the bit buffer is kept as two 32-bit halves so that every
+// shift is one funnel-shift instruction (no shift here exceeds 31 bits); words are handed out from
+// a 128-byte window per warp.
+struct TokReader {
+  const u8 *in;
+  u64 n;
+  const u32 *words;   // `in` rounded down to 4 bytes
+  u32 skew;
+  u64 wabs;           // absolute word index of window position 0
+  u32 wi;             // next word to consume, relative to wabs (the live window is [wi & ~31, +32))
+  u32 win, win_next;
+  u32 lo, hi;         // bit buffer: bits 0..31 and 32..63 of the unread stream
+  u32 bc;             // valid bits in (hi:lo)
+
+  __device__ __forceinline__ u32 load_word(u64 w) const {  // bytes outside [0, n) read as 0 (BitReadStream.ts:33-35)
+    const long long l0 = (long long)(w << 2) - (long long)skew;
+    if (l0 >= 0 && (u64)l0 + 4 <= n) return __ldg(words + w);
+    u32 v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const long long b = l0 + k;
+      if (b >= 0 && (u64)b < n) v |= (u32)in[b] << (8 * k);
+    }
+    return v;
+  }
+  __device__ __forceinline__ u32 next_word() {
+    const u32 w = __shfl_sync(ZLES_FULL, win, (int)(wi & 31));
+    wi++;
+    if ((wi & 31) == 0) {
+      win = win_next;
+      win_next = load_word(wabs + wi + 32 + lane_id());
+    }
+    return w;
+  }
+  __device__ __forceinline__ void init(const u8 *in_, u64 n_, u64 byte_pos) {
+    in = in_; n = n_;
+    skew = (u32)((uintptr_t)in_ & 3);
+    words = reinterpret_cast<const u32 *>(in_ - skew);
+    const u64 a = byte_pos + skew;
+    const u64 w0 = a >> 2;
+    wabs = w0 & ~(u64)31;
+    wi = (u32)(w0 - wabs);
+    win = load_word(wabs + lane_id());
+    win_next = load_word(wabs + 32 + lane_id());
+    const u32 sh = (u32)(a & 3) * 8;
+    lo = next_word() >> sh;
+    hi = 0;
+    bc = 32 - sh;
+    refill();
+  }
+  __device__ __forceinline__ void refill() {  // afterwards bc >= 33
+    if (bc <= 32) {
+      const u32 w = next_word();
+      lo |= __funnelshift_lc(0u, w, bc);   // w << bc (0 when bc == 32)
+      hi = __funnelshift_lc(w, 0u, bc);    // w >> (32 - bc) (w when bc == 32, 0 when bc == 0)
+      bc += 32;
+    }
+  }
+  __device__ __forceinline__ u32 peek(u32 k) const { return lo & ~(0xffffffffu << k); }  // k <= 31
+  __device__ __forceinline__ void skip(u32 k) {                                           // k <= 31
+    lo = __funnelshift_r(lo, hi, k);
+    hi >>= k;
+    bc -= k;
+  }
+  __device__ __forceinline__ u32 take(u32 k) { const u32 v = peek(k); skip(k); return v; }
+  __device__ __forceinline__ u64 bits64() const { return ((u64)hi << 32) | lo; }
+  __device__ __forceinline__ u64 bitpos() const { return ((wabs + wi) << 5) - bc - ((u64)skew << 3); }
+  __device__ __forceinline__ bool past_end() const { return bitpos() > (n << 3) + 64; }
+};
+
+// dynamic block header for phase A (same as inf_read_dynamic_header, on the TokReader)
+__device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem *S, u32 &status) {
   const u32 lane = lane_id();
-  InfReader r;
+  const u32 HLIT = r.take(5) + 257;
+  const u32 HDIST = r.take(5) + 1;
+  const u32 HCLEN = r.take(4) + 4;
+  S->cl_lens[lane] = 0;
+  for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
+  __syncwarp();
+  for (u32 i = 0; i < HCLEN; i++) {
+    r.refill();
+    const u32 v = r.take(3);
+    if (lane == 0) S->cl_lens[c_cl_order[i]] = (u8)v;
+  }
+  __syncwarp();
+  inf_build(S->cl_lens, 32, CL_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+  const u32 total = HLIT + HDIST;
+  u32 prev = 0;
+  for (u32 i = 0; i < total;) {
+    r.refill();
+    if (r.past_end()) { status = SEG_E_LACK; return false; }
+    u32 e = S->lut_d[r.peek(CL_ROOT)], l = e & 15, sym = e >> 4;
+    if (l == 0 && !inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) { status = SEG_E_CORRUPT; return false; }
+    r.skip(l);
+    u32 rep = 1, val = sym;
+    if (sym == 16) { rep = 3 + r.take(2); val = prev; }
+    else if (sym == 17) { rep = 3 + r.take(3); val = 0; prev = 0; }
+    else if (sym == 18) { rep = 11 + r.take(7); val = 0; prev = 0; }
+    else prev = sym;
+    if (val) {
+      for (u32 k = lane; k < rep; k += 32) {
+        const u32 j = i + k;
+        if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
+        else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
+      }
+    }
+    i += rep;
+  }
+  __syncwarp();
+  return true;
+}
+
+__device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out) {
+  const u32 lane = lane_id();
+  InfWarpSmem *S = &T->w;
+  TokReader r;
   r.init(in, n, in_pos);
   u32 o = 0, nt = 0, mytok = 0;
   u32 status = 0, flags = 0;
   u64 end_pos = 0;
+  // token t goes to lane (t & 31); `turn` counts down to this lane's turn, `left` to the next 128-byte store
+  u32 turn = lane, left = 32;
 #define ZLES_EMIT(t)                                         \
   do {                                                       \
-    if ((nt & 31) == lane) mytok = (t);                      \
+    if (turn == 0) mytok = (t);                              \
+    turn = (turn - 1) & 31;                                  \
     nt++;                                                    \
-    if ((nt & 31) == 0) tok[nt - 32 + lane] = mytok;         \
+    if (--left == 0) { tok[nt - 32 + lane] = mytok; left = 32; } \
   } while (0)
   for (;;) {
     r.refill();
-    if (r.overrun) { status = SEG_E_LACK; break; }
+    if (r.past_end()) { status = SEG_E_LACK; break; }
     const u32 bfinal = r.take(1);
     const u32 btype = r.take(2);
     if (btype == 3) { status = SEG_E_BTYPE3; break; }
@@ -500,36 +639,50 @@ __device__ __forceinline__ void inf_segment_tokens(InfWarpSmem *S, const u8 *in,
       for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
       __syncwarp();
     } else {
-      if (!inf_read_dynamic_header(r, S, status)) break;
+      if (!tk_read_dynamic_header(r, S, status)) break;
     }
     inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
     inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+    // invalid symbols (286, 287, distance 30, 31) are left out of the fast tables: they take the slow path, which rejects them
+    for (u32 i = lane; i < (1u << LL_ROOT); i += 32) { const u32 e = S->lut_ll[i]; T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0; }
+    for (u32 i = lane; i < (1u << D_ROOT); i += 32) { const u32 e = S->lut_d[i]; T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0; }
+    __syncwarp();
+    // symbol loop (/root/reference/src/inflate.ts:237-291 without the copy).  It cannot run away: every
+    // token accounts for at least one output byte and a token is only emitted while o < SUB.
     for (;;) {
       r.refill();
-      if (r.overrun) { status = SEG_E_LACK; break; }
-      u32 sym;
-      if (!inf_decode(r, S->lut_ll, LL_ROOT, &S->tab_ll, S->sorted_ll, sym)) { status = SEG_E_CORRUPT; break; }
-      if (sym < 256) {
-        if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
-        ZLES_EMIT(sym);
+      u32 e = T->lut_ll[r.lo & ((1u << LL_ROOT) - 1)];
+      if ((e & 15) == 0) {
+        u32 sym, l;
+        if (!inf_slow(r.bits64(), &S->tab_ll, S->sorted_ll, sym, l)) { status = SEG_E_CORRUPT; break; }
+        e = tk_entry_ll(sym, l);
+        if (e & TK_INV) { status = SEG_E_CORRUPT; break; }
+      }
+      r.skip(e & 15);
+      if (e & TK_EOB) break;
+      if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+      if (e < TK_LEN) {  // literal
+        ZLES_EMIT(e >> 8);
         o++;
         continue;
       }
-      if (sym == 256) break;
-      const u32 ls = sym - 257;
-      if (ls >= 29) { status = SEG_E_CORRUPT; break; }
-      const u32 len = c_len_base[ls] + r.take(c_len_extra[ls]);
+      const u32 len = ((e >> 8) & 0xffff) + r.take((e >> 4) & 15);
       r.refill();
-      u32 ds;
-      if (!inf_decode(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, ds)) { status = SEG_E_CORRUPT; break; }
-      if (ds >= 30) { status = SEG_E_CORRUPT; break; }
-      r.refill();
-      const u32 dist = c_dist_base[ds] + r.take(c_dist_extra[ds]);
-      if (o + len > SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+      u32 d = T->lut_d[r.lo & ((1u << D_ROOT) - 1)];
+      if ((d & 15) == 0) {
+        u32 sym, l;
+        if (!inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) { status = SEG_E_CORRUPT; break; }
+        d = tk_entry_d(sym, l);
+        if (d & TK_INV) { status = SEG_E_CORRUPT; break; }
+      }
+      r.skip(d & 15);
+      const u32 dist = (d >> 8) + r.take((d >> 4) & 15);
       ZLES_EMIT(0x80000000u | ((len - 3) << 16) | (dist - 1));
       o += len;
     }
+    if (o > SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; }
     if (status) break;
+    if (r.past_end()) { status = SEG_E_LACK; break; }
     if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
   }
 #undef ZLES_EMIT
@@ -549,26 +702,37 @@ __global__ void __launch_bounds__(INF_THREADS)
 k_inf_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res,
              u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);
-  InfWarpSmem *S = reinterpret_cast<InfWarpSmem *>(smem_raw) + warp_id();
+  TokWarpSmem *T = reinterpret_cast<TokWarpSmem *>(smem_raw) + warp_id();
   for (;;) {
     u32 j = 0;
     if (lane_id() == 0) j = atomicAdd(counter, 1u);
     j = __shfl_sync(ZLES_FULL, j, 0);
     if (j >= nseg) break;
-    inf_segment_tokens(S, in, n, seg_pos[j], tokens + (size_t)j * SUB, res + j, ntok + j);
+    inf_segment_tokens(T, in, n, seg_pos[j], tokens + (size_t)j * SUB, res + j, ntok + j);
     __syncwarp();
   }
 }
 
 // phase B: one warp per chunk.  seg_list (or identity when null) names the real segments in
 // stream order; chunk c is made of entries [4c, 4c+4) and is written at out + c * CHUNK.
+// Per batch of 32 tokens: a warp scan of the lengths gives the output offsets; literals are
+// stored at once; matches whose source lies entirely before the batch ("independent", the
+// common case on text) are copied lane-parallel with all loads issued before the stores; the
+// others — and long ones — are copied in token order by the whole warp, reading from a 16 KiB
+// shared-memory ring that mirrors the warp's most recent output, so that chains of near
+// references (structured data) run at shared-memory latency instead of one HBM/L2 round trip each.
 constexpr int RES_WARPS = 4;
 constexpr int RES_THREADS = RES_WARPS * 32;
-constexpr u32 RES_LONG = 24;  // matches at least this long are copied by the whole warp
+constexpr u32 RES_LONG = 17;         // matches at least this long are copied by the whole warp
+constexpr u32 RES_RING = 16384;      // >= 2 x the most a batch can produce (32 x 258 = 8256)
+constexpr int RES_SMEM = (int)(RES_WARPS * RES_RING);
 
 __global__ void __launch_bounds__(RES_THREADS)
 k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg, u8 *out, u64 cap,
               u32 *problems) {
+  ZLES_SMEM_DECL(smem_raw);
+  u8 *ring = smem_raw + warp_id() * RES_RING;
+  constexpr u32 RM = RES_RING - 1;
   const u32 lane = lane_id();
   const u32 c = blockIdx.x * RES_WARPS + warp_id();
   if (c * SUBS_PER_CHUNK >= nseg) return;
@@ -582,9 +746,11 @@ k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, cons
     const u32 sidx = seg_list ? seg_list[e] : e;
     const u32 nt = umin(ntok[sidx], SUB);
     const u32 *tok = tokens + (size_t)sidx * SUB;
+    u32 tnext = lane < nt ? __ldg(tok + lane) : 0;
     for (u32 b0 = 0; b0 < nt; b0 += 32) {
       const bool valid = b0 + lane < nt;
-      const u32 t = valid ? __ldg(tok + b0 + lane) : 0;
+      const u32 t = tnext;
+      tnext = b0 + 32 + lane < nt ? __ldg(tok + b0 + 32 + lane) : 0;  // next batch's tokens are in flight during this one
       const bool isM = valid && (t >> 31);
       const u32 len = !valid ? 0 : (isM ? ((t >> 16) & 255) + 3 : 1);
       const u32 dist = (t & 0x7fff) + 1;
@@ -598,46 +764,41 @@ k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, cons
       const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
       if (o + total > CHUNK) { bad |= 1; break; }
       if (o + total > room) { bad |= 2; break; }  // output buffer too small: nothing of this batch is written
-      if (valid && !isM) base[pos] = (u8)t;
-      const bool badref = isM && dist > pos;     // before the start of the chunk
-      if (__any_sync(ZLES_FULL, badref)) { bad |= 1; break; }
+      if (__any_sync(ZLES_FULL, isM && dist > pos)) { bad |= 1; break; }  // a reference before the start of the chunk
+      if (valid && !isM) { base[pos] = (u8)t; ring[pos & RM] = (u8)t; }
       const u32 src = pos - dist;
-      const u32 send = umin(src + len, pos);      // bytes [src, send) must be final before this match is copied
-      // dep = earlier matches of this batch whose output overlaps [src, send)
-      u32 dep = 0;
-      const u32 mmask = __ballot_sync(ZLES_FULL, isM);
-      if (__any_sync(ZLES_FULL, isM && send > o)) {
-        const u32 pend = pos + len;
-        u32 m = mmask;
-        while (m) {
-          const int j = __ffs((int)m) - 1;
-          m &= m - 1;
-          const u32 pj = __shfl_sync(ZLES_FULL, pos, j), ej = __shfl_sync(ZLES_FULL, pend, j);
-          if ((u32)j < lane && src < ej && send > pj) dep |= 1u << j;
-        }
+      const bool indep = isM && len < RES_LONG && src + len <= o;  // source entirely before this batch
+      const u32 later = __ballot_sync(ZLES_FULL, isM && !indep);
+      if (indep) {  // all loads first, then the stores: one memory round trip for the whole batch
+        u8 v[RES_LONG - 1];
+#pragma unroll
+        for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) v[q] = base[src + q];
+#pragma unroll
+        for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) { base[pos + q] = v[q]; ring[(pos + q) & RM] = v[q]; }
       }
       __syncwarp();
-      u32 done = ~mmask;
-      while (done != 0xffffffffu) {
-        const bool ready = isM && !((done >> lane) & 1) && (dep & ~done) == 0;
-        const u32 rmask = __ballot_sync(ZLES_FULL, ready);
-        const u32 lmask = __ballot_sync(ZLES_FULL, ready && len >= RES_LONG);
-        if (ready && len < RES_LONG) {
-          for (u32 q = 0; q < len; q++) base[pos + q] = base[src + q];  // byte-serial: right for overlapping copies too
-        }
-        u32 m = lmask;
-        while (m) {  // long matches: the whole warp copies one at a time
-          const int j = __ffs((int)m) - 1;
-          m &= m - 1;
-          const u32 pj = __shfl_sync(ZLES_FULL, pos, j), sj = __shfl_sync(ZLES_FULL, src, j), lj = __shfl_sync(ZLES_FULL, len, j);
-          const u32 dj = pj - sj;
-          if (dj >= lj) {
-            for (u32 q = lane; q < lj; q += 32) base[pj + q] = base[sj + q];
-          } else {  // overlapping: the output is periodic with period dj
-            for (u32 q = lane; q < lj; q += 32) base[pj + q] = base[sj + (q % dj)];
+      u32 m = later;
+      while (m) {  // dependent or long matches: in token order, the whole warp copies one at a time
+        const int j = __ffs((int)m) - 1;
+        m &= m - 1;
+        const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
+        const u32 sj = pj - dj;
+        // the ring holds this warp's latest output up to the end of this batch; everything from sj on is in it
+        // when o + total - sj <= RES_RING (and then nothing of it has been overwritten)
+        const bool in_ring = o + total - sj <= RES_RING;
+        if (dj >= lj) {
+          for (u32 q = lane; q < lj; q += 32) {
+            const u8 b = in_ring ? ring[(sj + q) & RM] : base[sj + q];
+            base[pj + q] = b;
+            ring[(pj + q) & RM] = b;
+          }
+        } else {  // overlapping: the output is periodic with period dj
+          for (u32 q = lane; q < lj; q += 32) {
+            const u8 b = in_ring ? ring[(sj + q % dj) & RM] : base[sj + q % dj];
+            base[pj + q] = b;
+            ring[(pj + q) & RM] = b;
           }
         }
-        done |= rmask;
         __syncwarp();
       }
       o += total;

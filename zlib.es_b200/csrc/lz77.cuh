@@ -52,10 +52,12 @@ constexpr u32 LZ_NSYM = 320;  // [0,288) literal/length symbols, [288,320) dista
 constexpr u32 LZ_OFF_DATA = 0;
 constexpr u32 LZ_OFF_X = 65536 + 384;                       // 65920
 constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256] | bitmap u32[1024] + hist u32[8*320]
-constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 16384;              // scratch u32[40] | specexit u32[64] | mbarrier
-constexpr u32 LZ_SMEM = LZ_OFF_MISC + 1024;                 // 214400 B
-constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (ring = 2 x 32 entries)
-static_assert(LZ_WARPS * 64 * 8 <= 16384, "candidate rings overlay the sort histograms");
+constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] | specexit u32[64] | mbarrier
+constexpr u32 LZ_SMEM = LZ_OFF_MISC + 1024;                 // 230784 B (of 232448 available)
+constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position
+// per-warp candidate ring: 64 entries of 8 bytes, stored twice (slot i and i + 64) so that "entry k - r"
+// is a constant offset from a per-lane base and needs no wrap-around arithmetic
+static_assert(LZ_WARPS * 128 * 8 <= 32768, "candidate rings overlay the sort histograms");
 
 struct LzParams {
   const u8 *in;       // this shard's input
@@ -64,7 +66,7 @@ struct LzParams {
   u32 *tokens;        // [nblocks][SUB]
   u32 *ntok;          // [nblocks]
   u32 *hist;          // [nblocks][LZ_NSYM]
-  u32 *scratch;       // [gridDim.x][SUB] u32: sort pass buffer (as u16[65536]), then match results
+  u32 *scratch;       // [gridDim.x][2 * SUB] u32: sort pass buffer, then match results
   u64 *adler_part;    // [nblocks][2]: sum d, sum (len - j) d[j] over the block's own bytes
   u32 max_checks;     // candidates compared per position, <= LZ_SCAN   (reference: FAST_INDEX_CHECK_MAX = 128, src/lz77.ts:7)
   u32 min_checks;     // of those, how many >= 7-byte candidates are extended (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
@@ -96,63 +98,93 @@ __device__ __forceinline__ u32 lz_match_len(const u8 *d, u32 c, u32 p, u32 maxle
   return umin(o, maxlen);
 }
 
-// One stable counting-sort pass over `N` items on the digit `shift` of their hash.
-// Items of warp w are [w*per, (w+1)*per); pass 1 takes the item index as position,
-// pass 2 reads positions from `src`.  Output order is stable (ascending source index).
-template <typename OutT>
-__device__ __forceinline__ void lz_sort_pass(const u8 *data, const u16 *src, OutT *dst, u16 *wh, u32 *scratch, u32 N, u32 per,
-                                             u32 shift) {
+// ---- S2: stable LSD radix sort of the positions by hash16(key3), 2 passes of 8 bits ----------
+// Warp w owns items [w*per, (w+1)*per) of each pass; per-warp digit histograms (u16, in `wh`)
+// make the scatter stable.  Counting uses fire-and-forget shared-memory atomics on packed u16
+// pairs (no dependency chain); the scatter ranks equal digits inside a warp with __match_any_sync.
+// Pass 1 reads the data, pass 2 reads pass 1's output Y (u32 = hash << 16 | position, in global
+// memory / L2, coalesced, four loads in flight per lane).
+
+__device__ __forceinline__ u32 lz_key3_fast(const u8 *d, u32 p) {  // 2 word loads instead of 3 byte loads
+  return lz_ld32(d, p) & 0xffffffu;
+}
+
+__device__ __forceinline__ void lz_hist_scan(u16 *wh, u32 *scratch) {  // exclusive scan, digit-major / warp-minor
+  u32 v[8], s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u32 e = threadIdx.x * 8 + k;
+    v[k] = wh[(e % LZ_WARPS) * 256 + e / LZ_WARPS];
+    s += v[k];
+  }
+  u32 total;
+  u32 ex = block_exscan(s, scratch, &total);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    u32 e = threadIdx.x * 8 + k;
+    wh[(e % LZ_WARPS) * 256 + e / LZ_WARPS] = (u16)ex;
+    ex += v[k];
+  }
+}
+
+__device__ __forceinline__ void lz_count(u16 *wh, u32 w, u32 digit) {
+  atomicAdd(reinterpret_cast<u32 *>(wh) + ((w * 256 + digit) >> 1), 1u << ((digit & 1) * 16));
+}
+
+// rank of this lane among the lanes of the warp with the same digit, and the slot it scatters to
+__device__ __forceinline__ u32 lz_slot(u16 *wh, u32 w, u32 digit, bool valid) {
+  const u32 lane = lane_id();
+  const u32 m = __match_any_sync(ZLES_FULL, digit);
+  const u32 basepos = valid ? wh[w * 256 + digit] : 0;
+  __syncwarp();
+  if (valid && lane == (u32)(__ffs((int)m) - 1)) wh[w * 256 + digit] = (u16)(basepos + __popc(m));
+  __syncwarp();
+  return basepos + __popc(m & lanemask_lt());
+}
+
+__device__ __forceinline__ void lz_sort(const u8 *data, u32 *Y, u16 *X, u16 *wh, u32 *scratch, u32 N, u32 per) {
   const u32 lane = lane_id(), w = warp_id();
   const u32 wbeg = umin(w * per, N), wend = umin(wbeg + per, N);
-  for (u32 i = threadIdx.x; i < LZ_WARPS * 256 / 2; i += LZ_THREADS) reinterpret_cast<u32 *>(wh)[i] = 0;
+  u32 *wh32 = reinterpret_cast<u32 *>(wh);
+  // ---- pass 1: low digit ----
+  for (u32 i = threadIdx.x; i < LZ_WARPS * 256 / 2; i += LZ_THREADS) wh32[i] = 0;
+  __syncthreads();
+  for (u32 idx = wbeg + lane; idx < wend; idx += 32) lz_count(wh, w, lz_hash16(lz_key3_fast(data, idx)) & 255);
+  __syncthreads();
+  lz_hist_scan(wh, scratch);
   __syncthreads();
   for (u32 base = wbeg; base < wend; base += 32) {
-    u32 idx = base + lane;
-    bool valid = idx < wend;
-    u32 digit = 256 + lane;
-    if (valid) {
-      u32 p = src ? (u32)src[idx] : idx;
-      digit = (lz_hash16(lz_key3(data, p)) >> shift) & 255;
-    }
-    u32 m = __match_any_sync(ZLES_FULL, digit);
-    if (valid && lane == (u32)(__ffs((int)m) - 1)) wh[w * 256 + digit] = (u16)(wh[w * 256 + digit] + __popc(m));
-    __syncwarp();
+    const u32 idx = base + lane;
+    const bool valid = idx < wend;
+    const u32 h = valid ? lz_hash16(lz_key3_fast(data, idx)) : 0;
+    const u32 slot = lz_slot(wh, w, valid ? (h & 255) : 256 + lane, valid);
+    if (valid) Y[slot] = (h << 16) | idx;
+  }
+  __syncthreads();  // also orders the global writes of Y before the reads below (same CTA)
+  // ---- pass 2: high digit ----
+  for (u32 i = threadIdx.x; i < LZ_WARPS * 256 / 2; i += LZ_THREADS) wh32[i] = 0;
+  __syncthreads();
+  for (u32 base = wbeg; base < wend; base += 128) {
+    u32 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const u32 idx = base + 32 * k + lane; v[k] = idx < wend ? __ldcg(Y + idx) : 0; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + 32 * k + lane < wend) lz_count(wh, w, v[k] >> 24);
   }
   __syncthreads();
-  {  // exclusive scan in digit-major, warp-minor order
-    u32 v[8], s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      u32 e = threadIdx.x * 8 + k;
-      v[k] = wh[(e % LZ_WARPS) * 256 + e / LZ_WARPS];
-      s += v[k];
-    }
-    u32 total;
-    u32 ex = block_exscan(s, scratch, &total);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      u32 e = threadIdx.x * 8 + k;
-      wh[(e % LZ_WARPS) * 256 + e / LZ_WARPS] = (u16)ex;
-      ex += v[k];
-    }
-  }
+  lz_hist_scan(wh, scratch);
   __syncthreads();
-  for (u32 base = wbeg; base < wend; base += 32) {
-    u32 idx = base + lane;
-    bool valid = idx < wend;
-    u32 digit = 256 + lane, p = 0;
-    if (valid) {
-      p = src ? (u32)src[idx] : idx;
-      digit = (lz_hash16(lz_key3(data, p)) >> shift) & 255;
+  for (u32 base = wbeg; base < wend; base += 128) {
+    u32 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const u32 idx = base + 32 * k + lane; v[k] = idx < wend ? __ldcg(Y + idx) : 0; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (base + 32 * k >= wend) break;  // warp-uniform
+      const bool valid = base + 32 * k + lane < wend;
+      const u32 slot = lz_slot(wh, w, valid ? (v[k] >> 24) : 256 + lane, valid);
+      if (valid) X[slot] = (u16)v[k];
     }
-    u32 m = __match_any_sync(ZLES_FULL, digit);
-    u32 basepos = valid ? wh[w * 256 + digit] : 0;
-    __syncwarp();
-    if (valid) {
-      dst[basepos + __popc(m & lanemask_lt())] = (OutT)p;
-      if (lane == (u32)(__ffs((int)m) - 1)) wh[w * 256 + digit] = (u16)(basepos + __popc(m));
-    }
-    __syncwarp();
   }
   __syncthreads();
 }
@@ -202,8 +234,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   if (tid == 0) mbar_init(mbar, 1);
   __syncthreads();
 #endif
-  u16 *Y = reinterpret_cast<u16 *>(P.scratch + (size_t)blockIdx.x * SUB);
-  u32 *R = P.scratch + (size_t)blockIdx.x * SUB;
+  u32 *Y = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // sort pass buffer, 2 * SUB entries
+  u32 *R = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // then the match results, SUB entries
 
   for (u32 b = blockIdx.x; b < P.nblocks; b += gridDim.x) {
     u64 own_off = (u64)b * SUB;
@@ -254,12 +286,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     // S2: stable radix sort of positions by hash16(key3)
     const u32 N = L >= 3 ? L - 2 : 0;
     const u32 per = ((N + LZ_THREADS - 1) / LZ_THREADS) * 32;
-    lz_sort_pass<u16>(data, nullptr, Y, wh, scratch, N, per, 0);
-    lz_sort_pass<u16>(data, Y, X, wh, scratch, N, per, 8);
+    lz_sort(data, Y, X, wh, scratch, N, per);
 
     // S3: per-position match search.  Warp w owns sorted entries [kbeg, kend).
     {
-      uint2 *ring = reinterpret_cast<uint2 *>(smem + LZ_OFF_WH) + w * 64;
+      uint2 *ring = reinterpret_cast<uint2 *>(smem + LZ_OFF_WH) + w * 128;
       const u32 kbeg = umin(w * per, N), kend = umin(kbeg + per, N);
       const u32 scan = umin(P.max_checks, LZ_SCAN);
       u32 Bprev = 0, hprev = 0xffffffffu;
@@ -269,6 +300,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         u32 lo, hi;
         lz_ld56(data, pj, lo, hi);
         ring[j & 63] = make_uint2(lo, hi);
+        ring[(j & 63) + 64] = make_uint2(lo, hi);
         const u32 hj = lz_hash16(lo & 0xffffffu);
         u32 hl = __shfl_up_sync(ZLES_FULL, hj, 1);
         if (lane == 0) hl = 0xffffffffu;  // whether entry kbeg-32 starts a run never matters (see rrun below)
@@ -285,6 +317,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
           h = lz_hash16(lo & 0xffffffu);
         }
         ring[k & 63] = make_uint2(lo, hi);
+        ring[(k & 63) + 64] = make_uint2(lo, hi);
         u32 hl = __shfl_up_sync(ZLES_FULL, h, 1);
         if (lane == 0) hl = hprev;
         const u32 B = __ballot_sync(ZLES_FULL, h != hl);  // bit l: entry kb+l starts a run of equal hashes
@@ -310,23 +343,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
           }
         }
         const u32 rmax = __reduce_max_sync(ZLES_FULL, rrun);
-        // Branch-free body: candidate r is entry k-r of the ring; ml = bytes equal from offset 0 (3..7).
+        // Branch-free, fully unrolled body: candidate r is entry k-r of the ring, at a constant offset from
+        // `rp`; ml = bytes equal from offset 0 (3..7).
         u32 best = 0, full = 0;
-        const u8 *rbase = reinterpret_cast<const u8 *>(ring);
-        u32 off = ((k - 1) & 63) * 8, rkey = 0x340u - 1, bit = 1;  // rkey = 0x300 + (64 - r), bit = 1 << (r - 1)
-#pragma unroll 4
-        for (u32 r = 1; r <= rmax; r++) {
-          const uint2 ce = *reinterpret_cast<const uint2 *>(rbase + off);
+        const uint2 *rp = ring + (k & 63) + 64;
+#pragma unroll
+        for (u32 r = 1; r <= LZ_SCAN; r++) {
+          if (((r - 1) & 7) == 0 && r > rmax) break;               // warp-uniform early out, checked every 8 candidates
+          const uint2 ce = rp[-(int)r];
           const u32 xl = lo ^ ce.x, xh = hi ^ ce.y;
-          const u32 v = __funnelshift_r(xl, xh, 24);              // bytes 3..6
-          const bool ok = ((xl & 0xffffffu) == 0) & (r <= rrun);  // same 3-byte key (src/lz77.ts:40), inside run and window
-          const u32 tz = (u32)__clz((int)__brev(v));              // 32 when bytes 3..6 are all equal
-          const u32 key = ((tz << 5) & 0x700u) + rkey;            // (3 + tz / 8) << 8 | (64 - r)
+          const u32 v = __funnelshift_r(xl, xh, 24);                // bytes 3..6
+          const bool ok = ((xl & 0xffffffu) == 0) & (r <= rrun);    // same 3-byte key (src/lz77.ts:40), inside run and window
+          const u32 tz = (u32)__clz((int)__brev(v));                // 32 when bytes 3..6 are all equal
+          const u32 key = ((tz << 5) & 0x700u) + (0x340u - r);      // (3 + tz / 8) << 8 | (64 - r)
           if (ok) best = umax(best, key);
-          if (ok & (v == 0)) full |= bit;
-          off = (off - 8) & 511;
-          rkey--;
-          bit <<= 1;
+          if (ok & (v == 0)) full |= 1u << (r - 1);
         }
         if (own) {
           const u32 maxlen = umin(MAX_MATCH, L - p);

@@ -196,7 +196,9 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff)");
   e = zrt_set_smem(k_inflate, INF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
-  e = zrt_set_smem(k_inf_tokens, INF_SMEM);
+  e = zrt_set_smem(k_inf_resolve, RES_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_resolve)");
+  e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens)");
   e = zrt_set_smem(k_inflate_batch, INF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate_batch)");
@@ -386,7 +388,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
   RET(c->ntok.reserve((size_t)nblocks * 4));
   RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
-  RET(c->scratch.reserve((size_t)grid_lz * SUB * 4));
+  RET(c->scratch.reserve((size_t)grid_lz * 2 * SUB * 4));
   RET(c->adler_part.reserve((size_t)nblocks * 16));
   RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
   RET(c->blk_bits.reserve((size_t)nblocks * 4));
@@ -619,14 +621,14 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
   if (fast) {
     // 2. phase A on every candidate, acceptance check, and — optimistically — phase B with candidate j
     //    taken as block j of the stream (true unless a marker pattern occurs inside compressed data)
-    LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
+    LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
            c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
     LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
            (u64)n, has_final ? 1u : 0u, &ctl->ok, &ctl->total);
     const u32 nchunks = (ncand + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
     const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only
     if (room)
-      LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, 0, (const u32 *)c->tokens.as<u32>(),
+      LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
              (const u32 *)c->ntok.as<u32>(), (const u32 *)nullptr, ncand, d_out, (u64)cap, &ctl->ok_res);
     CK(zrt_last_error());
     InfCtl h;
@@ -673,7 +675,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
         CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
         CK(zrt_sync(c->stream));  // list is host heap memory
         const u32 nch = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
-        LAUNCH(c, k_inf_resolve, (nch + RES_WARPS - 1) / RES_WARPS, RES_THREADS, 0, (const u32 *)c->tokens.as<u32>(),
+        LAUNCH(c, k_inf_resolve, (nch + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
                (const u32 *)c->ntok.as<u32>(), (const u32 *)c->seg_pos.as<u32>(), nseg, d_out, (u64)cap, &ctl->ok_res);
         CK(zrt_last_error());
         RET(read_ctl(c, &h));
@@ -900,7 +902,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
   RET(c->ntok.reserve((size_t)nblocks * 4));
   RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
-  RET(c->scratch.reserve((size_t)grid_lz * SUB * 4));
+  RET(c->scratch.reserve((size_t)grid_lz * 2 * SUB * 4));
   RET(c->adler_part.reserve((size_t)nblocks * 16));
   RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
   RET(c->blk_bits.reserve((size_t)nblocks * 4));

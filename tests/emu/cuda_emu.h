@@ -61,6 +61,7 @@ struct BlockCtx {
   std::vector<WarpSlot> warps;
   unsigned barrier_arrived = 0;
   unsigned barrier_gen = 0;
+  int vote = 0;            // __syncthreads_or accumulator
   uint8_t *smem = nullptr;
   uint3 bid{0, 0, 0};
   dim3 bdim, gdim;
@@ -123,6 +124,16 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
 #define gridDim (emu::g_blk->gdim)
 
 static inline void __syncthreads() { emu::block_barrier(); }
+static inline int __syncthreads_or(int pred) {
+  emu::BlockCtx *b = emu::g_blk;
+  if (pred) b->vote = 1;
+  emu::block_barrier();
+  const int r = b->vote;
+  emu::block_barrier();
+  if (b->cur == 0) b->vote = 0;  // thread 0 (fibers run one at a time; the next use is behind another barrier)
+  emu::block_barrier();
+  return r;
+}
 static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   uint64_t o[32];
   emu::warp_exchange(mask, 0, o);

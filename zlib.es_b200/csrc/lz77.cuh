@@ -44,8 +44,8 @@ namespace zles {
 constexpr int LZ_THREADS = 1024;
 constexpr int LZ_WARPS = LZ_THREADS / 32;
 constexpr u32 LZ_PAD = 320;
-constexpr u32 LZ_NWALK = 64;
-constexpr u32 LZ_RANGE = SUB / LZ_NWALK;  // 512 positions per speculative walker
+constexpr u32 LZ_NWALK = 128;
+constexpr u32 LZ_RANGE = SUB / LZ_NWALK;  // 256 positions per speculative walker
 constexpr u32 LZ_HCOPIES = 8;
 constexpr u32 LZ_NSYM = 320;  // [0,288) literal/length symbols, [288,320) distance symbols
 
@@ -53,7 +53,7 @@ constexpr u32 LZ_OFF_DATA = 0;
 constexpr u32 LZ_OFF_X = 65536 + 384;                       // 65920
 constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256] | bitmap u32[1024] + hist u32[8*320]
 constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] | specexit u32[64] | mbarrier
-constexpr u32 LZ_SMEM = LZ_OFF_MISC + 1024;                 // 230784 B (of 232448 available)
+constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 232448 available)
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position
 // per-warp candidate ring: 64 entries of 8 bytes, stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u32 *bm = reinterpret_cast<u32 *>(smem + LZ_OFF_WH);          // [1024]
   u32 *hcopies = reinterpret_cast<u32 *>(smem + LZ_OFF_WH) + 1024;  // [LZ_HCOPIES][LZ_NSYM]
   u32 *scratch = reinterpret_cast<u32 *>(smem + LZ_OFF_MISC);       // [40]
-  u32 *specexit = scratch + 40;                                      // [64]
-  u64 *mbar = reinterpret_cast<u64 *>(scratch + 40 + 64);           // 8-byte aligned: (40+64)*4 = 416
-  u64 *red = reinterpret_cast<u64 *>(scratch + 40 + 64 + 2);        // [2][LZ_WARPS] u64
+  u32 *specexit = scratch + 40;                                      // [LZ_NWALK]
+  u64 *mbar = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK);     // 8-byte aligned: (40+128)*4 = 672
+  u64 *red = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK + 2);  // [2][LZ_WARPS] u64
 
   const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
   u32 parity = 0;
@@ -396,42 +396,50 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     bm[tid] = 0;
     for (u32 i = tid; i < LZ_HCOPIES * LZ_NSYM; i += LZ_THREADS) hcopies[i] = 0;
     __syncthreads();
-    if (tid < LZ_NWALK) {
-      const u32 s = tid * LZ_RANGE;
-      if (s < own_len) {
-        const u32 e = umin(s + LZ_RANGE, own_len);
-        u32 pos = s;
-        while (pos < e) {
-          bm[pos >> 5] |= 1u << (pos & 31);
-          u32 len = lz_parse_len(XR, pos, own_len, P.lazy);
-          pos += len ? len : 1;
-        }
-        specexit[tid] = pos;
+    // Every walker parses its range from the range start (speculation), recording token starts in the
+    // bitmap and where it left the range.  Then, in rounds, every walker whose true entry (= where the
+    // previous range was really left) differs from the entry it last used re-parses from there until
+    // it meets its old path again — a greedy parse re-synchronises within a few tokens — so almost
+    // all ranges are final after two rounds; the loop ends when no exit moved.
+    const bool walker = tid < LZ_NWALK && tid * LZ_RANGE < own_len;
+    const u32 ws = tid * LZ_RANGE, we = umin(ws + LZ_RANGE, own_len);
+    u32 wentry = ws;
+    if (walker) {
+      u32 pos = ws;
+      while (pos < we) {
+        bm[pos >> 5] |= 1u << (pos & 31);
+        u32 len = lz_parse_len(XR, pos, own_len, P.lazy);
+        pos += len ? len : 1;
       }
+      specexit[tid] = pos;
     }
-    __syncthreads();
-    if (tid == 0) {  // stitch: the true parse enters range t where range t-1 really left off
-      u32 entry = 0;
-      for (u32 t = 0; t < LZ_NWALK; t++) {
-        const u32 s = t * LZ_RANGE;
-        if (s >= own_len) break;
-        const u32 e = umin(s + LZ_RANGE, own_len);
-        if (entry == s) { entry = specexit[t]; continue; }
-        lz_clear_bits(bm, s, umin(entry, e));
-        if (entry >= e) continue;
-        u32 pos = entry;
-        for (;;) {
-          if (pos >= e) { entry = pos; break; }
-          if ((bm[pos >> 5] >> (pos & 31)) & 1) { entry = specexit[t]; break; }  // re-synchronised
-          bm[pos >> 5] |= 1u << (pos & 31);
-          u32 len = lz_parse_len(XR, pos, own_len, P.lazy);
-          u32 nxt = pos + (len ? len : 1);
-          lz_clear_bits(bm, pos + 1, umin(nxt, e));
-          pos = nxt;
+    for (;;) {
+      __syncthreads();
+      const u32 entry = (walker && tid > 0) ? specexit[tid - 1] : ws;
+      __syncthreads();  // every exit has been read before any is rewritten
+      int changed = 0;
+      if (walker && entry != wentry) {
+        wentry = entry;
+        u32 exitpos = specexit[tid];
+        lz_clear_bits(bm, ws, umin(entry, we));
+        if (entry >= we) {
+          exitpos = entry;  // a token of the previous range covers this one entirely
+        } else {
+          u32 pos = entry;
+          for (;;) {
+            if (pos >= we) { exitpos = pos; break; }
+            if ((bm[pos >> 5] >> (pos & 31)) & 1) break;  // re-synchronised: the rest of the old path, and its exit, stand
+            bm[pos >> 5] |= 1u << (pos & 31);
+            u32 len = lz_parse_len(XR, pos, own_len, P.lazy);
+            u32 nxt = pos + (len ? len : 1);
+            lz_clear_bits(bm, pos + 1, umin(nxt, we));
+            pos = nxt;
+          }
         }
+        if (exitpos != specexit[tid]) { specexit[tid] = exitpos; changed = 1; }
       }
+      if (!__syncthreads_or(changed)) break;
     }
-    __syncthreads();
 
     // S5: emit tokens and count symbols
     {

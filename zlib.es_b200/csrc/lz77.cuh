@@ -55,6 +55,7 @@ constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256]
 constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] | specexit u32[64] | mbarrier
 constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 232448 available)
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position
+constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
 // per-warp candidate ring: 64 entries of 8 bytes, stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
 static_assert(LZ_WARPS * 128 * 8 <= 32768, "candidate rings overlay the sort histograms");
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u32 *specexit = scratch + 40;                                      // [LZ_NWALK]
   u64 *mbar = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK);     // 8-byte aligned: (40+128)*4 = 672
   u64 *red = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK + 2);  // [2][LZ_WARPS] u64
+  u32 *slice_ctr = scratch + 40 + LZ_NWALK + 2 + 4 * LZ_WARPS;       // S3 work counter
 
   const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
   u32 parity = 0;
@@ -276,6 +278,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       if (lane == 0) { red[w] = a; red[LZ_WARPS + w] = bsum; }
       __syncthreads();
       if (tid == 0) {
+        *slice_ctr = 0;  // consumed in S3, several barriers from here
         u64 ta = 0, tb = 0;
         for (int i = 0; i < LZ_WARPS; i++) { ta += red[i]; tb += red[LZ_WARPS + i]; }
         P.adler_part[2 * (size_t)b] = ta;
@@ -291,10 +294,17 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     // S3: per-position match search.  Warp w owns sorted entries [kbeg, kend).
     {
       uint2 *ring = reinterpret_cast<uint2 *>(smem + LZ_OFF_WH) + w * 128;
-      const u32 kbeg = umin(w * per, N), kend = umin(kbeg + per, N);
       const u32 scan = umin(P.max_checks, LZ_SCAN);
+      // slices of LZ_SLICE sorted entries are handed out dynamically (their cost depends on the run structure)
+      for (;;) {
+      u32 slice = 0;
+      if (lane == 0) slice = atomicAdd(slice_ctr, 1u);
+      slice = __shfl_sync(ZLES_FULL, slice, 0);
+      const u32 kbeg = slice * LZ_SLICE;
+      if (kbeg >= N) break;
+      const u32 kend = umin(kbeg + LZ_SLICE, N);
       u32 Bprev = 0, hprev = 0xffffffffu;
-      if (kbeg > 0 && kbeg < kend) {  // the 32 entries before the slice are candidates of its first ones (kbeg is a multiple of 32)
+      if (kbeg > 0) {  // the 32 entries before the slice are candidates of its first ones (kbeg is a multiple of 32)
         const u32 j = kbeg - 32 + lane;
         const u32 pj = X[j];
         u32 lo, hi;
@@ -306,6 +316,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         if (lane == 0) hl = 0xffffffffu;  // whether entry kbeg-32 starts a run never matters (see rrun below)
         Bprev = __ballot_sync(ZLES_FULL, hj != hl);
         hprev = __shfl_sync(ZLES_FULL, hj, 31);
+        __syncwarp();
       }
       for (u32 kb = kbeg; kb < kend; kb += 32) {
         const u32 k = kb + lane;
@@ -386,6 +397,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         Bprev = B;
         __syncwarp();  // the next batch overwrites the older half of the ring
       }
+      }  // slices
       // positions without a full 3-byte key (the last two of the window+block) have no match
       if (tid < 2 && own_len > tid) R[own_len - 1 - tid] = 0;
     }

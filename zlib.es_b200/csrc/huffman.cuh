@@ -183,11 +183,11 @@ __device__ __forceinline__ void huf_putbits(u32 *buf, u32 &pos, u32 v, u32 nb) {
   pos += nb;
 }
 
-__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 nblocks, BlockCodes *codes, u32 *blk_bits) {
+__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 first_block, u32 nblocks, BlockCodes *codes, u32 *blk_bits) {
   ZLES_SMEM_DECL(smem_raw);
   HufWarpSmem *S = reinterpret_cast<HufWarpSmem *>(smem_raw) + warp_id();
   const u32 lane = lane_id();
-  const u32 b = blockIdx.x * HUF_WARPS + warp_id();
+  const u32 b = first_block + blockIdx.x * HUF_WARPS + warp_id();
   if (b >= nblocks) return;  // whole warp leaves; no CTA barrier below
   for (u32 i = lane; i < 320; i += 32) S->freq[i] = hist[(size_t)b * 320 + i];
   __syncwarp();

@@ -63,7 +63,8 @@ static_assert(LZ_WARPS * 128 * 8 <= 32768, "candidate rings overlay the sort his
 struct LzParams {
   const u8 *in;       // this shard's input
   u64 n;              // its length
-  u32 nblocks;        // ceil(n / SUB)
+  u32 first_block = 0; // this launch covers blocks [first_block, nblocks)
+  u32 nblocks;        // ceil(n / SUB), or the end of the slab
   u32 *tokens;        // [nblocks][SUB]
   u32 *ntok;          // [nblocks]
   u32 *hist;          // [nblocks][LZ_NSYM]
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u32 *Y = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // sort pass buffer, 2 * SUB entries
   u32 *R = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // then the match results, SUB entries
 
-  for (u32 b = blockIdx.x; b < P.nblocks; b += gridDim.x) {
+  for (u32 b = P.first_block + blockIdx.x; b < P.nblocks; b += gridDim.x) {
     u64 own_off = (u64)b * SUB;
     u32 own_len, hist_len;
     if (P.table) {

@@ -93,6 +93,7 @@ struct HostMail {
 struct zles_ctx {
   int device = 0;
   zrt_stream_t stream{};
+  zrt_stream_t copy_stream{};  // host<->device copies that overlap kernels on `stream`
   bool own_stream = false;
   int sm_count = 148;
   uint64_t launches = 0;
@@ -216,6 +217,8 @@ extern "C" int zles_ctx_create(int device, zles_ctx **out) {
   zrt_err_t e = zrt_stream_create(&c->stream);
   if (e != ZRT_OK) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
   c->own_stream = true;
+  e = zrt_stream_create(&c->copy_stream);
+  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); delete c; return cuda_fail(e, "cudaStreamCreate"); }
   c->sm_count = zrt_sm_count(device);
   void *m = nullptr;
   e = zrt_host_alloc(&m, sizeof(HostMail));
@@ -241,6 +244,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   if (c->d_corpus) zrt_free(c->d_corpus);
   if (c->mail) zrt_host_free(c->mail);
   if (c->own_stream) zrt_stream_destroy(c->stream);
+  zrt_stream_destroy(c->copy_stream);
   delete c;
 }
 
@@ -365,7 +369,9 @@ extern "C" size_t zles_deflate_bound(size_t n) {
   return 6 + n + (n >> 3) + nblocks * 328 + 64;
 }
 
-static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info) {
+// h_src != nullptr: d_in is a staging buffer that is filled from host memory slab by slab on the copy
+// stream while the matcher already works on earlier slabs (blocks are independent per 128 KiB chunk).
+static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info, const u8 *h_src = nullptr) {
   c->p1_valid = false;
   if (!is_last && (n % CHUNK) != 0) return ZLES_E_ARG;
   if (!is_last && n == 0) {  // an empty shard in front of the last one contributes nothing
@@ -408,10 +414,25 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.min_checks = c->min_checks;
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
-  LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
-
-  LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), nblocks,
-         c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+  // slabs of 2 waves of CTAs (a multiple of the SM count keeps the tail of every launch short), whole chunks
+  u32 slab = h_src ? (2u * (u32)c->sm_count / SUBS_PER_CHUNK) * SUBS_PER_CHUNK : nblocks;
+  if (slab == 0 || nblocks < 2 * slab) slab = nblocks;
+  for (u32 b0 = 0; b0 < nblocks; b0 += slab) {
+    const u32 b1 = b0 + slab < nblocks ? b0 + slab : nblocks;
+    if (h_src) {
+      const size_t off = (size_t)b0 * SUB, len = (size_t)umin64((u64)(b1 - b0) * SUB, (u64)n - off);
+      if (len) CK(zrt_h2d(const_cast<u8 *>(d_in) + off, h_src + off, len, c->copy_stream));
+      zrt_event_t ev = timing_event(c);
+      CK(zrt_event_record(ev, c->copy_stream));
+      CK(zrt_stream_wait_event(c->stream, ev));
+      c->event_pool.push_back(ev);  // recorded and waited on in stream order; reusable once this call has synchronised
+    }
+    lp.first_block = b0;
+    lp.nblocks = b1;
+    LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
+    LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
+           c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+  }
 
   LayoutParams yp;
   yp.blk_bits = c->blk_bits.as<u32>();
@@ -526,9 +547,8 @@ extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *o
   if ((!in && n) || !out_len) return ZLES_E_ARG;
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
-  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
   zles_shard_info info;
-  RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info));
+  RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info, in));  // the host-to-device copy is pipelined with the matcher
   const size_t need = (size_t)info.comp_bytes + 6;
   *out_len = need;
   if (!out || cap < need) return ZLES_E_OUTPUT_FULL;
@@ -924,7 +944,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   lp.lazy = c->lazy;
   lp.table = d_tab;
   LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
-  LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), nblocks,
+  LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), 0u, nblocks,
          c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
   BatchPackParams bp;
   bp.tokens = c->tokens.as<u32>();

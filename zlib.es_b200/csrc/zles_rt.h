@@ -38,6 +38,7 @@ static inline zrt_err_t zrt_event_destroy(zrt_event_t) { return 0; }
 static inline zrt_err_t zrt_event_record(zrt_event_t, zrt_stream_t) { return 0; }
 static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t, zrt_event_t) { *ms = 0; return 0; }
 static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t) { memmove(d, s, n); return 0; }
+static inline zrt_err_t zrt_stream_wait_event(zrt_stream_t, zrt_event_t) { return 0; }
 #define ZLES_LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
 #else
@@ -67,6 +68,7 @@ static inline zrt_err_t zrt_event_create(zrt_event_t *e) { return cudaEventCreat
 static inline zrt_err_t zrt_event_destroy(zrt_event_t e) { return cudaEventDestroy(e); }
 static inline zrt_err_t zrt_event_record(zrt_event_t e, zrt_stream_t s) { return cudaEventRecord(e, s); }
 static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t a, zrt_event_t b) { return cudaEventElapsedTime(ms, a, b); }
+static inline zrt_err_t zrt_stream_wait_event(zrt_stream_t s, zrt_event_t e) { return cudaStreamWaitEvent(s, e, 0); }
 // device, host or peer-mapped pointers on either side (unified addressing)
 static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, st); }
 static inline int zrt_sm_count(int dev) {

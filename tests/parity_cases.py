@@ -95,3 +95,36 @@ def error_strings(c):
             assert str(e) == msg, (stream, str(e))
         else:
             raise AssertionError("no error for %r" % stream)
+
+
+def output_full_protocol(c):
+    """ZLES_E_OUTPUT_FULL reports the size needed; a second call with that size succeeds."""
+    import numpy as np
+    data = T.gen("G5", 100000)
+    small = np.zeros(10, dtype=np.uint8)
+    try:
+        c.deflate_into(data, small)
+    except Exception as e:
+        assert getattr(e, "code", None) == 16, e
+    else:
+        raise AssertionError("deflate into 10 bytes succeeded")
+    z = c.deflate(data)
+    for cap in (0, 1, 50000, 99999):
+        out = np.zeros(max(cap, 1), dtype=np.uint8)[:cap]
+        try:
+            c.inflate_into(z, out)
+        except Exception as e:
+            assert getattr(e, "code", None) == 16, (cap, e)
+        else:
+            raise AssertionError("inflate into %d bytes succeeded" % cap)
+    out = np.zeros(100000, dtype=np.uint8)
+    assert c.inflate_into(z, out) == 100000 and out.tobytes() == data
+    # a foreign stream (sequential path) follows the same protocol
+    zf = zlib.compress(data, 6)
+    try:
+        c.inflate_into(zf, np.zeros(5000, dtype=np.uint8))
+    except Exception as e:
+        assert getattr(e, "code", None) == 16, e
+    else:
+        raise AssertionError("inflate of a foreign stream into 5000 bytes succeeded")
+    assert c.inflate_into(zf, out) == 100000 and out.tobytes() == data

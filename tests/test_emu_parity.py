@@ -71,6 +71,10 @@ def test_lenient_and_errors(c):
     P.error_strings(c)
 
 
+def test_output_full_protocol(c):
+    P.output_full_protocol(c)
+
+
 def test_false_marker_in_payload(c):
     # the marker bytes 00 00 FF FF inside a stored block are not block boundaries
     payload = (b"\x00\x00\xff\xff" * 50 + b"abc") * 20

@@ -124,6 +124,10 @@ def test_lenient_and_errors(c):
     P.error_strings(c)
 
 
+def test_output_full_protocol(c):
+    P.output_full_protocol(c)
+
+
 def test_truncated_streams_raise(c):
     z = c.deflate(T.gen("G5", 100000))
     for cut in (len(z) // 3, len(z) - 10):

@@ -641,7 +641,13 @@ static void decode_table_build(DecodeTable *t, const int *lens, int n) {
 }
 /* the lookup loop at src/inflate.ts:238-252 / 84-96 / 155-168 */
 static int decode_symbol(BitReadStream *s, const DecodeTable *t, int *err) {
-  if (t->lmin > t->lmax) { *err = ZO_E_CORRUPTED; return -1; }
+  if (t->lmin > t->lmax) {
+    /* empty table: Math.min over no keys leaves codelenMin = Number.MAX_SAFE_INTEGER (src/inflate.ts:139-147,
+     * 206-224), so readRangeCoded(codelenMin) (src/utils/BitReadStream.ts:42-49) keeps calling read() until the
+     * buffer is exhausted and read() throws */
+    *err = ZO_E_LACK;
+    return -1;
+  }
   int codelen = t->lmin;
   uint32_t code = brs_readRangeCoded(s, t->lmin);
   if (s->err) { *err = s->err; return -1; }

@@ -128,3 +128,39 @@ def output_full_protocol(c):
     else:
         raise AssertionError("inflate of a foreign stream into 5000 bytes succeeded")
     assert c.inflate_into(zf, out) == 100000 and out.tobytes() == data
+
+
+def _outcome(f, z):
+    try:
+        return ("ok", f(z))
+    except Exception as e:
+        return ("err", str(e))
+
+
+def truncation_sweep(c, streams, step=1):
+    """Every prefix of a stream gives the reference's outcome: the same error text, or — the reference returns
+    partial data without an error when the last bit of the buffer is consumed by a Huffman-code read inside a
+    final block (BitReadStream.isEnd, /root/reference/src/utils/BitReadStream.ts:14-31, src/inflate.ts:34-36,76,237)
+    — the same partial bytes, including the effect of the stale bit read() leaves behind."""
+    for z in streams:
+        for cut in range(0, len(z), step):
+            a, b = _outcome(O.inflate, z[:cut]), _outcome(c.inflate, z[:cut])
+            assert a == b, (cut, a[0], a[1][-16:] if a[0] == "ok" else a[1], b[0], b[1][-16:] if b[0] == "ok" else b[1])
+
+
+def bitflip_sweep(c, streams, trials, seed=5):
+    """Single-bit corruptions: same garbage or same error as the reference."""
+    import random
+    rnd = random.Random(seed)
+    for z in streams:
+        for _ in range(trials):
+            pos = rnd.randrange(2, len(z))
+            zz = bytearray(z)
+            zz[pos] ^= 1 << rnd.randrange(8)
+            a, b = _outcome(O.inflate, bytes(zz)), _outcome(c.inflate, bytes(zz))
+            assert a == b, (pos, a[0], a[1][-16:] if a[0] == "ok" else a[1], b[0], b[1][-16:] if b[0] == "ok" else b[1])
+
+
+def damaged_streams(c):
+    d = T.gen("G5", 3000)
+    return [c.deflate(d), zlib.compress(d, 6), O.deflate(d), zlib.compress(T.gen("G3", 300), 0), T.FIXED, c.deflate(T.gen("G5", 40000))]

@@ -71,6 +71,13 @@ def test_lenient_and_errors(c):
     P.error_strings(c)
 
 
+def test_truncated_and_corrupted_streams_match_the_reference(c):
+    streams = P.damaged_streams(c)
+    P.truncation_sweep(c, streams[:5], step=7)
+    P.truncation_sweep(c, streams[5:], step=97)
+    P.bitflip_sweep(c, streams, trials=12)
+
+
 def test_output_full_protocol(c):
     P.output_full_protocol(c)
 

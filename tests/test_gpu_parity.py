@@ -128,13 +128,11 @@ def test_output_full_protocol(c):
     P.output_full_protocol(c)
 
 
-def test_truncated_streams_raise(c):
-    z = c.deflate(T.gen("G5", 100000))
-    for cut in (len(z) // 3, len(z) - 10):
-        with pytest.raises(Exception):
-            c.inflate(z[:cut])
-        with pytest.raises(O.OracleError):
-            O.inflate(z[:cut])
+def test_truncated_and_corrupted_streams_match_the_reference(c):
+    streams = P.damaged_streams(c)
+    P.truncation_sweep(c, streams[:5], step=1)
+    P.truncation_sweep(c, streams[5:], step=41)
+    P.bitflip_sweep(c, streams, trials=150)
 
 
 def test_marker_bytes_inside_data(c):

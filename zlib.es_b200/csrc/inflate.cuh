@@ -205,10 +205,58 @@ __device__ __forceinline__ bool inf_decode(InfReader &r, const u16 *lut, int roo
   return true;
 }
 
+// One Huffman-coded symbol in the sequential decoder, with the reference's end-of-buffer bookkeeping.
+// The reference reads code bits one at a time through BitReadStream.read()
+// (/root/reference/src/utils/BitReadStream.ts:14-31): a read() that consumes the last bit of the last
+// byte — or of a "phantom" zero byte that an earlier readRange() pulled in past the end — sets isEnd,
+// and any read() after that throws 'Lack of data length'.  readRange() (header fields, extra bits,
+// stored bytes) never sets isEnd and silently yields zeros past the end.  The symbol loops run
+// `while (!stream.isEnd)` and the block loop throws 'Data length is insufficient' when a non-final
+// block ends with isEnd set (/root/reference/src/inflate.ts:34-36).  Returns 0 or a SEG_E_* code.
+// When isEnd is set, read() leaves the bit it just consumed in nowBits with nowBitsLength = 0, so the NEXT
+// readRange() returns that bit again as its first bit, followed by zeros: `stale` carries it (inf_extra).
+__device__ __forceinline__ u32 inf_coded(InfReader &r, const u16 *lut, int root, const InfTab *t, const u16 *sorted, u64 nbits,
+                                         u32 &is_end, u32 &stale, u32 &sym) {
+  const u32 e = lut[r.peek((u32)root)];
+  u32 l = e & 15;
+  sym = e >> 4;
+  bool found = true;
+  if (l == 0) found = inf_slow(r.bb, t, sorted, sym, l);
+  const u64 P = r.bitpos();
+  if (P + 64 >= nbits) {  // only near the end of the buffer can the bookkeeping matter
+    if (is_end) return SEG_E_LACK;
+    u32 L = l;
+    if (!found) {  // the reference reads up to the longest code of the table before giving up
+      L = 0;
+      for (int k = 15; k >= 1; k--)
+        if (t->cnt[k]) { L = (u32)k; break; }
+      if (L == 0) return SEG_E_LACK;  // empty table: it reads until the buffer ends
+    }
+    const u64 x0 = P > nbits - 1 ? P : nbits - 1;
+    const u64 E = x0 + ((7 - (x0 & 7)) & 7);  // first bit position >= x0 that is the last bit of a byte
+    if (E < P + L - 1) return SEG_E_LACK;     // a read() after the one that reached the end
+    if (E == P + L - 1) {
+      is_end = 1;
+      stale = (u32)(r.bb >> (L - 1)) & 1;
+    }
+  }
+  if (!found) return SEG_E_CORRUPT;
+  r.skip(l);
+  return 0;
+}
+
+// readRange(k) of the sequential decoder (extra bits): after isEnd the first bit is the stale one, the rest are
+// phantom zeros (everything past the end of the buffer reads as zero)
+__device__ __forceinline__ u32 inf_extra(InfReader &r, u32 k, u32 &stale) {
+  u32 v = r.take(k);
+  if (k && stale) { v |= 1; stale = 0; }
+  return v;
+}
+
 // Dynamic block header (/root/reference/src/inflate.ts:121-202): HLIT/HDIST/HCLEN, the code-length
 // code, then the run-length coded literal/length and distance code lengths into S->lens.
 // Returns false with `status` set on error.  Warp-uniform.
-__device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSmem *S, u32 &status) {
+__device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSmem *S, u64 nbits, u32 &is_end, u32 &stale, u32 &status) {
   const u32 lane = lane_id();
   const u32 HLIT = r.take(5) + 257;
   const u32 HDIST = r.take(5) + 1;
@@ -227,13 +275,13 @@ __device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSme
   u32 prev = 0;
   for (u32 i = 0; i < total;) {
     r.refill();
-    if (r.overrun) { status = SEG_E_LACK; return false; }
     u32 sym;
-    if (!inf_decode(r, S->lut_d, CL_ROOT, &S->tab_d, S->sorted_d, sym)) { status = SEG_E_CORRUPT; return false; }
+    const u32 rc = inf_coded(r, S->lut_d, CL_ROOT, &S->tab_d, S->sorted_d, nbits, is_end, stale, sym);
+    if (rc) { status = rc; return false; }
     u32 rep = 1, val = sym;
-    if (sym == 16) { rep = 3 + r.take(2); val = prev; }
-    else if (sym == 17) { rep = 3 + r.take(3); val = 0; prev = 0; }
-    else if (sym == 18) { rep = 11 + r.take(7); val = 0; prev = 0; }
+    if (sym == 16) { rep = 3 + inf_extra(r, 2, stale); val = prev; }
+    else if (sym == 17) { rep = 3 + inf_extra(r, 3, stale); val = 0; prev = 0; }
+    else if (sym == 18) { rep = 11 + inf_extra(r, 7, stale); val = 0; prev = 0; }
     else prev = sym;
     if (val) {
       for (u32 k = lane; k < rep; k += 32) {
@@ -259,14 +307,15 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
   u32 status = 0, flags = 0;
   u64 end_pos = 0;
 
+  const u64 nbits = n << 3;
+  u32 is_end = 0, stale = 0;  // BitReadStream.isEnd and the bit it leaves behind, see inf_coded
   for (;;) {  // blocks, /root/reference/src/inflate.ts:22-37
     r.refill();
-    if (r.overrun) { status = SEG_E_LACK; break; }
-    if (r.bitpos() >= (n << 3)) { status = SEG_E_INSUFF; break; }
+    if (r.bitpos() > nbits + (1u << 20)) { status = SEG_E_LACK; break; }  // cannot happen (see inf_coded); bounds the loop
     const u32 bfinal = r.take(1);
     const u32 btype = r.take(2);
     if (btype == 3) { status = SEG_E_BTYPE3; break; }
-    if (btype == 0) {  // stored, src/inflate.ts:42-55
+    if (btype == 0) {  // stored, src/inflate.ts:42-55: readRange only — bytes past the end are zeros, never an error
       r.skip((u32)((0 - r.bitpos()) & 7));
       r.refill();
       const u32 LEN = r.take(16);
@@ -279,8 +328,8 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
         if (opos + i < cap) out[opos + i] = v;
       }
       opos += LEN;
-      if (q + LEN > n) { status = SEG_E_LACK; break; }
       if (bfinal) { status = SEG_FINAL; end_pos = q + LEN; break; }
+      if (is_end) { status = SEG_E_INSUFF; break; }  // src/inflate.ts:34-36
       if (LEN == 0 && stop_at_sync) { status = SEG_SYNC; end_pos = q; break; }
       r.init(in, n, q + LEN);
       continue;
@@ -289,17 +338,17 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
       for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
       __syncwarp();
     } else {  // dynamic header, src/inflate.ts:121-202
-      if (!inf_read_dynamic_header(r, S, status)) break;
+      if (!inf_read_dynamic_header(r, S, nbits, is_end, stale, status)) break;
     }
     inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
     inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
 
-    // symbol loop, src/inflate.ts:76-117 / 237-291
-    for (;;) {
+    // symbol loop, src/inflate.ts:76-117 / 237-291: `while (!stream.isEnd)`
+    while (!is_end) {
       r.refill();
-      if (r.overrun) { status = SEG_E_LACK; break; }
       u32 sym;
-      if (!inf_decode(r, S->lut_ll, LL_ROOT, &S->tab_ll, S->sorted_ll, sym)) { status = SEG_E_CORRUPT; break; }
+      u32 rc = inf_coded(r, S->lut_ll, LL_ROOT, &S->tab_ll, S->sorted_ll, nbits, is_end, stale, sym);
+      if (rc) { status = rc; break; }
       if (sym < 256) {
         if (lane == 0 && opos < cap) out[opos] = (u8)sym;
         opos++;
@@ -308,13 +357,14 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
       if (sym == 256) break;
       const u32 ls = sym - 257;
       if (ls >= 29) { status = SEG_E_CORRUPT; break; }
-      const u32 len = c_len_base[ls] + r.take(c_len_extra[ls]);
+      const u32 len = c_len_base[ls] + inf_extra(r, c_len_extra[ls], stale);
       r.refill();
       u32 ds;
-      if (!inf_decode(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, ds)) { status = SEG_E_CORRUPT; break; }
+      rc = inf_coded(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, nbits, is_end, stale, ds);
+      if (rc) { status = rc; break; }
       if (ds >= 30) { status = SEG_E_CORRUPT; break; }
       r.refill();
-      const u32 dist = c_dist_base[ds] + r.take(c_dist_extra[ds]);
+      const u32 dist = c_dist_base[ds] + inf_extra(r, c_dist_extra[ds], stale);
       // back-reference copy, src/inflate.ts:287-290; bytes before the start read as 0
       const long long src = (long long)opos - (long long)dist;
       if (src < (long long)obase) flags |= SEGF_HISTORY;
@@ -336,7 +386,8 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
       __syncwarp();
     }
     if (status) break;
-    if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
+    if (bfinal) { status = SEG_FINAL; end_pos = umin64((r.bitpos() + 7) >> 3, n); break; }
+    if (is_end) { status = SEG_E_INSUFF; break; }  // src/inflate.ts:34-36
   }
   if (opos > cap) flags |= SEGF_OVERFLOW;
   if (lane == 0) {
@@ -555,7 +606,7 @@ struct TokReader {
   __device__ __forceinline__ u32 take(u32 k) { const u32 v = peek(k); skip(k); return v; }
   __device__ __forceinline__ u64 bits64() const { return ((u64)hi << 32) | lo; }
   __device__ __forceinline__ u64 bitpos() const { return ((wabs + wi) << 5) - bc - ((u64)skew << 3); }
-  __device__ __forceinline__ bool past_end() const { return bitpos() > (n << 3) + 64; }
+  __device__ __forceinline__ bool past_end() const { return bitpos() > (n << 3); }  // consumed bits the buffer does not have
 };
 
 // dynamic block header for phase A (same as inf_read_dynamic_header, on the TokReader)

@@ -20,11 +20,12 @@ namespace zles {
 constexpr int HUF_WARPS = 4;
 constexpr int HUF_THREADS = HUF_WARPS * 32;
 constexpr u32 HDR_BYTES = 576;  // >= ceil((14 + 19*3 + 316*14) / 8) = 562
+constexpr u32 HUF_STORED = 0xffffffffu;  // BlockCodes::hdr_nbits of a block that is smaller stored (BTYPE=0) than coded
 
 struct BlockCodes {       // written by k_huff, read by k_pack
   u32 ll[288];            // (bit-reversed code << 8) | length, 0 for unused symbols
   u32 d[32];
-  u32 hdr_nbits;          // HLIT..code lengths, starts right after BFINAL/BTYPE
+  u32 hdr_nbits;          // HLIT..code lengths, starts right after BFINAL/BTYPE; HUF_STORED: emit the block stored
   u32 pad_[3];
   u8 hdr[HDR_BYTES];      // header bits, LSB first
 };
@@ -183,7 +184,9 @@ __device__ __forceinline__ void huf_putbits(u32 *buf, u32 &pos, u32 v, u32 nb) {
   pos += nb;
 }
 
-__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 first_block, u32 nblocks, BlockCodes *codes, u32 *blk_bits) {
+// own_len[b] = input bytes of block b: n and table describe them as in LzParams (one stream, or a batch table).
+__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 first_block, u32 nblocks, BlockCodes *codes, u32 *blk_bits,
+                                                      u64 n, const BatchBlk *__restrict__ table) {
   ZLES_SMEM_DECL(smem_raw);
   HufWarpSmem *S = reinterpret_cast<HufWarpSmem *>(smem_raw) + warp_id();
   const u32 lane = lane_id();
@@ -278,8 +281,19 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hi
   C->d[lane] = S->code[288 + lane];
   for (u32 i = lane; i < HDR_BYTES / 4; i += 32) reinterpret_cast<u32 *>(C->hdr)[i] = S->hdr[i];
   if (lane == 0) {
-    C->hdr_nbits = hbits;
-    blk_bits[b] = 3 + hbits + bits;
+    // The reference always emits BTYPE=2 (src/deflate.ts:28) and so expands incompressible data; a stored block
+    // (3 header bits + pad, LEN, NLEN, the bytes: RFC 1951 3.2.4) is taken when it is smaller.  Blocks start on a
+    // byte boundary, so a stored block costs exactly 5 + own_len bytes.
+    const u32 own_len = table ? table[b].own_len : (u32)umin64((u64)SUB, n - (u64)b * SUB);
+    const u32 coded = 3 + hbits + bits;
+    const u32 stored = 8 * (5 + own_len);
+    if (stored < ((coded + 7) & ~7u)) {
+      C->hdr_nbits = HUF_STORED;
+      blk_bits[b] = stored;
+    } else {
+      C->hdr_nbits = hbits;
+      blk_bits[b] = coded;
+    }
   }
 }
 

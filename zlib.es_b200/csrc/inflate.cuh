@@ -515,6 +515,7 @@ k_mark_emit(const u8 *__restrict__ in, u64 n, u64 first, const u32 *tile_base, u
 //                           of 32 tokens at a time, in rounds that respect their dependencies.
 // Tokens use the encoder's format (lz77.cuh): literal = byte value; match = bit31 | (len-3)<<16 | (dist-1).
 constexpr u32 SEGF_BADREF = 4;            // a distance reached before the start of the chunk
+constexpr u32 SEGF_STORED = 8;            // the segment's data block is a stored one: no tokens, phase B copies the bytes
 
 // Phase A uses 32-bit LUT entries so that one shared-memory load yields everything about a symbol:
 //   bits 0-3 code length (0 = longer than the root: canonical slow path) | bits 4-7 extra-bit count |
@@ -681,11 +682,22 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
       r.refill();
       const u32 NLEN = r.take(16);
       if (LEN + NLEN != 65535) { status = SEG_E_CORRUPT; break; }
-      if (LEN != 0) { status = SEG_E_CORRUPT; break; }  // stored data: not one of our streams, sequential path
-      end_pos = r.bitpos() >> 3;
+      const u64 q = r.bitpos() >> 3;
+      if (LEN != 0) {
+        // a stored data block: ours only as the one data block of its segment (incompressible input, see k_huff);
+        // phase B copies the bytes [q, q + LEN) from the input.  Anything else takes the sequential path.
+        if (o != 0 || nt != 0 || (flags & SEGF_STORED) || LEN > SUB || q + LEN > n) { status = SEG_E_CORRUPT; break; }
+        flags |= SEGF_STORED;
+        o = LEN;
+        if (bfinal) { status = SEG_FINAL; end_pos = q + LEN; break; }
+        r.init(in, n, q + LEN);
+        continue;
+      }
+      end_pos = q;
       status = bfinal ? SEG_FINAL : SEG_SYNC;
       break;
     }
+    if (flags & SEGF_STORED) { status = SEG_E_CORRUPT; break; }  // a coded block after stored data: not one of ours
     if (btype == 1) {
       for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
       __syncwarp();
@@ -779,8 +791,8 @@ constexpr u32 RES_RING = 16384;      // >= 2 x the most a batch can produce (32 
 constexpr int RES_SMEM = (int)(RES_WARPS * RES_RING);
 
 __global__ void __launch_bounds__(RES_THREADS)
-k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg, u8 *out, u64 cap,
-              u32 *problems) {
+k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg,
+              const u8 *__restrict__ in, const InfRes *__restrict__ res, u8 *out, u64 cap, u32 *problems) {
   ZLES_SMEM_DECL(smem_raw);
   u8 *ring = smem_raw + warp_id() * RES_RING;
   constexpr u32 RM = RES_RING - 1;
@@ -795,6 +807,21 @@ k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, cons
     const u32 e = c * SUBS_PER_CHUNK + k;
     if (e >= nseg) break;
     const u32 sidx = seg_list ? seg_list[e] : e;
+    if (res[sidx].flags & SEGF_STORED) {  // stored block: the bytes sit in the input right before the marker / the end
+      const InfRes r = res[sidx];
+      const u32 len = (u32)r.out_len;
+      const u8 *srcp = in + (r.end_pos - len - (r.status == SEG_SYNC ? 5 : 0));
+      if (o + len > CHUNK) { bad |= 1; break; }
+      if (o + len > room) { bad |= 2; break; }
+      for (u32 q = lane; q < len; q += 32) {
+        const u8 v = srcp[q];
+        base[o + q] = v;
+        ring[(o + q) & RM] = v;
+      }
+      __syncwarp();
+      o += len;
+      continue;
+    }
     const u32 nt = umin(ntok[sidx], SUB);
     const u32 *tok = tokens + (size_t)sidx * SUB;
     u32 tnext = lane < nt ? __ldg(tok + lane) : 0;

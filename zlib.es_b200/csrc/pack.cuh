@@ -95,6 +95,8 @@ struct PackParams {
   u32 nblocks;
   u32 last_is_final;
   u8 *out;                 // destination of this shard's first byte (local or peer memory)
+  const u8 *in;            // the shard's input (stored blocks copy from it)
+  u64 n;
 };
 
 struct PackState {
@@ -168,13 +170,38 @@ __device__ __forceinline__ void pack_finish(PackState &st) {
 
 // Appends deflate blocks [b0, b1) bit-concatenated and then either the final pad
 // (src/deflate.ts:35-37) or the empty stored block that makes the next block byte aligned.
+// raw[b] = the block's own input bytes (for stored blocks), raw_len = their number.
 __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *tokens, const u32 *ntok, const BlockCodes *codes,
-                                           u32 b0, u32 b1, bool final_chunk) {
+                                           u32 b0, u32 b1, bool final_chunk, const u8 *raw, u32 raw_len) {
   const u32 tid = threadIdx.x;
   u64 bits[PACK_ITEMS];
   u32 nb[PACK_ITEMS];
   for (u32 b = b0; b < b1; b++) {
     const BlockCodes *C = codes + b;
+    if (C->hdr_nbits == HUF_STORED) {  // BTYPE=0: header byte, LEN, NLEN, the bytes; then the marker unless final
+      const bool fin = final_chunk && b + 1 == b1;
+      const u32 nitems = 2 + (raw_len + 3) / 4 + (fin ? 0 : 2);  // 8 + 32 header bits | payload words | 8 + 32 marker bits
+      for (u32 base = 0; base < nitems; base += PACK_TILE) {
+#pragma unroll
+        for (int k = 0; k < PACK_ITEMS; k++) {
+          const u32 i = base + tid * PACK_ITEMS + k;
+          bits[k] = 0; nb[k] = 0;
+          if (i == 0) { bits[k] = fin ? 1u : 0u; nb[k] = 8; }                          // BFINAL, BTYPE=00, 5 pad bits
+          else if (i == 1) { bits[k] = raw_len | ((raw_len ^ 0xffffu) << 16); nb[k] = 32; }  // LEN, NLEN
+          else if (i - 2 < (raw_len + 3) / 4) {
+            const u32 o = (i - 2) * 4, cnt = umin(4u, raw_len - o);
+            u32 v = 0;
+            for (u32 q = 0; q < cnt; q++) v |= (u32)raw[o + q] << (8 * q);
+            bits[k] = v; nb[k] = 8 * cnt;
+          } else if (i < nitems) {
+            const u32 m = i - 2 - (raw_len + 3) / 4;                                     // the sync marker: 00 | 00 00 FF FF
+            if (m == 0) { bits[k] = 0; nb[k] = 8; } else { bits[k] = 0xFFFF0000u; nb[k] = 32; }
+          }
+        }
+        pack_emit(st, bits, nb);
+      }
+      continue;
+    }
     for (u32 i = tid; i < 320; i += PACK_THREADS) ctab[i] = i < 288 ? C->ll[i] : C->d[i - 288];
     __syncthreads();
     // block header: BFINAL, BTYPE=2 (src/deflate.ts:21-28), then the code-length header in 32-bit pieces
@@ -257,7 +284,8 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(const PackParams P) {
   if (b >= P.nblocks) return;
   PackState st;
   pack_begin(st, stage, scratch, P.out + P.blk_off[b]);
-  pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, P.last_is_final && b + 1 == P.nblocks);
+  pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, P.last_is_final && b + 1 == P.nblocks, P.in + (u64)b * SUB,
+             (u32)umin64((u64)SUB, P.n - (u64)b * SUB));
   pack_finish(st);
 }
 
@@ -311,6 +339,7 @@ struct BatchPackParams {
   const u64 *in_off;       // [count + 1]
   const u64 *out_off;      // [count + 1]
   u32 count;
+  const u8 *in;            // the batch's input (stored blocks copy from it)
   u8 *out;
   u64 *out_len;            // [count]
   int32_t *status;         // [count]
@@ -368,7 +397,8 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_batch(const BatchPackPara
   for (int k = 0; k < PACK_ITEMS; k++) { bits[k] = 0; nb[k] = 0; }
   if (tid == 0) { bits[0] = 0x9C78u; nb[0] = 16; }  // CMF = 78, FLG = 9C (src/zlib.ts:28-34)
   pack_emit(st, bits, nb);
-  for (u32 b = b0; b < b1; b++) pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, b + 1 == b1);
+  for (u32 b = b0; b < b1; b++)
+    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, b + 1 == b1, P.in + P.table[b].in_off, P.table[b].own_len);
   nb[0] = 0;
   if (tid == 0) {  // big-endian Adler-32 (src/zlib.ts:36-40)
     bits[0] = ((adler >> 24) & 0xff) | ((adler >> 8) & 0xff00) | ((adler << 8) & 0xff0000) | (adler << 24);

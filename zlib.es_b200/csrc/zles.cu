@@ -118,6 +118,7 @@ struct zles_ctx {
   std::vector<KernelTotal> totals;
   // state between phase 1 and phase 2 of a deflate
   bool p1_valid = false;
+  const u8 *p1_in = nullptr;
   u64 p1_n = 0;
   u32 p1_nblocks = 0, p1_nchunks = 0;
   int p1_final = 0;
@@ -362,11 +363,11 @@ extern "C" int zles_adler32(zles_ctx *c, const uint8_t *in, size_t n, uint32_t *
 // ---- deflate (K1..K5) --------------------------------------------------------------------
 
 extern "C" size_t zles_deflate_bound(size_t n) {
-  // every 32 KiB block: <= 3 + 14 + 19*3 + 316*7 header bits, <= 9 bits per literal
-  // (an optimal length-limited code is never worse than a flat 8/9-bit one) and 5 marker bytes.
+  // every 32 KiB block costs at most what it costs stored (5 bytes + its input) plus the 5-byte marker;
+  // 6 bytes of zlib framing.  (Rounded up generously: callers size buffers with this.)
   size_t nblocks = (n + SUB - 1) / SUB;
   if (nblocks == 0) nblocks = 1;
-  return 6 + n + (n >> 3) + nblocks * 328 + 64;
+  return 6 + n + nblocks * 16 + 64;
 }
 
 // h_src != nullptr: d_in is a staging buffer that is filled from host memory slab by slab on the copy
@@ -431,7 +432,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     lp.nblocks = b1;
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
-           c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+           c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);
   }
 
   LayoutParams yp;
@@ -448,6 +449,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   CK(zrt_d2h(c->mail->summary, c->summary.p, 24, c->stream));
   CK(zrt_sync(c->stream));
   c->p1_valid = true;
+  c->p1_in = d_in;
   c->p1_n = n;
   c->p1_nblocks = nblocks;
   c->p1_nchunks = nchunks;
@@ -475,6 +477,8 @@ static int deflate_phase2(zles_ctx *c, u8 *d_dst) {
   pp.nblocks = c->p1_nblocks;
   pp.last_is_final = c->p1_final ? 1u : 0u;
   pp.out = d_dst;
+  pp.in = c->p1_in;
+  pp.n = c->p1_n;
   LAUNCH(c, k_pack, c->p1_nblocks, PACK_THREADS, PACK_SMEM, pp);
   CK(zrt_last_error());
   return 0;
@@ -649,7 +653,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only
     if (room)
       LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
-             (const u32 *)c->ntok.as<u32>(), (const u32 *)nullptr, ncand, d_out, (u64)cap, &ctl->ok_res);
+             (const u32 *)c->ntok.as<u32>(), (const u32 *)nullptr, ncand, d_in, (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap,
+             &ctl->ok_res);
     CK(zrt_last_error());
     InfCtl h;
     RET(read_ctl(c, &h));
@@ -696,7 +701,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
         CK(zrt_sync(c->stream));  // list is host heap memory
         const u32 nch = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
         LAUNCH(c, k_inf_resolve, (nch + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
-               (const u32 *)c->ntok.as<u32>(), (const u32 *)c->seg_pos.as<u32>(), nseg, d_out, (u64)cap, &ctl->ok_res);
+               (const u32 *)c->ntok.as<u32>(), (const u32 *)c->seg_pos.as<u32>(), nseg, d_in, (const InfRes *)c->res.as<InfRes>(), d_out,
+               (u64)cap, &ctl->ok_res);
         CK(zrt_last_error());
         RET(read_ctl(c, &h));
         if (h.ok_res == 0) return 0;
@@ -945,7 +951,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   lp.table = d_tab;
   LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
   LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), 0u, nblocks,
-         c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+         c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)0, (const BatchBlk *)d_tab);
   BatchPackParams bp;
   bp.tokens = c->tokens.as<u32>();
   bp.ntok = c->ntok.as<u32>();
@@ -957,6 +963,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   bp.in_off = d_in_off;
   bp.out_off = d_out_off;
   bp.count = count;
+  bp.in = d_in;
   bp.out = d_out;
   bp.out_len = d_out_len;
   bp.status = d_status;

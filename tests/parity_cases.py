@@ -164,3 +164,24 @@ def bitflip_sweep(c, streams, trials, seed=5):
 def damaged_streams(c):
     d = T.gen("G5", 3000)
     return [c.deflate(d), zlib.compress(d, 6), O.deflate(d), zlib.compress(T.gen("G3", 300), 0), T.FIXED, c.deflate(T.gen("G5", 40000))]
+
+
+def foreign_tier(c, n):
+    """Streams of other encoders — zlib.es's own bit-concatenated blocks (no markers), system zlib at several
+    levels (32 KiB history across blocks, stored and empty blocks) — are decoded by the block-parallel path
+    (k_hdr_scan / k_blk_tokens / k_blk_resolve), not by the sequential warp, and give the reference's bytes."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    data = (T.gen("G5", n // 2) + T.fixture_raw() + rng.integers(0, 256, 20000, dtype=np.uint8).tobytes())[:n]
+    co = zlib.compressobj(6)
+    flushed = co.compress(data[:50000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[50000:]) + co.flush()
+    for name, z in [("zlib.es", O.deflate(data)), ("zlib1", zlib.compress(data, 1)), ("zlib6", zlib.compress(data, 6)),
+                    ("zlib9", zlib.compress(data, 9)), ("zlib0", zlib.compress(data[:200000], 0)), ("sync-flush", flushed),
+                    ("fixture", T.fixture_compressed())]:
+        c.set_timing(True)
+        out = c.inflate(z)
+        used = c.kernel_time("k_blk_resolve")[1]
+        seq = c.kernel_time("k_inflate")[1]
+        c.set_timing(False)
+        assert out == O.inflate(z), name
+        assert used >= 1 and seq == 0, (name, used, seq)

@@ -66,6 +66,10 @@ def test_inflate_system_zlib_streams(c):
     P.inflate_matches_oracle(c, z)  # markers with history across them: must not be taken for our format
 
 
+def test_foreign_streams_decode_in_parallel(c):
+    P.foreign_tier(c, 300000)
+
+
 def test_lenient_and_errors(c):
     P.lenient_like_reference(c)
     P.error_strings(c)
@@ -73,9 +77,9 @@ def test_lenient_and_errors(c):
 
 def test_truncated_and_corrupted_streams_match_the_reference(c):
     streams = P.damaged_streams(c)
-    P.truncation_sweep(c, streams[:5], step=7)
-    P.truncation_sweep(c, streams[5:], step=97)
-    P.bitflip_sweep(c, streams, trials=12)
+    P.truncation_sweep(c, streams[:5], step=41)
+    P.truncation_sweep(c, streams[5:], step=997)
+    P.bitflip_sweep(c, streams, trials=4)
 
 
 def test_output_full_protocol(c):

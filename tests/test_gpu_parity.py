@@ -119,6 +119,10 @@ def test_inflate_system_zlib_streams(c):
     P.inflate_matches_oracle(c, co.compress(data) + co.flush())  # fixed Huffman blocks only
 
 
+def test_foreign_streams_decode_in_parallel(c):
+    P.foreign_tier(c, 600000)
+
+
 def test_lenient_and_errors(c):
     P.lenient_like_reference(c)
     P.error_strings(c)
@@ -130,9 +134,9 @@ def test_output_full_protocol(c):
 
 def test_truncated_and_corrupted_streams_match_the_reference(c):
     streams = P.damaged_streams(c)
-    P.truncation_sweep(c, streams[:5], step=1)
-    P.truncation_sweep(c, streams[5:], step=41)
-    P.bitflip_sweep(c, streams, trials=150)
+    P.truncation_sweep(c, streams[:5], step=5)
+    P.truncation_sweep(c, streams[5:], step=211)
+    P.bitflip_sweep(c, streams, trials=60)
 
 
 def test_marker_bytes_inside_data(c):

@@ -790,99 +790,125 @@ constexpr u32 RES_LONG = 17;         // matches at least this long are copied by
 constexpr u32 RES_RING = 16384;      // >= 2 x the most a batch can produce (32 x 258 = 8256)
 constexpr int RES_SMEM = (int)(RES_WARPS * RES_RING);
 
+// State of one warp of phase B: it writes a run of segments/blocks one after the other at `base`.
+struct ResState {
+  u8 *base;     // where the run's first byte goes
+  u8 *ring;     // RES_RING bytes of shared memory mirroring the latest output
+  u32 room;     // bytes of the run that fit in the output buffer
+  u32 limit;    // the run may not decode to more than this
+  u32 o;        // bytes written so far (run-relative)
+  u32 bad;      // problem bits: 1 = not a stream this path handles, 2 = output buffer too small
+};
+
+// Appends the output of `nt` tokens to the run.  Warp-uniform; returns false when st.bad was set.
+__device__ __forceinline__ bool res_tokens(ResState &st, const u32 *__restrict__ tok, u32 nt) {
+  constexpr u32 RM = RES_RING - 1;
+  const u32 lane = lane_id();
+  u8 *base = st.base, *ring = st.ring;
+  u32 o = st.o;
+  u32 tnext = lane < nt ? __ldg(tok + lane) : 0;
+  for (u32 b0 = 0; b0 < nt; b0 += 32) {
+    const bool valid = b0 + lane < nt;
+    const u32 t = tnext;
+    tnext = b0 + 32 + lane < nt ? __ldg(tok + b0 + 32 + lane) : 0;  // next batch's tokens are in flight during this one
+    const bool isM = valid && (t >> 31);
+    const u32 len = !valid ? 0 : (isM ? ((t >> 16) & 255) + 3 : 1);
+    const u32 dist = (t & 0x7fff) + 1;
+    u32 inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 v = __shfl_up_sync(ZLES_FULL, inc, d);
+      if (lane >= (u32)d) inc += v;
+    }
+    const u32 pos = o + inc - len;            // run-relative offset of this token's first byte
+    const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
+    if (total > st.limit - o) { st.bad |= 1; break; }
+    if (o + total > st.room) { st.bad |= 2; break; }  // output buffer too small: nothing of this batch is written
+    if (__any_sync(ZLES_FULL, isM && dist > pos)) { st.bad |= 1; break; }  // a reference before the start of the run
+    if (valid && !isM) { base[pos] = (u8)t; ring[pos & RM] = (u8)t; }
+    const u32 src = pos - dist;
+    const bool indep = isM && len < RES_LONG && src + len <= o;  // source entirely before this batch
+    const u32 later = __ballot_sync(ZLES_FULL, isM && !indep);
+    if (indep) {  // all loads first, then the stores: one memory round trip for the whole batch
+      u8 v[RES_LONG - 1];
+#pragma unroll
+      for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) v[q] = base[src + q];
+#pragma unroll
+      for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) { base[pos + q] = v[q]; ring[(pos + q) & RM] = v[q]; }
+    }
+    __syncwarp();
+    u32 m = later;
+    while (m) {  // dependent or long matches: in token order, the whole warp copies one at a time
+      const int j = __ffs((int)m) - 1;
+      m &= m - 1;
+      const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
+      const u32 sj = pj - dj;
+      // the ring holds this warp's latest output up to the end of this batch; everything from sj on is in it
+      // when o + total - sj <= RES_RING (and then nothing of it has been overwritten)
+      const bool in_ring = o + total - sj <= RES_RING;
+      if (dj >= lj) {
+        for (u32 q = lane; q < lj; q += 32) {
+          const u8 b = in_ring ? ring[(sj + q) & RM] : base[sj + q];
+          base[pj + q] = b;
+          ring[(pj + q) & RM] = b;
+        }
+      } else {  // overlapping: the output is periodic with period dj
+        for (u32 q = lane; q < lj; q += 32) {
+          const u8 b = in_ring ? ring[(sj + q % dj) & RM] : base[sj + q % dj];
+          base[pj + q] = b;
+          ring[(pj + q) & RM] = b;
+        }
+      }
+      __syncwarp();
+    }
+    o += total;
+  }
+  st.o = o;
+  return st.bad == 0;
+}
+
+// Appends `len` raw bytes (a stored block's payload) to the run.
+__device__ __forceinline__ bool res_bytes(ResState &st, const u8 *__restrict__ srcp, u32 len) {
+  constexpr u32 RM = RES_RING - 1;
+  if (len > st.limit - st.o) { st.bad |= 1; return false; }
+  if (st.o + len > st.room) { st.bad |= 2; return false; }
+  for (u32 q = lane_id(); q < len; q += 32) {
+    const u8 v = srcp[q];
+    st.base[st.o + q] = v;
+    st.ring[(st.o + q) & RM] = v;
+  }
+  __syncwarp();
+  st.o += len;
+  return true;
+}
+
 __global__ void __launch_bounds__(RES_THREADS)
 k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg,
               const u8 *__restrict__ in, const InfRes *__restrict__ res, u8 *out, u64 cap, u32 *problems) {
   ZLES_SMEM_DECL(smem_raw);
-  u8 *ring = smem_raw + warp_id() * RES_RING;
-  constexpr u32 RM = RES_RING - 1;
-  const u32 lane = lane_id();
   const u32 c = blockIdx.x * RES_WARPS + warp_id();
   if (c * SUBS_PER_CHUNK >= nseg) return;
-  u8 *base = out + (u64)c * CHUNK;
+  ResState st;
+  st.base = out + (u64)c * CHUNK;
+  st.ring = smem_raw + warp_id() * RES_RING;
   const u64 room64 = (u64)c * CHUNK >= cap ? 0 : cap - (u64)c * CHUNK;
-  const u32 room = (u32)umin64(room64, (u64)CHUNK);  // bytes of this chunk that fit in the output
-  u32 o = 0, bad = 0;
-  for (u32 k = 0; k < SUBS_PER_CHUNK && !bad; k++) {
+  st.room = (u32)umin64(room64, (u64)CHUNK);  // bytes of this chunk that fit in the output
+  st.limit = CHUNK;
+  st.o = 0;
+  st.bad = 0;
+  for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
     const u32 e = c * SUBS_PER_CHUNK + k;
     if (e >= nseg) break;
     const u32 sidx = seg_list ? seg_list[e] : e;
     if (res[sidx].flags & SEGF_STORED) {  // stored block: the bytes sit in the input right before the marker / the end
       const InfRes r = res[sidx];
       const u32 len = (u32)r.out_len;
-      const u8 *srcp = in + (r.end_pos - len - (r.status == SEG_SYNC ? 5 : 0));
-      if (o + len > CHUNK) { bad |= 1; break; }
-      if (o + len > room) { bad |= 2; break; }
-      for (u32 q = lane; q < len; q += 32) {
-        const u8 v = srcp[q];
-        base[o + q] = v;
-        ring[(o + q) & RM] = v;
-      }
-      __syncwarp();
-      o += len;
+      if (!res_bytes(st, in + (r.end_pos - len - (r.status == SEG_SYNC ? 5 : 0)), len)) break;
       continue;
     }
-    const u32 nt = umin(ntok[sidx], SUB);
-    const u32 *tok = tokens + (size_t)sidx * SUB;
-    u32 tnext = lane < nt ? __ldg(tok + lane) : 0;
-    for (u32 b0 = 0; b0 < nt; b0 += 32) {
-      const bool valid = b0 + lane < nt;
-      const u32 t = tnext;
-      tnext = b0 + 32 + lane < nt ? __ldg(tok + b0 + 32 + lane) : 0;  // next batch's tokens are in flight during this one
-      const bool isM = valid && (t >> 31);
-      const u32 len = !valid ? 0 : (isM ? ((t >> 16) & 255) + 3 : 1);
-      const u32 dist = (t & 0x7fff) + 1;
-      u32 inc = len;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const u32 v = __shfl_up_sync(ZLES_FULL, inc, d);
-        if (lane >= (u32)d) inc += v;
-      }
-      const u32 pos = o + inc - len;            // chunk-relative offset of this token's first byte
-      const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
-      if (o + total > CHUNK) { bad |= 1; break; }
-      if (o + total > room) { bad |= 2; break; }  // output buffer too small: nothing of this batch is written
-      if (__any_sync(ZLES_FULL, isM && dist > pos)) { bad |= 1; break; }  // a reference before the start of the chunk
-      if (valid && !isM) { base[pos] = (u8)t; ring[pos & RM] = (u8)t; }
-      const u32 src = pos - dist;
-      const bool indep = isM && len < RES_LONG && src + len <= o;  // source entirely before this batch
-      const u32 later = __ballot_sync(ZLES_FULL, isM && !indep);
-      if (indep) {  // all loads first, then the stores: one memory round trip for the whole batch
-        u8 v[RES_LONG - 1];
-#pragma unroll
-        for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) v[q] = base[src + q];
-#pragma unroll
-        for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) { base[pos + q] = v[q]; ring[(pos + q) & RM] = v[q]; }
-      }
-      __syncwarp();
-      u32 m = later;
-      while (m) {  // dependent or long matches: in token order, the whole warp copies one at a time
-        const int j = __ffs((int)m) - 1;
-        m &= m - 1;
-        const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
-        const u32 sj = pj - dj;
-        // the ring holds this warp's latest output up to the end of this batch; everything from sj on is in it
-        // when o + total - sj <= RES_RING (and then nothing of it has been overwritten)
-        const bool in_ring = o + total - sj <= RES_RING;
-        if (dj >= lj) {
-          for (u32 q = lane; q < lj; q += 32) {
-            const u8 b = in_ring ? ring[(sj + q) & RM] : base[sj + q];
-            base[pj + q] = b;
-            ring[(pj + q) & RM] = b;
-          }
-        } else {  // overlapping: the output is periodic with period dj
-          for (u32 q = lane; q < lj; q += 32) {
-            const u8 b = in_ring ? ring[(sj + q % dj) & RM] : base[sj + q % dj];
-            base[pj + q] = b;
-            ring[(pj + q) & RM] = b;
-          }
-        }
-        __syncwarp();
-      }
-      o += total;
-    }
+    if (!res_tokens(st, tokens + (size_t)sidx * SUB, umin(ntok[sidx], SUB))) break;
   }
-  if (bad && lane == 0) atomicOr(problems, bad);
+  if (st.bad && lane_id() == 0) atomicOr(problems, st.bad);
 }
 
 // stream too short to hold a marker: the only candidate is `first`

@@ -1,0 +1,289 @@
+// inflate_foreign.cuh — parallel inflate of zlib streams made by OTHER encoders, first of all by
+// zlib.es itself: its deflate bit-concatenates independent 128 KiB dynamic blocks
+// (/root/reference/src/deflate.ts:20-34, src/lz77.ts:11-22,37) without any marker, so block
+// starts have to be found.
+//
+//   k_hdr_scan      every bit position of the stream is tested for being the start of a dynamic
+//                   block (BTYPE=2): field ranges, a complete code-length code, code lengths that
+//                   decode without overrun into complete literal/length and distance codes with an
+//                   end-of-block code.  What passes is a candidate (false positives are harmless).
+//   k_blk_tokens    one warp per candidate decodes that ONE block into tokens (same decoder as
+//                   phase A of inflate.cuh) and records where it ends, how many bytes it stands
+//                   for and how far before its own start it reaches.
+//   (host)          walks the chain from the first block: the block after one that ends at bit e is
+//                   the candidate at bit e, until a BFINAL block.  Any gap (a stored or fixed block,
+//                   an error) hands the stream to the sequential decoder, which is exact about the
+//                   reference's behaviour on every input.
+//   k_blk_resolve   phase B over runs of blocks: when no block reaches before its own start (zlib.es
+//                   streams) every block is its own run and they are copied in parallel, one warp
+//                   each; otherwise (system zlib: 32 KiB of history across blocks) one warp
+//                   resolves the whole chain in order.
+#pragma once
+#include "inflate.cuh"
+
+namespace zles {
+
+constexpr u32 FB_TOK = 131072 + 32;  // token capacity per block (a zlib.es block of 128 KiB of literals fits)
+constexpr u32 FB_OK = 1;       // a decoded dynamic block
+
+struct FbRes {
+  u64 end_bit;     // bit position just after the block's end-of-block code
+  u32 out_len;     // bytes the block stands for
+  u32 ntok;
+  u32 status;      // FB_OK or 0
+  u32 bfinal;
+  u32 hist_need;   // how many bytes before the block's own start its matches reach
+  u32 pad;
+};
+
+// k <= 24 bits at an arbitrary bit position; bytes outside [0, n) read as 0
+__device__ __forceinline__ u32 fb_bits(const u8 *__restrict__ in, u64 n, u64 bit, u32 k) {
+  const u64 B = bit >> 3;
+  u32 w = 0;
+  if (B + 4 <= n) {
+    w = (u32)in[B] | ((u32)in[B + 1] << 8) | ((u32)in[B + 2] << 16) | ((u32)in[B + 3] << 24);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      if (B + q < n) w |= (u32)in[B + q] << (8 * q);
+  }
+  return (w >> (bit & 7)) & ((1u << k) - 1);
+}
+
+// Is `bit` plausibly the first bit (BFINAL) of a dynamic block?  Thread-level.
+__device__ __forceinline__ bool fb_header_ok(const u8 *__restrict__ in, u64 n, u64 bit) {
+  const u32 h = fb_bits(in, n, bit, 17);
+  if (((h >> 1) & 3) != 2) return false;                      // BTYPE
+  const u32 hlit = (h >> 3) & 31, hdist = (h >> 8) & 31, hclen = ((h >> 13) & 15) + 4;
+  if (hlit > 29 || hdist > 29) return false;                  // more than 286 / 30 codes
+  // code-length code: (hclen) 3-bit lengths in the order of src/const.ts:33-35
+  u32 cl[19];
+#pragma unroll
+  for (int i = 0; i < 19; i++) cl[i] = 0;
+  u32 kraft = 0, used = 0;
+  u64 p = bit + 17;
+  for (u32 i = 0; i < hclen; i += 8) {
+    const u32 v = fb_bits(in, n, p, 24);
+    p += 24;
+#pragma unroll
+    for (u32 q = 0; q < 8; q++) {
+      if (i + q < hclen) {
+        const u32 l = (v >> (3 * q)) & 7;
+        cl[c_cl_order[i + q]] = l;
+        if (l) { kraft += 128u >> l; used++; }
+      }
+    }
+  }
+  p = bit + 17 + 3 * hclen;
+  if (!(kraft == 128 || used == 1)) return false;             // encoders emit complete codes (or a single one)
+  // canonical code-length code (codes by length, then symbol: src/huffman.ts:8-39)
+  u32 cnt[8], first[8], offs[8];
+  u8 sorted[19];
+#pragma unroll
+  for (int l = 0; l < 8; l++) cnt[l] = 0;
+  for (int i = 0; i < 19; i++) cnt[cl[i]]++;
+  {
+    u32 code = 0, o = 0;
+    first[0] = 0; offs[0] = 0;
+    for (int l = 1; l < 8; l++) {
+      first[l] = code;
+      offs[l] = o;
+      o += cnt[l];
+      code = (code + cnt[l]) << 1;
+    }
+    u32 cur[8];
+    for (int l = 0; l < 8; l++) cur[l] = offs[l];
+    for (int i = 0; i < 19; i++)
+      if (cl[i]) sorted[cur[cl[i]]++] = (u8)i;
+  }
+  // the HLIT + HDIST code lengths: only their Kraft sums are kept
+  const u32 nll = hlit + 257, total = nll + hdist + 1;
+  u32 kll = 0, kd = 0, nd = 0, nl = 0, eob = 0, prev = 0;
+  u32 i = 0;
+  while (i < total) {
+    const u32 v = fb_bits(in, n, p, 14);  // <= 7 code bits + <= 7 extra bits
+    u32 code = 0, sym = 99, l = 0;
+    for (l = 1; l < 8; l++) {
+      code = (code << 1) | ((v >> (l - 1)) & 1);
+      const u32 d = code - first[l];
+      if (code >= first[l] && d < cnt[l]) { sym = sorted[offs[l] + d]; break; }
+    }
+    if (sym == 99) return false;
+    u32 rep = 1, val = sym;
+    if (sym == 16) { if (i == 0) return false; rep = 3 + ((v >> l) & 3); val = prev; l += 2; }
+    else if (sym == 17) { rep = 3 + ((v >> l) & 7); val = 0; l += 3; }
+    else if (sym == 18) { rep = 11 + ((v >> l) & 127); val = 0; l += 7; }
+    if (sym <= 15) prev = sym; else if (sym != 16) prev = 0;
+    p += l;
+    if (i + rep > total) return false;                        // a run past the last code
+    if (val) {
+      const u32 w = 32768u >> val;
+      for (u32 q = 0; q < rep; q++) {
+        const u32 j = i + q;
+        if (j < nll) { kll += w; nl++; if (j == 256) eob = 1; } else { kd += w; nd++; }
+      }
+    }
+    i += rep;
+  }
+  if (p > (n << 3)) return false;                             // header runs past the buffer
+  if (!eob) return false;
+  if (!(kll == 32768 || nl == 1)) return false;
+  if (!(kd == 32768 || nd <= 1)) return false;
+  return true;
+}
+
+struct FbStored {   // a stored-block candidate found by the scan
+  u64 bit;          // position of its BFINAL bit
+  u32 len;          // LEN
+  u32 bfinal;
+};
+
+struct FbChainEnt { // one block of the accepted chain, as phase B needs it
+  u64 a;            // dynamic: offset of its tokens in the token buffer; stored: byte offset of its payload in the input
+  u32 b;            // dynamic: number of tokens; stored: LEN
+  u32 stored;
+};
+
+// thread per byte of the stream, 8 bit offsets each; candidates are appended in no particular order:
+// dynamic-block headers to cand[], stored-block headers to st[]; cnt[0] / cnt[1] count them
+__global__ void __launch_bounds__(256) k_hdr_scan(const u8 *__restrict__ in, u64 n, u64 first_bit, u64 *cand, u32 cap, FbStored *st, u32 st_cap,
+                                                  u32 *cnt) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 B = (u64)blockIdx.x * blockDim.x + threadIdx.x; B < n; B += stride) {
+    const u32 w = fb_bits(in, n, B << 3, 24);
+    for (u32 s = 0; s < 8; s++) {
+      const u32 h = w >> s;
+      const u64 bit = (B << 3) + s;
+      if (bit < first_bit) continue;
+      if (((h >> 1) & 3) == 0) {
+        // a stored block (RFC 1951 3.2.4): after the 3 header bits and the pad, LEN and its complement
+        const u64 q = (bit + 3 + 7) >> 3;
+        if (q + 4 <= n) {
+          const u32 len = (u32)in[q] | ((u32)in[q + 1] << 8), nlen = (u32)in[q + 2] | ((u32)in[q + 3] << 8);
+          if ((len ^ nlen) == 0xffffu && q + 4 + len <= n) {
+            const u32 o = atomicAdd(cnt + 1, 1u);
+            if (o < st_cap) { st[o].bit = bit; st[o].len = len; st[o].bfinal = h & 1; }
+          }
+        }
+      } else if (((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29) {  // quick reject, then the full test
+        if (fb_header_ok(in, n, bit)) {
+          const u32 o = atomicAdd(cnt, 1u);
+          if (o < cap) cand[o] = bit;
+        }
+      }
+    }
+  }
+}
+
+// One block, from its BFINAL bit to its end-of-block code, into tokens.
+__device__ __forceinline__ void fb_block_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 bit, u32 *tok, u32 tok_cap, FbRes *res) {
+  const u32 lane = lane_id();
+  InfWarpSmem *S = &T->w;
+  TokReader r;
+  r.init(in, n, bit >> 3);
+  r.skip((u32)(bit & 7));
+  r.refill();
+  u32 o = 0, nt = 0, mytok = 0, turn = lane, left = 32, ok = 0, hist = 0;
+  const u32 bfinal = r.take(1);
+  const u32 btype = r.take(2);
+  u32 status = 0;
+  if (btype == 2 && tk_read_dynamic_header(r, S, status)) {
+    inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
+    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+    for (u32 i = lane; i < (1u << LL_ROOT); i += 32) { const u32 e = S->lut_ll[i]; T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0; }
+    for (u32 i = lane; i < (1u << D_ROOT); i += 32) { const u32 e = S->lut_d[i]; T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0; }
+    __syncwarp();
+    for (;;) {
+      r.refill();
+      u32 e = T->lut_ll[r.lo & ((1u << LL_ROOT) - 1)];
+      if ((e & 15) == 0) {
+        u32 sym, l;
+        if (!inf_slow(r.bits64(), &S->tab_ll, S->sorted_ll, sym, l)) break;
+        e = tk_entry_ll(sym, l);
+        if (e & TK_INV) break;
+      }
+      r.skip(e & 15);
+      if (e & TK_EOB) { ok = 1; break; }
+      if (nt >= tok_cap || o >= 0x7fff0000u) break;
+      u32 t;
+      if (e < TK_LEN) {
+        t = e >> 8;
+        o++;
+      } else {
+        const u32 len = ((e >> 8) & 0xffff) + r.take((e >> 4) & 15);
+        r.refill();
+        u32 d = T->lut_d[r.lo & ((1u << D_ROOT) - 1)];
+        if ((d & 15) == 0) {
+          u32 sym, l;
+          if (!inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) break;
+          d = tk_entry_d(sym, l);
+          if (d & TK_INV) break;
+        }
+        r.skip(d & 15);
+        const u32 dist = (d >> 8) + r.take((d >> 4) & 15);
+        if (dist > o) hist = umax(hist, dist - o);
+        t = 0x80000000u | ((len - 3) << 16) | (dist - 1);
+        o += len;
+      }
+      if (turn == 0) mytok = t;
+      turn = (turn - 1) & 31;
+      nt++;
+      if (--left == 0) { tok[nt - 32 + lane] = mytok; left = 32; }
+    }
+    if (r.past_end()) ok = 0;  // consumed bits the buffer does not have: the sequential decoder knows what the reference does
+  }
+  if (lane < (nt & 31)) tok[(nt & ~31u) + lane] = mytok;
+  if (lane == 0) {
+    res->end_bit = r.bitpos();
+    res->out_len = o;
+    res->ntok = nt;
+    res->status = ok ? FB_OK : 0;
+    res->bfinal = bfinal;
+    res->hist_need = hist;
+    res->pad = 0;
+  }
+}
+
+// candidate j's tokens go to tokens + tok_off[j] (room for tok_cap[j], a multiple of 32)
+__global__ void __launch_bounds__(INF_THREADS)
+k_blk_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 *tokens, const u64 *__restrict__ tok_off,
+             const u32 *__restrict__ tok_cap, FbRes *res, u32 *counter) {
+  ZLES_SMEM_DECL(smem_raw);
+  TokWarpSmem *T = reinterpret_cast<TokWarpSmem *>(smem_raw) + warp_id();
+  for (;;) {
+    u32 j = 0;
+    if (lane_id() == 0) j = atomicAdd(counter, 1u);
+    j = __shfl_sync(ZLES_FULL, j, 0);
+    if (j >= ncand) break;
+    fb_block_tokens(T, in, n, cand[j], tokens + tok_off[j], tok_cap[j], res + j);
+    __syncwarp();
+  }
+}
+
+// run r = chain entries [run_first[r], run_first[r + 1]) written at out + run_off[r]
+__global__ void __launch_bounds__(RES_THREADS)
+k_blk_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ chain, const u32 *__restrict__ run_first,
+              const u64 *__restrict__ run_off, u32 nruns, const u8 *__restrict__ in, u8 *out, u64 cap, u32 *problems) {
+  ZLES_SMEM_DECL(smem_raw);
+  const u32 r = blockIdx.x * RES_WARPS + warp_id();
+  if (r >= nruns) return;
+  ResState st;
+  const u64 off = run_off[r];
+  st.base = out + off;
+  st.ring = smem_raw + warp_id() * RES_RING;
+  st.room = (u32)umin64(off >= cap ? 0 : cap - off, 0xffffffffull);
+  st.limit = 0xffffffffu;
+  st.o = 0;
+  st.bad = 0;
+  for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
+    const FbChainEnt e = chain[i];
+    if (e.stored) {
+      if (!res_bytes(st, in + e.a, e.b)) break;
+    } else if (!res_tokens(st, tokens + e.a, e.b)) {
+      break;
+    }
+  }
+  if (st.bad && lane_id() == 0) atomicOr(problems, st.bad);
+}
+
+}  // namespace zles

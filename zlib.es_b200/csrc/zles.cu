@@ -11,6 +11,7 @@
 // tests only).
 #include "../../include/zles.h"
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <string>
@@ -23,6 +24,7 @@
 #include "corpus_text.h"
 #include "huffman.cuh"
 #include "inflate.cuh"
+#include "inflate_foreign.cuh"
 #include "lz77.cuh"
 #include "pack.cuh"
 
@@ -102,7 +104,7 @@ struct zles_ctx {
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
-  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off;
+  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain;
   // adler / misc
   DevBuf acc;
   // staging for the host forms
@@ -200,6 +202,10 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
   e = zrt_set_smem(k_inf_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_resolve)");
+  e = zrt_set_smem(k_blk_tokens, TOK_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_tokens)");
+  e = zrt_set_smem(k_blk_resolve, RES_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens)");
   e = zrt_set_smem(k_inflate_batch, INF_SMEM);
@@ -237,7 +243,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_set_device(c->device);
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
-                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
   timing_collect(c);
@@ -632,6 +638,127 @@ static int read_ctl(zles_ctx *c, InfCtl *h) {
   return 0;
 }
 
+// Returns 0 (decoded), a positive status, or -1 when the stream is not something this path handles.
+static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
+  if (n < first + 8 || (u64)n >= (1ull << 40)) return -1;
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  const u64 dcap64 = (u64)n / 64 + 1024;   // a dynamic block is rarely shorter than 64 bytes
+  const u64 scap64 = (u64)n / 16 + 4096;   // stored-block candidates: any LEN / ~LEN pair in the data looks like one
+  if (scap64 > 0x7fffffffull) return -1;
+  const u32 dcap = (u32)dcap64, scap = (u32)scap64;
+  if (c->cand.reserve((size_t)dcap * 8) || c->fstored.reserve((size_t)scap * sizeof(FbStored))) return -1;
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  {
+    const u64 want = ((u64)n + 255) / 256;
+    const u32 grid = (u32)umin64(want, (u64)c->sm_count * 32);
+    LAUNCH(c, k_hdr_scan, grid, 256, 0, d_in, (u64)n, first * 8, c->cand.as<u64>(), dcap, c->fstored.as<FbStored>(), scap, &ctl->ncand);
+  }
+  CK(zrt_last_error());
+  InfCtl h;
+  RET(read_ctl(c, &h));
+  const u32 ncand = h.ncand, nst = h.counter;  // k_hdr_scan counts into (ncand, counter)
+  if (ncand > dcap || nst > scap || ncand + nst == 0) return -1;
+  std::vector<u64> cand(ncand);
+  std::vector<FbStored> stv(nst);
+  if (ncand) CK(zrt_d2h(cand.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+  if (nst) CK(zrt_d2h(stv.data(), c->fstored.p, (size_t)nst * sizeof(FbStored), c->stream));
+  CK(zrt_sync(c->stream));
+  std::sort(cand.begin(), cand.end());
+  std::sort(stv.begin(), stv.end(), [](const FbStored &a, const FbStored &b) { return a.bit < b.bit; });
+  // token room per dynamic candidate: a block's tokens are bounded by its compressed span (the next
+  // candidate's start); 4 tokens per compressed byte is far above what encoders produce
+  std::vector<u64> tok_off(ncand + 1, 0);
+  std::vector<u32> tok_cap(ncand, 0);
+  for (u32 i = 0; i < ncand; i++) {
+    const u64 span = ((i + 1 < ncand ? cand[i + 1] : (u64)n * 8) - cand[i] + 7) / 8;
+    u64 capt = span * 4 + 256;
+    if (capt > FB_TOK) capt = FB_TOK;
+    tok_cap[i] = (u32)((capt + 31) & ~31ull);
+    tok_off[i + 1] = tok_off[i] + tok_cap[i];
+  }
+  std::vector<FbRes> res(ncand);
+  if (ncand) {
+    if (c->tokens.reserve((size_t)tok_off[ncand] * 4) || c->fres.reserve((size_t)ncand * sizeof(FbRes)) ||
+        c->seg_off.reserve((size_t)(ncand + 1) * 8) || c->run_first.reserve((size_t)ncand * 4))
+      return -1;
+    CK(zrt_h2d(c->cand.p, cand.data(), (size_t)ncand * 8, c->stream));
+    CK(zrt_h2d(c->seg_off.p, tok_off.data(), (size_t)ncand * 8, c->stream));
+    CK(zrt_h2d(c->run_first.p, tok_cap.data(), (size_t)ncand * 4, c->stream));
+    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+    LAUNCH(c, k_blk_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
+           c->tokens.as<u32>(), (const u64 *)c->seg_off.as<u64>(), (const u32 *)c->run_first.as<u32>(), c->fres.as<FbRes>(), &ctl->counter);
+    CK(zrt_last_error());
+    CK(zrt_d2h(res.data(), c->fres.p, (size_t)ncand * sizeof(FbRes), c->stream));
+    CK(zrt_sync(c->stream));
+  }
+  // chain walk: the block after one that ends at bit e starts at bit e
+  std::vector<FbChainEnt> chain;
+  std::vector<u64> blk_off;  // output offset of every chain entry
+  u64 pos = first * 8, total = 0;
+  bool self_contained = true;
+  for (;;) {
+    if (chain.size() > (size_t)ncand + nst) return -1;
+    const auto it = std::lower_bound(cand.begin(), cand.end(), pos);
+    u32 bfinal;
+    u64 next;
+    if (it != cand.end() && *it == pos) {
+      const FbRes &r = res[(size_t)(it - cand.begin())];
+      if (r.status != FB_OK) return -1;
+      if (r.hist_need) {
+        if (r.hist_need > total) return -1;  // reaches before the start of the output: the reference yields zeros, sequential path
+        self_contained = false;
+      }
+      chain.push_back(FbChainEnt{tok_off[(size_t)(it - cand.begin())], r.ntok, 0});
+      blk_off.push_back(total);
+      total += r.out_len;
+      bfinal = r.bfinal;
+      next = r.end_bit;
+    } else {
+      const auto is = std::lower_bound(stv.begin(), stv.end(), pos, [](const FbStored &a, u64 p) { return a.bit < p; });
+      if (is == stv.end() || is->bit != pos) return -1;  // a fixed block, or not a block at all: sequential path
+      const u64 q = (pos + 3 + 7) >> 3;
+      chain.push_back(FbChainEnt{q + 4, is->len, 1});
+      blk_off.push_back(total);
+      total += is->len;
+      bfinal = is->bfinal;
+      next = (q + 4 + is->len) * 8;
+    }
+    if (total >= 0xfff00000ull) return -1;  // run-relative offsets are 32-bit
+    if (bfinal) break;
+    if (next <= pos) return -1;
+    pos = next;
+  }
+  *out_len = (size_t)total;
+  if (total > cap) return ZLES_E_OUTPUT_FULL;
+  // runs: every block on its own when none needs history, else the whole chain on one warp
+  const u32 nblk = (u32)chain.size();
+  std::vector<u32> run_first;
+  std::vector<u64> run_off;
+  if (self_contained) {
+    for (u32 i = 0; i < nblk; i++) { run_first.push_back(i); run_off.push_back(blk_off[i]); }
+  } else {
+    run_first.push_back(0);
+    run_off.push_back(0);
+  }
+  const u32 nruns = (u32)run_first.size();
+  run_first.push_back(nblk);
+  RET(c->fchain.reserve((size_t)nblk * sizeof(FbChainEnt)));
+  RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
+  RET(c->seg_off.reserve((size_t)nruns * 8));
+  CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbChainEnt), c->stream));
+  CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
+  CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)nruns * 8, c->stream));
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  CK(zrt_sync(c->stream));  // the vectors are host heap memory
+  LAUNCH(c, k_blk_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
+         (const FbChainEnt *)c->fchain.as<FbChainEnt>(), (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns, d_in,
+         d_out, (u64)cap, &ctl->ok_res);
+  CK(zrt_last_error());
+  RET(read_ctl(c, &h));
+  if (h.ok_res != 0) return -1;
+  return 0;
+}
+
 // Steps 2.. of inflate.  On success *out_len = decoded size.  ZLES_E_OUTPUT_FULL: *out_len = size needed.
 static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 ncand_all, u32 cand_cap, u8 *d_out, size_t cap,
                           size_t *out_len, bool has_final = true) {
@@ -710,9 +837,18 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     }
   }
 
-  // 4. sequential decode of the whole stream on one warp: exactly the reference's order of
-  //    events (src/inflate.ts:22-37), used for foreign streams and for error reporting.
   if (!has_final) return ZLES_E_CORRUPTED;  // a shard of one of our streams must have decoded above
+
+  // 3b. a stream from another encoder (zlib.es itself, system zlib): find the dynamic blocks, decode them in
+  //     parallel, chain them up.  Only a complete, consistent chain that ends in a BFINAL block is accepted;
+  //     everything else is left to the sequential decoder below.
+  {
+    int rc = inflate_foreign(c, d_in, n, first, d_out, cap, out_len);
+    if (rc >= 0) return rc;  // decoded (0) or ZLES_E_OUTPUT_FULL / CUDA error; -1 = not handled
+  }
+
+  // 4. sequential decode of the whole stream on one warp: exactly the reference's order of
+  //    events (src/inflate.ts:22-37), used for everything else and for error reporting.
   {
     const u32 one = 1;
     const u64 zero = 0;

@@ -14,10 +14,15 @@
 //                   the candidate at bit e, until a BFINAL block.  Any gap (a stored or fixed block,
 //                   an error) hands the stream to the sequential decoder, which is exact about the
 //                   reference's behaviour on every input.
-//   k_blk_resolve   phase B over runs of blocks: when no block reaches before its own start (zlib.es
-//                   streams) every block is its own run and they are copied in parallel, one warp
-//                   each; otherwise (system zlib: 32 KiB of history across blocks) one warp
-//                   resolves the whole chain in order.
+//   k_blk_resolve   phase B when no block reaches before its own start (zlib.es streams): every
+//                   block is copied on its own warp.
+//   k_run_resolve / k_win_propagate / k_sym_finalize
+//                   phase B when blocks use the 32 KiB before them (system zlib): the chain is cut into
+//                   runs of >= 256 KiB; every run is resolved in parallel into 16-bit symbols, a byte
+//                   that comes from the unknown 32 KiB window before the run staying symbolic
+//                   (0x8000 | window offset, copied around like any other value); then the windows are
+//                   made concrete run after run (32 KiB each, cheap), and a last parallel pass
+//                   substitutes them (the two-pass scheme of pugz / rapidgzip).
 #pragma once
 #include "inflate.cuh"
 
@@ -284,6 +289,134 @@ k_blk_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ cha
     }
   }
   if (st.bad && lane_id() == 0) atomicOr(problems, st.bad);
+}
+
+// ---- chains with history across blocks: symbolic 32 KiB windows -------------------------------------
+constexpr u32 SYM_WIN = 32768;          // deflate's window
+constexpr u32 SYM_REF = 0x8000;         // symbol >= SYM_REF: byte (sym & 0x7fff) of the window before the run
+constexpr u32 SYM_RING = 16384;         // u16 entries mirrored in shared memory per warp (>= 32 x 258)
+constexpr int SYM_SMEM = (int)(RES_WARPS * SYM_RING * 2);
+constexpr u32 SYM_RUN = 262144;         // target bytes per run
+
+struct SymState {
+  u16 *base;    // the run's symbols
+  u16 *ring;
+  u32 o;
+};
+
+// Same as res_tokens, on 16-bit symbols; a source position before the run (negative) yields a window reference.
+__device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__ tok, u32 nt) {
+  constexpr u32 RM = SYM_RING - 1;
+  const u32 lane = lane_id();
+  u16 *base = st.base, *ring = st.ring;
+  u32 o = st.o;
+  u32 tnext = lane < nt ? __ldg(tok + lane) : 0;
+  for (u32 b0 = 0; b0 < nt; b0 += 32) {
+    const bool valid = b0 + lane < nt;
+    const u32 t = tnext;
+    tnext = b0 + 32 + lane < nt ? __ldg(tok + b0 + 32 + lane) : 0;
+    const bool isM = valid && (t >> 31);
+    const u32 len = !valid ? 0 : (isM ? ((t >> 16) & 255) + 3 : 1);
+    const u32 dist = (t & 0x7fff) + 1;
+    u32 inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 v = __shfl_up_sync(ZLES_FULL, inc, d);
+      if (lane >= (u32)d) inc += v;
+    }
+    const u32 pos = o + inc - len;
+    const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
+    if (valid && !isM) { base[pos] = (u16)t; ring[pos & RM] = (u16)t; }
+    const bool indep = isM && len < RES_LONG && dist <= pos && pos - dist + len <= o;  // source inside the run, before this batch
+    const u32 later = __ballot_sync(ZLES_FULL, isM && !indep);
+    if (indep) {
+      const u32 src = pos - dist;
+      u16 v[RES_LONG - 1];
+#pragma unroll
+      for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) v[q] = base[src + q];
+#pragma unroll
+      for (u32 q = 0; q < RES_LONG - 1; q++) if (q < len) { base[pos + q] = v[q]; ring[(pos + q) & RM] = v[q]; }
+    }
+    __syncwarp();
+    u32 m = later;
+    while (m) {
+      const int j = __ffs((int)m) - 1;
+      m &= m - 1;
+      const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
+      const int sj = (int)pj - (int)dj;  // may be negative: before the run
+      const bool in_ring = sj >= 0 && o + total - (u32)sj <= SYM_RING;
+      for (u32 q = lane; q < lj; q += 32) {
+        const int s = sj + (int)(dj >= lj ? q : q % dj);
+        u16 b;
+        if (s < 0) b = (u16)(SYM_REF | (u32)((int)SYM_WIN + s));  // dist <= 32768, so SYM_WIN + s >= 0
+        else b = in_ring ? ring[(u32)s & RM] : base[s];
+        base[pj + q] = b;
+        ring[(pj + q) & RM] = b;
+      }
+      __syncwarp();
+    }
+    o += total;
+  }
+  st.o = o;
+}
+
+__device__ __forceinline__ void sym_bytes(SymState &st, const u8 *__restrict__ srcp, u32 len) {
+  constexpr u32 RM = SYM_RING - 1;
+  for (u32 q = lane_id(); q < len; q += 32) {
+    const u16 v = srcp[q];
+    st.base[st.o + q] = v;
+    st.ring[(st.o + q) & RM] = v;
+  }
+  __syncwarp();
+  st.o += len;
+}
+
+// pass 1: run r = chain entries [run_first[r], run_first[r + 1]), symbols at sym + run_off[r]
+__global__ void __launch_bounds__(RES_THREADS)
+k_run_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ chain, const u32 *__restrict__ run_first,
+              const u64 *__restrict__ run_off, u32 nruns, const u8 *__restrict__ in, u16 *sym) {
+  ZLES_SMEM_DECL(smem_raw);
+  const u32 r = blockIdx.x * RES_WARPS + warp_id();
+  if (r >= nruns) return;
+  SymState st;
+  st.base = sym + run_off[r];
+  st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SYM_RING;
+  st.o = 0;
+  for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
+    const FbChainEnt e = chain[i];
+    if (e.stored) sym_bytes(st, in + e.a, e.b);
+    else sym_tokens(st, tokens + e.a, e.b);
+  }
+}
+
+// pass 2, one CTA: win[r] = the last 32 KiB of run r, concrete; win[-1] (before the stream) is all zeros, which is
+// what the reference's inflate reads there (/root/reference/src/inflate.ts:287-290).  Runs are >= 32 KiB except the last.
+__global__ void __launch_bounds__(1024) k_win_propagate(const u16 *__restrict__ sym, const u64 *__restrict__ run_off, u32 nruns, u8 *win) {
+  for (u32 r = 0; r + 1 < nruns; r++) {
+    const u64 end = run_off[r + 1];
+    const u8 *prev = r ? win + (size_t)(r - 1) * SYM_WIN : nullptr;
+    for (u32 k = threadIdx.x; k < SYM_WIN; k += 1024) {
+      const u16 v = sym[end - SYM_WIN + k];
+      u8 b;
+      if (v < SYM_REF) b = (u8)v;
+      else b = prev ? prev[v & 0x7fff] : (u8)0;
+      win[(size_t)r * SYM_WIN + k] = b;
+    }
+    __syncthreads();
+  }
+}
+
+// pass 3: symbols -> bytes
+__global__ void __launch_bounds__(256) k_sym_finalize(const u16 *__restrict__ sym, const u64 *__restrict__ run_off, u32 nruns,
+                                                      const u8 *__restrict__ win, u8 *out) {
+  for (u32 r = blockIdx.y; r < nruns; r += gridDim.y) {
+    const u64 a = run_off[r], b = run_off[r + 1];
+    const u8 *prev = r ? win + (size_t)(r - 1) * SYM_WIN : nullptr;
+    for (u64 i = a + (u64)blockIdx.x * blockDim.x + threadIdx.x; i < b; i += (u64)gridDim.x * blockDim.x) {
+      const u16 v = sym[i];
+      out[i] = v < SYM_REF ? (u8)v : (prev ? prev[v & 0x7fff] : (u8)0);
+    }
+  }
 }
 
 }  // namespace zles

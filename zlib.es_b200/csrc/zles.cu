@@ -104,7 +104,7 @@ struct zles_ctx {
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
-  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain;
+  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain, fsym, fwin;
   // adler / misc
   DevBuf acc;
   // staging for the host forms
@@ -204,6 +204,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_resolve)");
   e = zrt_set_smem(k_blk_tokens, TOK_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_tokens)");
+  e = zrt_set_smem(k_run_resolve, SYM_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_run_resolve)");
   e = zrt_set_smem(k_blk_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
@@ -243,7 +245,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_set_device(c->device);
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
-                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
   timing_collect(c);
@@ -704,10 +706,7 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
     if (it != cand.end() && *it == pos) {
       const FbRes &r = res[(size_t)(it - cand.begin())];
       if (r.status != FB_OK) return -1;
-      if (r.hist_need) {
-        if (r.hist_need > total) return -1;  // reaches before the start of the output: the reference yields zeros, sequential path
-        self_contained = false;
-      }
+      if (r.hist_need) self_contained = false;  // (before the start of the output the reference reads zeros: so does the window scheme)
       chain.push_back(FbChainEnt{tok_off[(size_t)(it - cand.begin())], r.ntok, 0});
       blk_off.push_back(total);
       total += r.out_len;
@@ -730,32 +729,61 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   }
   *out_len = (size_t)total;
   if (total > cap) return ZLES_E_OUTPUT_FULL;
-  // runs: every block on its own when none needs history, else the whole chain on one warp
   const u32 nblk = (u32)chain.size();
   std::vector<u32> run_first;
   std::vector<u64> run_off;
   if (self_contained) {
+    // no block reaches before its own start (zlib.es's own streams): every block is copied on its own warp
     for (u32 i = 0; i < nblk; i++) { run_first.push_back(i); run_off.push_back(blk_off[i]); }
-  } else {
-    run_first.push_back(0);
-    run_off.push_back(0);
+    const u32 nruns = nblk;
+    run_first.push_back(nblk);
+    RET(c->fchain.reserve((size_t)nblk * sizeof(FbChainEnt)));
+    RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
+    RET(c->seg_off.reserve((size_t)nruns * 8));
+    CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbChainEnt), c->stream));
+    CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
+    CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)nruns * 8, c->stream));
+    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+    CK(zrt_sync(c->stream));  // the vectors are host heap memory
+    LAUNCH(c, k_blk_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
+           (const FbChainEnt *)c->fchain.as<FbChainEnt>(), (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns, d_in,
+           d_out, (u64)cap, &ctl->ok_res);
+    CK(zrt_last_error());
+    RET(read_ctl(c, &h));
+    if (h.ok_res != 0) return -1;
+    return 0;
+  }
+  // blocks use the 32 KiB before them (system zlib): runs of >= SYM_RUN bytes resolved in parallel into 16-bit
+  // symbols with symbolic windows, windows made concrete run after run, then substituted (inflate_foreign.cuh)
+  {
+    u64 acc = 0;
+    for (u32 i = 0; i < nblk; i++) {
+      if (i == 0 || acc >= SYM_RUN) { run_first.push_back(i); run_off.push_back(blk_off[i]); acc = 0; }
+      acc += (i + 1 < nblk ? blk_off[i + 1] : total) - blk_off[i];
+    }
   }
   const u32 nruns = (u32)run_first.size();
   run_first.push_back(nblk);
+  run_off.push_back(total);
+  if (c->fsym.reserve((size_t)total * 2 + 64) || c->fwin.reserve((size_t)nruns * SYM_WIN)) return -1;
   RET(c->fchain.reserve((size_t)nblk * sizeof(FbChainEnt)));
   RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
-  RET(c->seg_off.reserve((size_t)nruns * 8));
+  RET(c->seg_off.reserve((size_t)(nruns + 1) * 8));
   CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbChainEnt), c->stream));
   CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
-  CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)nruns * 8, c->stream));
-  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)(nruns + 1) * 8, c->stream));
   CK(zrt_sync(c->stream));  // the vectors are host heap memory
-  LAUNCH(c, k_blk_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
+  LAUNCH(c, k_run_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SYM_SMEM, (const u32 *)c->tokens.as<u32>(),
          (const FbChainEnt *)c->fchain.as<FbChainEnt>(), (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns, d_in,
-         d_out, (u64)cap, &ctl->ok_res);
+         c->fsym.as<u16>());
+  LAUNCH(c, k_win_propagate, 1, 1024, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns, c->fwin.as<u8>());
+  {
+    dim3 grid(16, nruns < 4096 ? nruns : 4096);
+    LAUNCH(c, k_sym_finalize, grid, 256, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns,
+           (const u8 *)c->fwin.as<u8>(), d_out);
+  }
   CK(zrt_last_error());
-  RET(read_ctl(c, &h));
-  if (h.ok_res != 0) return -1;
+  CK(zrt_sync(c->stream));
   return 0;
 }
 

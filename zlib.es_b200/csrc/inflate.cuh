@@ -1,23 +1,22 @@
-// inflate.cuh — kernels K6/K7: warp-per-segment table-driven Huffman decode with
-// LZ77 back-reference copy, and the sync-marker scan that finds the independent
-// segments our own deflate emits.
+// inflate.cuh — kernels K6/K7: Huffman decode and LZ77 back-reference copy.
 //
 // Replaces /root/reference/src/inflate.ts:16-292 (bit-serial canonical decode, one
 // `read()` per code bit, byte-serial copy), src/huffman.ts:8-53 (decode tables),
 // src/utils/BitReadStream.ts and src/utils/Uint8WriteStream.ts.
 //
-// A "segment" is a run of deflate blocks that starts on a byte boundary and ends
-// with the final block or with an empty stored block (the 00 00 FF FF sync
-// marker).  Our encoder ends every independent 128 KiB chunk with that marker,
-// so the segments of one of our streams decode in parallel, one warp each;
-// streams from other encoders (zlib.es itself, system zlib, the reference's
-// test/data/compressed.bin) are a single segment and decode on one warp.
-// A segment is accepted only through k_inf_check / the chain walk in capi: it
-// must start where the previous one ended, decode without error, and never
-// reach back before its own start.
+// Three tiers, tried in this order by zles.cu:
+//  1. OUR streams (this file, "fast path"): every 32 KiB block ends with an empty stored block
+//     (the 00 00 FF FF sync marker), so block starts are found by a byte scan (k_mark_*), every
+//     block ("segment") is Huffman-decoded into tokens on its own warp (k_inf_tokens), the result
+//     is verified (k_inf_check) and the copies are resolved one warp per 128 KiB chunk
+//     (k_inf_resolve).
+//  2. streams of other encoders (inflate_foreign.cuh): block headers are searched at every bit.
+//  3. everything else, and every error: k_inflate, one warp, sequential, exactly the reference's
+//     order of events including BitReadStream's end-of-buffer behaviour.  k_inflate_batch runs
+//     tier 3 on a batch of independent streams, one warp per stream.
 //
-// Roofline: HBM-bound in principle (algorithmic bytes = C read + U written),
-// in practice bound by the serial decode chain of each warp; see DESIGN.md.
+// Roofline: HBM-bound in principle (algorithmic bytes = C read + U written), in practice bound
+// by the serial decode chain of each warp; see DESIGN.md.
 #pragma once
 #include "zles_dev.h"
 
@@ -75,7 +74,6 @@ struct InfReader {
   u32 win, win_next;
   u64 bb;
   u32 bc;
-  u32 overrun;
 
   __device__ __forceinline__ u32 load_word(u64 wi) const {
     // word wi covers stream bytes [4*wi - skew, 4*wi - skew + 4); bytes outside [0, n) read as 0
@@ -97,7 +95,6 @@ struct InfReader {
       win_next = load_word(win_base + 32 + lane_id());
     }
     u32 w = __shfl_sync(ZLES_FULL, win, (int)(widx & 31));
-    if (((widx << 2) > n + skew + 8)) overrun = 1;
     widx++;
     return w;
   }
@@ -105,7 +102,6 @@ struct InfReader {
     in = in_; n = n_;
     skew = (u32)((uintptr_t)in_ & 3);
     words = reinterpret_cast<const u32 *>(in_ - skew);
-    overrun = 0;
     u64 a = byte_pos + skew;
     widx = a >> 2;
     win_base = widx & ~(u64)31;
@@ -194,15 +190,6 @@ __device__ __forceinline__ bool inf_slow(u64 bb, const InfTab *t, const u16 *sor
     }
   }
   return false;
-}
-
-__device__ __forceinline__ bool inf_decode(InfReader &r, const u16 *lut, int root, const InfTab *t, const u16 *sorted, u32 &sym) {
-  u32 e = lut[r.peek((u32)root)];
-  u32 l = e & 15;
-  sym = e >> 4;
-  if (l == 0 && !inf_slow(r.bb, t, sorted, sym, l)) return false;
-  r.skip(l);
-  return true;
 }
 
 // One Huffman-coded symbol in the sequential decoder, with the reference's end-of-buffer bookkeeping.

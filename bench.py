@@ -131,7 +131,7 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -336,6 +336,11 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_lz", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo)},
+            "roofline_inflate": {"bound": "hbm", "kernels": "k_inf_tokens + k_inf_resolve",
+                                 "achieved": round(algo / ((tok_ms + res_ms) / max(1, tok_n) * 1e-3) / 1e9, 2) if tok_ms + res_ms > 0 else 0.0,
+                                 "peak": peak, "unit": "GB/s",
+                                 "frac": round(algo / ((tok_ms + res_ms) / max(1, tok_n) * 1e-3) / 1e9 / peak, 5) if tok_ms + res_ms > 0 else 0.0,
+                                 "algorithmic_bytes_per_launch": int(algo)},
             "clocks": clocks,
         }
         if cpu:

@@ -143,6 +143,12 @@ def test_marker_bytes_inside_data(c):
     payload = (b"\x00\x00\xff\xff" * 50 + b"abc") * 2000
     P.inflate_matches_oracle(c, zlib.compress(payload, 0))  # stored blocks: the pattern appears verbatim
     P.roundtrip(c, payload, check_size=False)
+    # a marker pattern followed by something that looks like a stored block and then by garbage: that candidate
+    # fails half-way (regression: the optimistic copy pass used its unset end position)
+    bait = b"\x00\x00\xff\xff" + b"\x00\x05\x00\xfa\xffabcde" + b"\x07" + b"\x00\x00\xff\xff" + b"\x00\xff\x7f\x00\x80" + b"\x06"
+    payload = (T.gen("G5", 3000) + bait) * 60
+    P.inflate_matches_oracle(c, zlib.compress(payload, 0))
+    P.inflate_matches_oracle(c, zlib.compress(payload, 1))
     # our own stream with a marker pattern spliced between two blocks' worth of compressed bytes cannot
     # be built by hand; instead check that removing candidates is exercised: a stream = ours + foreign tail
     z = c.deflate(T.gen("G5", 100000))

@@ -887,10 +887,15 @@ k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, cons
     const u32 e = c * SUBS_PER_CHUNK + k;
     if (e >= nseg) break;
     const u32 sidx = seg_list ? seg_list[e] : e;
-    if (res[sidx].flags & SEGF_STORED) {  // stored block: the bytes sit in the input right before the marker / the end
-      const InfRes r = res[sidx];
+    const InfRes r = res[sidx];
+    // This kernel also runs optimistically on candidates that k_inf_check will turn down: a segment that did not
+    // decode cleanly has no usable end position (a stored block followed by garbage leaves end_pos = 0).
+    if (r.status != SEG_SYNC && r.status != SEG_FINAL) { st.bad |= 1; break; }
+    if (r.flags & SEGF_STORED) {  // stored block: the bytes sit in the input right before the marker / the end
       const u32 len = (u32)r.out_len;
-      if (!res_bytes(st, in + (r.end_pos - len - (r.status == SEG_SYNC ? 5 : 0)), len)) break;
+      const u64 back = (u64)len + (r.status == SEG_SYNC ? 5 : 0);
+      if (r.end_pos < back) { st.bad |= 1; break; }
+      if (!res_bytes(st, in + (r.end_pos - back), len)) break;
       continue;
     }
     if (!res_tokens(st, tokens + (size_t)sidx * SUB, umin(ntok[sidx], SUB))) break;

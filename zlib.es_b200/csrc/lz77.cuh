@@ -77,6 +77,24 @@ struct LzParams {
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
 };
 
+// Per-stage cycle counters (tools/lz_stages.py builds with -DZLES_STAGE_CLOCKS; off in the product build):
+// thread 0 adds the cycles since the previous mark to g_lz_clk[i].  The previous mark lives in the last
+// 8 bytes of the misc area of shared memory.
+#ifdef ZLES_STAGE_CLOCKS
+__device__ unsigned long long g_lz_clk[16];
+#define LZ_CLK(scr, i)                                                                   \
+  do {                                                                                   \
+    if (threadIdx.x == 0) {                                                              \
+      long long *cp_ = reinterpret_cast<long long *>((scr) + 510);                       \
+      const long long t_ = clock64();                                                    \
+      if ((i) >= 0) atomicAdd(&g_lz_clk[(i) < 0 ? 0 : (i)], (unsigned long long)(t_ - *cp_)); \
+      *cp_ = t_;                                                                         \
+    }                                                                                    \
+  } while (0)
+#else
+#define LZ_CLK(scr, i) do { } while (0)
+#endif
+
 // token encoding shared with pack.cuh: literal = byte value; match = bit31 | (len-3)<<16 | (dist-1)
 __device__ __forceinline__ u32 tok_match(u32 len, u32 dist) { return 0x80000000u | ((len - 3) << 16) | (dist - 1); }
 
@@ -101,9 +119,9 @@ __device__ __forceinline__ u32 lz_match_len(const u8 *d, u32 c, u32 p, u32 maxle
 }
 
 // ---- S2: stable LSD radix sort of the positions by hash16(key3), 2 passes of 8 bits ----------
-// Warp w owns items [w*per, (w+1)*per) of each pass; per-warp digit histograms (u16, in `wh`)
+// Every warp owns a contiguous range of items in each pass; per-warp digit histograms (u16, in `wh`)
 // make the scatter stable.  Counting uses fire-and-forget shared-memory atomics on packed u16
-// pairs (no dependency chain); the scatter ranks equal digits inside a warp with __match_any_sync.
+// pairs (no dependency chain); the scatter ranks equal digits inside a warp (lz_peers).
 // Pass 1 reads the data, pass 2 reads pass 1's output Y (u32 = hash << 16 | position, in global
 // memory / L2, coalesced, four loads in flight per lane).
 
@@ -133,10 +151,30 @@ __device__ __forceinline__ void lz_count(u16 *wh, u32 w, u32 digit) {
   atomicAdd(reinterpret_cast<u32 *>(wh) + ((w * 256 + digit) >> 1), 1u << ((digit & 1) * 16));
 }
 
+// lanes of the warp that hold the same 8-bit digit (valid lanes only).  BALLOT: eight ballots, a fixed ~40
+// instructions; otherwise __match_any_sync, whose cost grows with the number of distinct digits in the warp
+// (measured: ~7 cycles of the scheduler per distinct value).  Pass 1 sees ~28 distinct digits per warp on text
+// (consecutive positions), pass 2 only a few (its input is grouped by the first digit).
+template <bool BALLOT>
+__device__ __forceinline__ u32 lz_peers(u32 digit, bool valid) {
+  if (BALLOT) {
+    u32 peers = __ballot_sync(ZLES_FULL, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const bool bit = (digit >> b) & 1;
+      const u32 bal = __ballot_sync(ZLES_FULL, bit);
+      peers &= bit ? bal : ~bal;
+    }
+    return peers;
+  }
+  return __match_any_sync(ZLES_FULL, valid ? digit : 256 + lane_id());
+}
+
 // rank of this lane among the lanes of the warp with the same digit, and the slot it scatters to
+template <bool BALLOT>
 __device__ __forceinline__ u32 lz_slot(u16 *wh, u32 w, u32 digit, bool valid) {
   const u32 lane = lane_id();
-  const u32 m = __match_any_sync(ZLES_FULL, digit);
+  const u32 m = lz_peers<BALLOT>(digit, valid);
   const u32 basepos = valid ? wh[w * 256 + digit] : 0;
   __syncwarp();
   if (valid && lane == (u32)(__ffs((int)m) - 1)) wh[w * 256 + digit] = (u16)(basepos + __popc(m));
@@ -144,38 +182,39 @@ __device__ __forceinline__ u32 lz_slot(u16 *wh, u32 w, u32 digit, bool valid) {
   return basepos + __popc(m & lanemask_lt());
 }
 
-__device__ __forceinline__ void lz_sort(const u8 *data, u32 *Y, u16 *X, u16 *wh, u32 *scratch, u32 N, u32 per) {
+// Warp w owns items [w << lper, (w + 1) << lper) of each pass.  `wh` = per-warp histograms of pass 1,
+// `wh + LZ_WARPS * 256` = those of pass 2, which are counted while pass 1 scatters (the item that lands in
+// slot s belongs to warp s >> lper in pass 2), so pass 2 reads Y only once.
+__device__ __forceinline__ void lz_sort(const u8 *data, u32 *Y, u16 *X, u16 *wh, u32 *scratch, u32 N, u32 lper) {
   const u32 lane = lane_id(), w = warp_id();
-  const u32 wbeg = umin(w * per, N), wend = umin(wbeg + per, N);
+  const u32 wbeg = umin(w << lper, N), wend = umin(wbeg + (1u << lper), N);
+  u16 *wh2 = wh + LZ_WARPS * 256;
   u32 *wh32 = reinterpret_cast<u32 *>(wh);
   // ---- pass 1: low digit ----
-  for (u32 i = threadIdx.x; i < LZ_WARPS * 256 / 2; i += LZ_THREADS) wh32[i] = 0;
+  for (u32 i = threadIdx.x; i < LZ_WARPS * 256; i += LZ_THREADS) wh32[i] = 0;  // both histograms
   __syncthreads();
   for (u32 idx = wbeg + lane; idx < wend; idx += 32) lz_count(wh, w, lz_hash16(lz_key3_fast(data, idx)) & 255);
   __syncthreads();
+  LZ_CLK(scratch, 2);
   lz_hist_scan(wh, scratch);
   __syncthreads();
+  LZ_CLK(scratch, 3);
   for (u32 base = wbeg; base < wend; base += 32) {
     const u32 idx = base + lane;
     const bool valid = idx < wend;
     const u32 h = valid ? lz_hash16(lz_key3_fast(data, idx)) : 0;
-    const u32 slot = lz_slot(wh, w, valid ? (h & 255) : 256 + lane, valid);
-    if (valid) Y[slot] = (h << 16) | idx;
+    const u32 slot = lz_slot<true>(wh, w, h & 255, valid);
+    if (valid) {
+      Y[slot] = (h << 16) | idx;
+      lz_count(wh2, slot >> lper, h >> 8);
+    }
   }
   __syncthreads();  // also orders the global writes of Y before the reads below (same CTA)
+  LZ_CLK(scratch, 4);
   // ---- pass 2: high digit ----
-  for (u32 i = threadIdx.x; i < LZ_WARPS * 256 / 2; i += LZ_THREADS) wh32[i] = 0;
+  lz_hist_scan(wh2, scratch);
   __syncthreads();
-  for (u32 base = wbeg; base < wend; base += 128) {
-    u32 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) { const u32 idx = base + 32 * k + lane; v[k] = idx < wend ? __ldcg(Y + idx) : 0; }
-#pragma unroll
-    for (int k = 0; k < 4; k++) if (base + 32 * k + lane < wend) lz_count(wh, w, v[k] >> 24);
-  }
-  __syncthreads();
-  lz_hist_scan(wh, scratch);
-  __syncthreads();
+  LZ_CLK(scratch, 6);
   for (u32 base = wbeg; base < wend; base += 128) {
     u32 v[4];
 #pragma unroll
@@ -184,11 +223,12 @@ __device__ __forceinline__ void lz_sort(const u8 *data, u32 *Y, u16 *X, u16 *wh,
     for (int k = 0; k < 4; k++) {
       if (base + 32 * k >= wend) break;  // warp-uniform
       const bool valid = base + 32 * k + lane < wend;
-      const u32 slot = lz_slot(wh, w, valid ? (v[k] >> 24) : 256 + lane, valid);
+      const u32 slot = lz_slot<false>(wh2, w, v[k] >> 24, valid);
       if (valid) X[slot] = (u16)v[k];
     }
   }
   __syncthreads();
+  LZ_CLK(scratch, 7);
 }
 
 // bytes d[p .. p+6] as (lo = bytes 0-3, hi = bytes 4-6); unaligned shared-memory read
@@ -252,10 +292,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     }
     const u32 L = hist_len + own_len;
 
+    LZ_CLK(scratch, -1);
     // S0: stage window + block, zero the pad so word reads past the end are defined
     stage_g2s(data, P.in + own_off - hist_len, L, mbar, parity);
     for (u32 i = tid; i < LZ_PAD; i += LZ_THREADS) data[L + i] = 0;
     __syncthreads();
+    LZ_CLK(scratch, 0);
 
     // S1: Adler-32 partial sums of the block's own bytes (K8 fused into the load)
     {
@@ -285,12 +327,14 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         P.adler_part[2 * (size_t)b] = ta;
         P.adler_part[2 * (size_t)b + 1] = tb;
       }
+      LZ_CLK(scratch, 1);
     }
 
     // S2: stable radix sort of positions by hash16(key3)
     const u32 N = L >= 3 ? L - 2 : 0;
-    const u32 per = ((N + LZ_THREADS - 1) / LZ_THREADS) * 32;
-    lz_sort(data, Y, X, wh, scratch, N, per);
+    u32 lper = 5;  // items per warp and pass: the power of two >= ceil(N / warps), at least one batch
+    while (((u32)LZ_WARPS << lper) < N) lper++;
+    lz_sort(data, Y, X, wh, scratch, N, lper);
 
     // S3: per-position match search.  Warp w owns sorted entries [kbeg, kend).
     {
@@ -403,12 +447,14 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       if (tid < 2 && own_len > tid) R[own_len - 1 - tid] = 0;
     }
     __syncthreads();
+    LZ_CLK(scratch, 8);
 
     // S4: match results into shared memory (over the sorted array), then the parse
     for (u32 i = tid; i < own_len; i += LZ_THREADS) XR[i] = R[i];
     bm[tid] = 0;
     for (u32 i = tid; i < LZ_HCOPIES * LZ_NSYM; i += LZ_THREADS) hcopies[i] = 0;
     __syncthreads();
+    LZ_CLK(scratch, 9);
     // Every walker parses its range from the range start (speculation), recording token starts in the
     // bitmap and where it left the range.  Then, in rounds, every walker whose true entry (= where the
     // previous range was really left) differs from the entry it last used re-parses from there until
@@ -453,6 +499,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       }
       if (!__syncthreads_or(changed)) break;
     }
+    LZ_CLK(scratch, 10);
 
     // S5: emit tokens and count symbols
     {
@@ -490,6 +537,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       if (tid == 0) P.ntok[b] = total;
     }
     __syncthreads();
+    LZ_CLK(scratch, 11);
   }
 }
 

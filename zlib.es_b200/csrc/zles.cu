@@ -11,6 +11,8 @@
 // tests only).
 #include "../../include/zles.h"
 
+#include <stdio.h>
+
 #include <algorithm>
 #include <mutex>
 #include <new>
@@ -138,7 +140,16 @@ static void timing_end(zles_ctx *c);
     ZLES_LAUNCH(kern, grid, block, smem, (ctx)->stream, __VA_ARGS__);    \
     if ((ctx)->timing) timing_end((ctx));                                \
     (ctx)->launches++;                                                   \
+    if (debug_sync()) debug_check((ctx), #kern);                         \
   } while (0)
+
+// ZLES_DEBUG_SYNC=1 in the environment: synchronise after every launch and name the kernel that faulted
+// on stderr (compute-sanitizer is not available on the GPU pool).
+static bool debug_sync() {
+  static const bool on = [] { const char *e = getenv("ZLES_DEBUG_SYNC"); return e && *e && *e != '0'; }();
+  return on;
+}
+static void debug_check(zles_ctx *c, const char *kern);
 
 static int resolve_ctx(zles_ctx *&c);
 
@@ -147,6 +158,11 @@ static zrt_event_t timing_event(zles_ctx *c) {
   zrt_event_t e{};
   zrt_event_create(&e);
   return e;
+}
+static void debug_check(zles_ctx *c, const char *kern) {
+  zrt_err_t e = zrt_sync(c->stream);
+  if (e == ZRT_OK) e = zrt_last_error();
+  if (e != ZRT_OK) fprintf(stderr, "[zles debug] %s: %s\n", kern, zrt_err_str(e));
 }
 static void timing_begin(zles_ctx *c, const char *name) {
   zles_ctx::TimedLaunch t{name, timing_event(c), timing_event(c)};
@@ -1267,3 +1283,15 @@ extern "C" int zles_dev_corpus(zles_ctx *c, int kind, uint64_t offset, uint8_t *
   CK(zrt_sync(c->stream));
   return 0;
 }
+
+#ifdef ZLES_STAGE_CLOCKS
+// profiling build only (tools/lz_stages.py): per-stage cycle totals of k_lz, summed over CTAs
+extern "C" int zles_debug_lz_clocks(unsigned long long *out16, int reset) {
+  if (out16) CK(cudaMemcpyFromSymbol(out16, g_lz_clk, sizeof(unsigned long long) * 16));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    CK(cudaMemcpyToSymbol(g_lz_clk, z, sizeof z));
+  }
+  return ZLES_OK;
+}
+#endif

@@ -271,6 +271,12 @@ static inline T atomicCAS(T *p, T cmp, T v) {
 }
 
 // integer intrinsics
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {  // selector nibbles 0..7 only (no sign replication)
+  const unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

@@ -56,9 +56,9 @@ constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] |
 constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 232448 available)
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position
 constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
-// per-warp candidate ring: 64 entries of 8 bytes, stored twice (slot i and i + 64) so that "entry k - r"
+// per-warp candidate ring: 64 entries of 4 bytes (lz_tag), stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
-static_assert(LZ_WARPS * 128 * 8 <= 32768, "candidate rings overlay the sort histograms");
+static_assert(LZ_WARPS * 128 * 4 <= 32768, "candidate rings overlay the sort histograms");
 
 struct LzParams {
   const u8 *in;       // this shard's input
@@ -99,7 +99,12 @@ __device__ unsigned long long g_lz_clk[16];
 __device__ __forceinline__ u32 tok_match(u32 len, u32 dist) { return 0x80000000u | ((len - 3) << 16) | (dist - 1); }
 
 __device__ __forceinline__ u32 lz_key3(const u8 *d, u32 p) { return (u32)d[p] | ((u32)d[p + 1] << 8) | ((u32)d[p + 2] << 16); }
-__device__ __forceinline__ u32 lz_hash16(u32 key) { return (key * 0x9E3779B1u) >> 16; }
+// lz_mix(w), w = the four bytes at a position: (w * M) with M = C << 8, C odd, depends on the 3-byte key only (the
+// fourth byte is multiplied out of the 32 bits) and is a bijection of the key onto bits 31..8.  Bits 31..16 are the
+// sort hash, bits 15..8 the "key fold": two positions with equal hash AND equal fold have the same 3-byte key.
+constexpr u32 LZ_HMUL = 0x3779B100u;
+__device__ __forceinline__ u32 lz_mix(u32 w) { return w * LZ_HMUL; }
+__device__ __forceinline__ u32 lz_hash16(u32 w) { return lz_mix(w) >> 16; }
 
 // unaligned 32-bit read from shared memory (two aligned loads + funnel shift)
 __device__ __forceinline__ u32 lz_ld32(const u8 *d, u32 p) {
@@ -125,8 +130,8 @@ __device__ __forceinline__ u32 lz_match_len(const u8 *d, u32 c, u32 p, u32 maxle
 // Pass 1 reads the data, pass 2 reads pass 1's output Y (u32 = hash << 16 | position, in global
 // memory / L2, coalesced, four loads in flight per lane).
 
-__device__ __forceinline__ u32 lz_key3_fast(const u8 *d, u32 p) {  // 2 word loads instead of 3 byte loads
-  return lz_ld32(d, p) & 0xffffffu;
+__device__ __forceinline__ u32 lz_key3_fast(const u8 *d, u32 p) {  // the key's bytes + one more (lz_mix ignores it)
+  return lz_ld32(d, p);
 }
 
 __device__ __forceinline__ void lz_hist_scan(u16 *wh, u32 *scratch) {  // exclusive scan, digit-major / warp-minor
@@ -240,6 +245,11 @@ __device__ __forceinline__ void lz_ld56(const u8 *d, u32 p, u32 &lo, u32 &hi) {
   hi = __funnelshift_r(w1, w2, sh) & 0x00ffffffu;
 }
 
+// ring entry of a position: [key fold, byte 3, byte 4, byte 5] (q = lz_mix(lo); lo, hi from lz_ld56)
+__device__ __forceinline__ u32 lz_tag(u32 q, u32 lo, u32 hi) {
+  return __byte_perm(__byte_perm(q, lo, 0x0071), hi, 0x5410);
+}
+
 // match length the parse uses at own-relative position pos (0 = literal)
 __device__ __forceinline__ u32 lz_parse_len(const u32 *XR, u32 pos, u32 own_len, u32 lazy) {
   u32 len = XR[pos] >> 16;
@@ -256,6 +266,36 @@ __device__ __forceinline__ void lz_clear_bits(u32 *bm, u32 a, u32 b) {  // clear
     a += hi - lo;
   }
 }
+
+// One candidate of the S3 scan (see there): uses es, rp, rrun, one; updates best, full.  `one` is the value 1 in a
+// register the assembler cannot see through, which keeps the two multiply-adds on the FMA pipe.
+#ifdef ZLES_EMU
+#define LZ_CAND(r)                                                 \
+  do {                                                             \
+    const u32 v_ = es ^ rp[-(int)(r)];                             \
+    const u32 z_ = ~v_ & (v_ * one - 1u) & 0x80808080u;            \
+    if ((r) <= rrun) {                                             \
+      best = umax(best, z_ | (64u - (r)));                         \
+      if (v_ == 0) full |= 1u << ((r) - 1);                        \
+    }                                                              \
+  } while (0)
+#else
+#define LZ_CAND(r)                                                 \
+  asm("{\n\t"                                                      \
+      ".reg .pred p, q;\n\t"                                       \
+      ".reg .b32 v, t, z;\n\t"                                     \
+      "xor.b32 v, %2, %3;\n\t"                                     \
+      "mad.lo.u32 t, v, %4, 0xffffffff;\n\t"                       \
+      "lop3.b32 z, v, t, 0x80808080, 0x08;\n\t"                    \
+      "mad.lo.u32 z, z, %4, %6;\n\t"                               \
+      "setp.ge.u32 p, %5, %7;\n\t"                                 \
+      "setp.eq.and.u32 q, v, 0, p;\n\t"                            \
+      "@p max.u32 %0, %0, z;\n\t"                                  \
+      "@q or.b32 %1, %1, %8;\n\t"                                  \
+      "}"                                                          \
+      : "+r"(best), "+r"(full)                                     \
+      : "r"(es), "r"(rp[-(int)(r)]), "r"(one), "r"(rrun), "n"(64 - (r)), "n"(r), "n"(1u << ((r) - 1)))
+#endif
 
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   ZLES_SMEM_DECL(smem);
@@ -336,10 +376,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     while (((u32)LZ_WARPS << lper) < N) lper++;
     lz_sort(data, Y, X, wh, scratch, N, lper);
 
-    // S3: per-position match search.  Warp w owns sorted entries [kbeg, kend).
+    // S3: per-position match search.  Warps take slices of the sorted array.
     {
-      uint2 *ring = reinterpret_cast<uint2 *>(smem + LZ_OFF_WH) + w * 128;
+      u32 *ring = reinterpret_cast<u32 *>(smem + LZ_OFF_WH) + w * 128;
       const u32 scan = umin(P.max_checks, LZ_SCAN);
+      const u32 one = (P.max_checks >> 31) + 1;  // 1 (max_checks <= LZ_SCAN is enforced by the host)
       // slices of LZ_SLICE sorted entries are handed out dynamically (their cost depends on the run structure)
       for (;;) {
       u32 slice = 0;
@@ -351,12 +392,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       u32 Bprev = 0, hprev = 0xffffffffu;
       if (kbeg > 0) {  // the 32 entries before the slice are candidates of its first ones (kbeg is a multiple of 32)
         const u32 j = kbeg - 32 + lane;
-        const u32 pj = X[j];
         u32 lo, hi;
-        lz_ld56(data, pj, lo, hi);
-        ring[j & 63] = make_uint2(lo, hi);
-        ring[(j & 63) + 64] = make_uint2(lo, hi);
-        const u32 hj = lz_hash16(lo & 0xffffffu);
+        lz_ld56(data, X[j], lo, hi);
+        const u32 q = lz_mix(lo);
+        const u32 e = lz_tag(q, lo, hi);
+        ring[j & 63] = e;
+        ring[(j & 63) + 64] = e;
+        const u32 hj = q >> 16;
         u32 hl = __shfl_up_sync(ZLES_FULL, hj, 1);
         if (lane == 0) hl = 0xffffffffu;  // whether entry kbeg-32 starts a run never matters (see rrun below)
         Bprev = __ballot_sync(ZLES_FULL, hj != hl);
@@ -366,20 +408,24 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       for (u32 kb = kbeg; kb < kend; kb += 32) {
         const u32 k = kb + lane;
         const bool valid = k < kend;
-        u32 p = 0, lo = 0, hi = 0, h = 0x10000u + lane;
+        u32 p = 0, es = 0, h = 0x10000u + lane;
         if (valid) {
+          u32 lo, hi;
           p = X[k];
           lz_ld56(data, p, lo, hi);
-          h = lz_hash16(lo & 0xffffffu);
+          const u32 q = lz_mix(lo);
+          es = lz_tag(q, lo, hi);
+          h = q >> 16;
         }
-        ring[k & 63] = make_uint2(lo, hi);
-        ring[(k & 63) + 64] = make_uint2(lo, hi);
+        ring[k & 63] = es;
+        ring[(k & 63) + 64] = es;
         u32 hl = __shfl_up_sync(ZLES_FULL, h, 1);
         if (lane == 0) hl = hprev;
         const u32 B = __ballot_sync(ZLES_FULL, h != hl);  // bit l: entry kb+l starts a run of equal hashes
         hprev = __shfl_sync(ZLES_FULL, h, 31);
         __syncwarp();
-        // rrun = how many entries before k belong to k's run (capped at the scan width)
+        // rrun = how many entries before k belong to k's run (capped at the scan width): the only ones that
+        // may be looked at — what precedes them in the ring is another run, an older slice, or stale
         const bool own = valid && p >= hist_len;
         u32 rrun = 0;
         if (own) {
@@ -399,42 +445,46 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
           }
         }
         const u32 rmax = __reduce_max_sync(ZLES_FULL, rrun);
-        // Branch-free, fully unrolled body: candidate r is entry k-r of the ring, at a constant offset from
-        // `rp`; ml = bytes equal from offset 0 (3..7).
+        // Branch-free, fully unrolled body: candidate r is entry k-r of the ring, at a constant offset from `rp`.
+        // v = own tag ^ candidate's tag: its zero bytes from the bottom are [fold, byte 3, byte 4, byte 5];
+        // ~v & (v - 1) has bit 7 of exactly those bytes set, so z orders candidates by match length 2 + popc(z)
+        // (0: another key; 3, 4, 5; 6 = at least six, to be extended), and z | (64 - r) prefers the nearer of equals
+        // (src/lz77.ts:86-92).  The loop is bound by the ALU pipe (one warp instruction per 2 cycles and scheduler),
+        // so LZ_CAND spells it out: 6 ALU instructions, 2 integer multiply-adds (FMA pipe) and the load.
         u32 best = 0, full = 0;
-        const uint2 *rp = ring + (k & 63) + 64;
-#pragma unroll
-        for (u32 r = 1; r <= LZ_SCAN; r++) {
-          if (((r - 1) & 7) == 0 && r > rmax) break;               // warp-uniform early out, checked every 8 candidates
-          const uint2 ce = rp[-(int)r];
-          const u32 xl = lo ^ ce.x, xh = hi ^ ce.y;
-          const u32 v = __funnelshift_r(xl, xh, 24);                // bytes 3..6
-          const bool ok = ((xl & 0xffffffu) == 0) & (r <= rrun);    // same 3-byte key (src/lz77.ts:40), inside run and window
-          const u32 tz = (u32)__clz((int)__brev(v));                // 32 when bytes 3..6 are all equal
-          const u32 key = ((tz << 5) & 0x700u) + (0x340u - r);      // (3 + tz / 8) << 8 | (64 - r)
-          if (ok) best = umax(best, key);
-          if (ok & (v == 0)) full |= 1u << (r - 1);
+        const u32 *rp = ring + (k & 63) + 64;
+        if (rmax >= 1) {
+          LZ_CAND(1); LZ_CAND(2); LZ_CAND(3); LZ_CAND(4); LZ_CAND(5); LZ_CAND(6); LZ_CAND(7); LZ_CAND(8);
+          if (rmax >= 9) {
+            LZ_CAND(9); LZ_CAND(10); LZ_CAND(11); LZ_CAND(12); LZ_CAND(13); LZ_CAND(14); LZ_CAND(15); LZ_CAND(16);
+            if (rmax >= 17) {
+              LZ_CAND(17); LZ_CAND(18); LZ_CAND(19); LZ_CAND(20); LZ_CAND(21); LZ_CAND(22); LZ_CAND(23); LZ_CAND(24);
+              if (rmax >= 25) {
+                LZ_CAND(25); LZ_CAND(26); LZ_CAND(27); LZ_CAND(28); LZ_CAND(29); LZ_CAND(30); LZ_CAND(31); LZ_CAND(32);
+              }
+            }
+          }
         }
         if (own) {
           const u32 maxlen = umin(MAX_MATCH, L - p);
           u32 len = 0, dist = 0;
-          if (full) {  // candidates equal on 7 bytes: extend, nearest first
+          if (full) {  // candidates equal on 6 bytes: extend, nearest first
             u32 m = full, n = 0;
             while (m && n < P.min_checks) {
               const u32 r = (u32)__ffs((int)m);
               m &= m - 1;
               n++;
               const u32 c = X[k - r];
-              const u32 l = maxlen > 7 ? 7 + lz_match_len(data, c + 7, p + 7, maxlen - 7) : maxlen;
+              const u32 l = maxlen > 6 ? 6 + lz_match_len(data, c + 6, p + 6, maxlen - 6) : maxlen;
               if (l > len) {  // strictly longer wins, ties keep the nearest (src/lz77.ts:86-92)
                 len = l;
                 dist = p - c;
                 if (l >= maxlen) break;
               }
             }
-          } else if (best) {
-            len = umin(best >> 8, maxlen);
-            dist = p - (u32)X[k - (64 - (best & 255))];
+          } else if (best >= 0x80u) {
+            len = umin(2u + (u32)__popc(best & 0x80808080u), maxlen);
+            dist = p - (u32)X[k - (64 - (best & 0x7fu))];
           }
           if (len == MIN_MATCH && dist > 4096) len = 0;  // costs more than three literals
           R[p - hist_len] = len >= MIN_MATCH ? (len << 16) | dist : 0;

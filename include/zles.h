@@ -53,8 +53,10 @@ int zles_ctx_create(int device, zles_ctx **ctx);
 void zles_ctx_destroy(zles_ctx *ctx);
 /* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
 int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
-/* Encoder search depth; defaults mirror /root/reference/src/lz77.ts:7-9 scaled for an
- * all-positions search: max_checks, min_checks (once good_len is reached), good_len, lazy. */
+/* Encoder search depth (the reference's FAST_INDEX_CHECK_MAX, /root/reference/src/lz77.ts:7, scaled for an
+ * all-positions search): max_checks = candidates compared per position (1..32, default 32); lazy = defer a match by
+ * one literal when the next position has a longer one (default 1).  min_checks and good_len are reserved (ignored):
+ * the nearest candidate of the longest class is the one that is extended. */
 int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);

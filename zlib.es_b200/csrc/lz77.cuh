@@ -54,7 +54,7 @@ constexpr u32 LZ_OFF_X = 65536 + 384;                       // 65920
 constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256] | bitmap u32[1024] + hist u32[8*320]
 constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] | specexit u32[64] | mbarrier
 constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 232448 available)
-constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position
+constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (at most)
 constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
 // per-warp candidate ring: 64 entries of 4 bytes (lz_tag), stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
@@ -71,7 +71,7 @@ struct LzParams {
   u32 *scratch;       // [gridDim.x][2 * SUB] u32: sort pass buffer, then match results
   u64 *adler_part;    // [nblocks][2]: sum d, sum (len - j) d[j] over the block's own bytes
   u32 max_checks;     // candidates compared per position, <= LZ_SCAN   (reference: FAST_INDEX_CHECK_MAX = 128, src/lz77.ts:7)
-  u32 min_checks;     // of those, how many >= 7-byte candidates are extended (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
+  u32 min_checks;     // reserved (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
   u32 good_len;       // reserved (reference: FAST_REPEAT_LENGTH = 8, src/lz77.ts:9)
   u32 lazy;           // 1: defer a match by one literal when the next position has a longer one
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
@@ -91,8 +91,20 @@ __device__ unsigned long long g_lz_clk[16];
       *cp_ = t_;                                                                         \
     }                                                                                    \
   } while (0)
+// inside S3: warp 0 accumulates its own cycles per sub-stage (fill + run lengths, scan, finalize)
+#define LZ_WCLK(i)                                                        \
+  do {                                                                    \
+    if (threadIdx.x == 0) {                                               \
+      const long long t_ = clock64();                                     \
+      atomicAdd(&g_lz_clk[i], (unsigned long long)(t_ - wclk));           \
+      wclk = t_;                                                          \
+    }                                                                     \
+  } while (0)
+#define LZ_WCLK_DECL long long wclk = clock64()
 #else
 #define LZ_CLK(scr, i) do { } while (0)
+#define LZ_WCLK(i) do { } while (0)
+#define LZ_WCLK_DECL do { } while (0)
 #endif
 
 // token encoding shared with pack.cuh: literal = byte value; match = bit31 | (len-3)<<16 | (dist-1)
@@ -245,6 +257,14 @@ __device__ __forceinline__ void lz_ld56(const u8 *d, u32 p, u32 &lo, u32 &hi) {
   hi = __funnelshift_r(w1, w2, sh) & 0x00ffffffu;
 }
 
+// bytes d[p .. p+7] as one u64; unaligned shared-memory read (3 aligned loads)
+__device__ __forceinline__ u64 lz_ld64(const u8 *d, u32 p) {
+  const u32 *w = reinterpret_cast<const u32 *>(d + (p & ~3u));
+  const u32 sh = (p & 3) * 8;
+  const u32 w0 = w[0], w1 = w[1], w2 = w[2];
+  return ((u64)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+}
+
 // ring entry of a position: [key fold, byte 3, byte 4, byte 5] (q = lz_mix(lo); lo, hi from lz_ld56)
 __device__ __forceinline__ u32 lz_tag(u32 q, u32 lo, u32 hi) {
   return __byte_perm(__byte_perm(q, lo, 0x0071), hi, 0x5410);
@@ -267,34 +287,29 @@ __device__ __forceinline__ void lz_clear_bits(u32 *bm, u32 a, u32 b) {  // clear
   }
 }
 
-// One candidate of the S3 scan (see there): uses es, rp, rrun, one; updates best, full.  `one` is the value 1 in a
+// One candidate of the S3 scan (see there): uses es, rp, rrun, one; updates best.  `one` is the value 1 in a
 // register the assembler cannot see through, which keeps the two multiply-adds on the FMA pipe.
 #ifdef ZLES_EMU
 #define LZ_CAND(r)                                                 \
   do {                                                             \
     const u32 v_ = es ^ rp[-(int)(r)];                             \
     const u32 z_ = ~v_ & (v_ * one - 1u) & 0x80808080u;            \
-    if ((r) <= rrun) {                                             \
-      best = umax(best, z_ | (64u - (r)));                         \
-      if (v_ == 0) full |= 1u << ((r) - 1);                        \
-    }                                                              \
+    if ((r) <= rrun) best = umax(best, z_ | (64u - (r)));          \
   } while (0)
 #else
 #define LZ_CAND(r)                                                 \
   asm("{\n\t"                                                      \
-      ".reg .pred p, q;\n\t"                                       \
+      ".reg .pred p;\n\t"                                          \
       ".reg .b32 v, t, z;\n\t"                                     \
-      "xor.b32 v, %2, %3;\n\t"                                     \
-      "mad.lo.u32 t, v, %4, 0xffffffff;\n\t"                       \
+      "xor.b32 v, %1, %2;\n\t"                                     \
+      "mad.lo.u32 t, v, %3, 0xffffffff;\n\t"                       \
       "lop3.b32 z, v, t, 0x80808080, 0x08;\n\t"                    \
-      "mad.lo.u32 z, z, %4, %6;\n\t"                               \
-      "setp.ge.u32 p, %5, %7;\n\t"                                 \
-      "setp.eq.and.u32 q, v, 0, p;\n\t"                            \
+      "mad.lo.u32 z, z, %3, %5;\n\t"                               \
+      "setp.ge.u32 p, %4, %6;\n\t"                                 \
       "@p max.u32 %0, %0, z;\n\t"                                  \
-      "@q or.b32 %1, %1, %8;\n\t"                                  \
       "}"                                                          \
-      : "+r"(best), "+r"(full)                                     \
-      : "r"(es), "r"(rp[-(int)(r)]), "r"(one), "r"(rrun), "n"(64 - (r)), "n"(r), "n"(1u << ((r) - 1)))
+      : "+r"(best)                                                 \
+      : "r"(es), "r"(rp[-(int)(r)]), "r"(one), "r"(rrun), "n"(64 - (r)), "n"(r))
 #endif
 
 __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
@@ -406,6 +421,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         __syncwarp();
       }
       for (u32 kb = kbeg; kb < kend; kb += 32) {
+        LZ_WCLK_DECL;
         const u32 k = kb + lane;
         const bool valid = k < kend;
         u32 p = 0, es = 0, h = 0x10000u + lane;
@@ -429,9 +445,8 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         const bool own = valid && p >= hist_len;
         u32 rrun = 0;
         if (own) {
-          const u64 t = ((((u64)B) << 32) | Bprev) << (31 - lane);  // bit 63 = entry k, bit 62 = entry k-1, ...
-          rrun = t ? (u32)__clzll((long long)t) : 64u;
-          rrun = umin(rrun, scan);
+          // bit 31 = entry k's run-start flag, bit 30 = entry k-1's, ...: the leading zeros count the run's earlier entries
+          rrun = umin((u32)__clz((int)__funnelshift_rc(Bprev, B, lane + 1)), scan);
           if (rrun && p > WINDOW && (u32)X[k - rrun] < p - WINDOW) {
             // candidates older than the window (src/lz77.ts:49): positions ascend inside a run, so
             // binary-search the largest r with X[k-r] >= p - WINDOW
@@ -450,9 +465,10 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         // ~v & (v - 1) has bit 7 of exactly those bytes set, so z orders candidates by match length 2 + popc(z)
         // (0: another key; 3, 4, 5; 6 = at least six, to be extended), and z | (64 - r) prefers the nearer of equals
         // (src/lz77.ts:86-92).  The loop is bound by the ALU pipe (one warp instruction per 2 cycles and scheduler),
-        // so LZ_CAND spells it out: 6 ALU instructions, 2 integer multiply-adds (FMA pipe) and the load.
-        u32 best = 0, full = 0;
+        // so LZ_CAND spells it out: 4 ALU instructions, 2 integer multiply-adds (FMA pipe) and the load.
+        u32 best = 0;
         const u32 *rp = ring + (k & 63) + 64;
+        LZ_WCLK(12);
         if (rmax >= 1) {
           LZ_CAND(1); LZ_CAND(2); LZ_CAND(3); LZ_CAND(4); LZ_CAND(5); LZ_CAND(6); LZ_CAND(7); LZ_CAND(8);
           if (rmax >= 9) {
@@ -465,32 +481,31 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
             }
           }
         }
-        if (own) {
+        LZ_WCLK(13);
+        // The winner: the nearest candidate of the longest class.  Classes 3..5 are exact lengths; the class "six or
+        // more" is extended — its first 8 bytes in straight-line code for the whole warp, the rest (rare on text) in a loop.
+        const bool hit = own && best >= 0x80u;
+        if (__any_sync(ZLES_FULL, hit)) {
+          const u32 c = hit ? (u32)X[k - (64 - (best & 0x7fu))] : p;
           const u32 maxlen = umin(MAX_MATCH, L - p);
-          u32 len = 0, dist = 0;
-          if (full) {  // candidates equal on 6 bytes: extend, nearest first
-            u32 m = full, n = 0;
-            while (m && n < P.min_checks) {
-              const u32 r = (u32)__ffs((int)m);
-              m &= m - 1;
-              n++;
-              const u32 c = X[k - r];
-              const u32 l = maxlen > 6 ? 6 + lz_match_len(data, c + 6, p + 6, maxlen - 6) : maxlen;
-              if (l > len) {  // strictly longer wins, ties keep the nearest (src/lz77.ts:86-92)
-                len = l;
-                dist = p - c;
-                if (l >= maxlen) break;
-              }
+          u32 len = 2u + (u32)__popc(best & 0x80808080u);
+          if (__any_sync(ZLES_FULL, hit && len == 6)) {
+            const u64 x = lz_ld64(data, p + 6) ^ lz_ld64(data, c + 6);
+            if (hit && len == 6) {
+              len = x ? 6 + ((u32)(__ffsll((long long)x) - 1) >> 3) : 14;
+              if (!x && maxlen > 14) len = 14 + lz_match_len(data, c + 14, p + 14, maxlen - 14);
             }
-          } else if (best >= 0x80u) {
-            len = umin(2u + (u32)__popc(best & 0x80808080u), maxlen);
-            dist = p - (u32)X[k - (64 - (best & 0x7fu))];
           }
+          len = umin(len, maxlen);
+          const u32 dist = p - c;
           if (len == MIN_MATCH && dist > 4096) len = 0;  // costs more than three literals
-          R[p - hist_len] = len >= MIN_MATCH ? (len << 16) | dist : 0;
+          if (own) R[p - hist_len] = (hit && len >= MIN_MATCH) ? (len << 16) | dist : 0;
+        } else if (own) {
+          R[p - hist_len] = 0;
         }
         Bprev = B;
         __syncwarp();  // the next batch overwrites the older half of the ring
+        LZ_WCLK(14);
       }
       }  // slices
       // positions without a full 3-byte key (the last two of the window+block) have no match

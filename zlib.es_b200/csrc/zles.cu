@@ -102,7 +102,7 @@ struct zles_ctx {
   int sm_count = 148;
   uint64_t launches = 0;
   // encoder search depth (see zles_ctx_set_level)
-  u32 max_checks = 24, min_checks = 2, good_len = 8, lazy = 1;
+  u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace

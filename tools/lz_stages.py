@@ -47,3 +47,15 @@ if __name__ == "__main__":
         print("  %-16s %6.2f %%   %8.0f cycles/block" % (nm, 100.0 * out[i] / tot, out[i] / (n / 32768)))
     w = sum(out[12:15]) or 1
     print("  inside S3 (warp 0's own cycles): fill + run lengths %.1f %%, scan %.1f %%, finalize %.1f %%" % tuple(100.0 * out[i] / w for i in (12, 13, 14)))
+    # phase A of inflate on the stream just made
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    c.dev_inflate(comp.data_ptr(), clen, back.data_ptr(), n)
+    torch.cuda.synchronize()
+    io = (ctypes.c_ulonglong * 8)()
+    L.zles_debug_inf_clocks(None, 1)
+    assert c.dev_inflate(comp.data_ptr(), clen, back.data_ptr(), n) == n
+    torch.cuda.synchronize()
+    L.zles_debug_inf_clocks(io, 0)
+    nseg = (n + 32767) // 32768
+    print("  k_inf_tokens per segment: header+tables %.0f cycles, symbol loop %.0f cycles, reader re-seating %.0f cycles; %.0f tokens, %.0f rounds (%.2f tokens/round, %.0f cycles/round), %.1f tokens decoded alone"
+          % (io[0] / nseg, io[1] / nseg, io[5] / nseg, io[3] / nseg, io[2] / nseg, io[3] / max(io[2], 1), io[1] / max(io[2], 1), io[4] / nseg))

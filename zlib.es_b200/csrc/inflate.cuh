@@ -597,6 +597,46 @@ struct TokReader {
   __device__ __forceinline__ bool past_end() const { return bitpos() > (n << 3); }  // consumed bits the buffer does not have
 };
 
+// Reader of the symbol loop of phase A.  The warp holds the next 128 unread bits of the stream, from a word
+// boundary, in four warp-uniform registers; `boff` bits of W0 are consumed.  Lane i looks at the stream at bit
+// offset boff + i, so the 32 lanes decode the tokens that would start at the next 32 bit positions all at once
+// (inf_segment_tokens); the words come from TokReader's 128-byte warp window.
+struct SpecReader : TokReader {
+  u32 W0, W1, W2, W3;
+  u32 boff;
+
+  __device__ __forceinline__ void begin(const u8 *in_, u64 n_, u64 bit_pos) {  // bit_pos relative to in_
+    in = in_; n = n_;
+    skew = (u32)((uintptr_t)in_ & 3);
+    words = reinterpret_cast<const u32 *>(in_ - skew);
+    const u64 a = bit_pos + ((u64)skew << 3);
+    const u64 w0 = a >> 5;
+    boff = (u32)(a & 31);
+    wabs = w0 & ~(u64)31;
+    wi = (u32)(w0 - wabs);
+    win = load_word(wabs + lane_id());
+    win_next = load_word(wabs + 32 + lane_id());
+    W0 = next_word(); W1 = next_word(); W2 = next_word(); W3 = next_word();
+  }
+  __device__ __forceinline__ u64 pos() const { return ((wabs + wi - 4) << 5) + boff - ((u64)skew << 3); }
+  __device__ __forceinline__ void advance(u32 c) {  // warp-uniform
+    boff += c;
+    while (boff >= 32) {
+      W0 = W1; W1 = W2; W2 = W3;
+      W3 = next_word();
+      boff -= 32;
+    }
+  }
+  // the 64 bits at offset boff + s, s <= 31
+  __device__ __forceinline__ void at(u32 s, u32 &lo, u32 &hi) const {
+    const u32 t = boff + s;
+    const bool up = t >= 32;
+    const u32 a = up ? W1 : W0, b = up ? W2 : W1, c = up ? W3 : W2;
+    lo = __funnelshift_r(a, b, t);  // shift taken modulo 32
+    hi = __funnelshift_r(b, c, t);
+  }
+};
+
 // dynamic block header for phase A (same as inf_read_dynamic_header, on the TokReader)
 __device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem *S, u32 &status) {
   const u32 lane = lane_id();
@@ -639,6 +679,26 @@ __device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem
   return true;
 }
 
+// profiling build (tools/lz_stages.py): warp totals of phase A — cycles in block headers + table builds, cycles in the
+// symbol loop, rounds, tokens, tokens decoded on their own, cycles re-seating the readers
+#ifdef ZLES_STAGE_CLOCKS
+__device__ unsigned long long g_inf_clk[8];
+#define INF_CLK(i)                                                         \
+  do {                                                                     \
+    if (lane_id() == 0) {                                                  \
+      const long long t_ = clock64();                                      \
+      atomicAdd(&g_inf_clk[i], (unsigned long long)(t_ - iclk));           \
+      iclk = t_;                                                           \
+    }                                                                      \
+  } while (0)
+#define INF_CNT(i, v) do { if (lane_id() == 0) atomicAdd(&g_inf_clk[i], (unsigned long long)(v)); } while (0)
+#define INF_CLK_DECL long long iclk = clock64()
+#else
+#define INF_CLK(i) do { } while (0)
+#define INF_CNT(i, v) do { } while (0)
+#define INF_CLK_DECL do { } while (0)
+#endif
+
 __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out) {
   const u32 lane = lane_id();
   InfWarpSmem *S = &T->w;
@@ -647,6 +707,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
   u32 o = 0, nt = 0, mytok = 0;
   u32 status = 0, flags = 0;
   u64 end_pos = 0;
+  INF_CLK_DECL;
   // token t goes to lane (t & 31); `turn` counts down to this lane's turn, `left` to the next 128-byte store
   u32 turn = lane, left = 32;
 #define ZLES_EMIT(t)                                         \
@@ -699,36 +760,89 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
     __syncwarp();
     // symbol loop (/root/reference/src/inflate.ts:237-291 without the copy).  It cannot run away: every
     // token accounts for at least one output byte and a token is only emitted while o < SUB.
-    for (;;) {
-      r.refill();
-      u32 e = T->lut_ll[r.lo & ((1u << LL_ROOT) - 1)];
-      if ((e & 15) == 0) {
-        u32 sym, l;
-        if (!inf_slow(r.bits64(), &S->tab_ll, S->sorted_ll, sym, l)) { status = SEG_E_CORRUPT; break; }
-        e = tk_entry_ll(sym, l);
-        if (e & TK_INV) { status = SEG_E_CORRUPT; break; }
+    // Every round, lane i decodes the token that would start i bits from the current position — both table
+    // look-ups, extra bits and all — and the warp then follows the chain from lane 0: a token of b bits at lane c
+    // is followed by the one at lane c + b.  Two or three tokens per round on text, for the instructions of one.
+    {
+      INF_CLK(0);
+      SpecReader sr;
+      sr.begin(in, n, r.bitpos());
+      INF_CLK(5);
+      bool eob = false;
+      while (!eob && !status) {
+        INF_CNT(2, 1);
+        u32 lo, hi;
+        sr.at(lane, lo, hi);
+        const u32 e = T->lut_ll[lo & ((1u << LL_ROOT) - 1)];
+        const u32 l1 = e & 15, eb = (e >> 4) & 15, sh2 = l1 + eb;
+        const u32 len = ((e >> 8) & 0xffff) + ((lo >> l1) & ~(0xffffffffu << eb));  // a literal's value when eb == 0
+        const u32 y = __funnelshift_r(lo, hi, sh2);                                 // the stream after the length's extra bits
+        const u32 d = T->lut_d[y & ((1u << D_ROOT) - 1)];
+        const u32 l2 = d & 15, db = (d >> 4) & 15;
+        const u32 dist = (d >> 8) + ((y >> l2) & ~(0xffffffffu << db));
+        const bool is_len = (e & TK_LEN) != 0;
+        // pack: bits the token takes (0 = a code the fast tables do not hold: decoded on its own below) | bit 8 end of block
+        u32 pack = is_len ? (l2 ? sh2 + l2 + db : 0) : l1;
+        if (l1 == 0) pack = 0;
+        if (e & TK_EOB) pack |= 0x100;
+        const u32 tokv = is_len ? (0x80000000u | ((len - 3) << 16) | (dist - 1)) : (len & 0xff);
+        u32 cur = 0;
+        bool slow = false;
+        for (;;) {
+          const u32 pk = __shfl_sync(ZLES_FULL, pack, (int)cur);
+          const u32 nb = pk & 0xff;
+          if (nb == 0) { slow = true; break; }
+          if (pk & 0x100) { cur += nb; eob = true; break; }
+          if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+          const u32 t = __shfl_sync(ZLES_FULL, tokv, (int)cur);
+          ZLES_EMIT(t);
+          o += (t >> 31) ? ((t >> 16) & 0x1ff) + 3 : 1;
+          cur += nb;
+          if (cur >= 32) break;
+        }
+        sr.advance(cur);
+        if (slow) {  // one token with a code longer than the root table (or an invalid one), the canonical way
+          INF_CNT(4, 1);
+          sr.at(0, lo, hi);
+          u32 e2 = T->lut_ll[lo & ((1u << LL_ROOT) - 1)];
+          if ((e2 & 15) == 0) {
+            u32 sym, l;
+            if (!inf_slow(((u64)hi << 32) | lo, &S->tab_ll, S->sorted_ll, sym, l)) { status = SEG_E_CORRUPT; break; }
+            e2 = tk_entry_ll(sym, l);
+            if (e2 & TK_INV) { status = SEG_E_CORRUPT; break; }
+          }
+          if (e2 & TK_EOB) { sr.advance(e2 & 15); eob = true; break; }
+          if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+          if (e2 < TK_LEN) {
+            sr.advance(e2 & 15);
+            ZLES_EMIT(e2 >> 8);
+            o++;
+            continue;
+          }
+          const u32 eb2 = (e2 >> 4) & 15;
+          const u32 len2 = ((e2 >> 8) & 0xffff) + ((lo >> (e2 & 15)) & ~(0xffffffffu << eb2));  // code <= 15 bits, extra <= 5
+          sr.advance((e2 & 15) + eb2);
+          sr.at(0, lo, hi);
+          u32 d2 = T->lut_d[lo & ((1u << D_ROOT) - 1)];
+          if ((d2 & 15) == 0) {
+            u32 sym, l;
+            if (!inf_slow(((u64)hi << 32) | lo, &S->tab_d, S->sorted_d, sym, l)) { status = SEG_E_CORRUPT; break; }
+            d2 = tk_entry_d(sym, l);
+            if (d2 & TK_INV) { status = SEG_E_CORRUPT; break; }
+          }
+          const u32 db2 = (d2 >> 4) & 15;
+          const u32 dist2 = (d2 >> 8) + ((lo >> (d2 & 15)) & ~(0xffffffffu << db2));           // code <= 15 bits, extra <= 13
+          sr.advance((d2 & 15) + db2);
+          ZLES_EMIT(0x80000000u | ((len2 - 3) << 16) | (dist2 - 1));
+          o += len2;
+        }
       }
-      r.skip(e & 15);
-      if (e & TK_EOB) break;
-      if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
-      if (e < TK_LEN) {  // literal
-        ZLES_EMIT(e >> 8);
-        o++;
-        continue;
-      }
-      const u32 len = ((e >> 8) & 0xffff) + r.take((e >> 4) & 15);
-      r.refill();
-      u32 d = T->lut_d[r.lo & ((1u << D_ROOT) - 1)];
-      if ((d & 15) == 0) {
-        u32 sym, l;
-        if (!inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) { status = SEG_E_CORRUPT; break; }
-        d = tk_entry_d(sym, l);
-        if (d & TK_INV) { status = SEG_E_CORRUPT; break; }
-      }
-      r.skip(d & 15);
-      const u32 dist = (d >> 8) + r.take((d >> 4) & 15);
-      ZLES_EMIT(0x80000000u | ((len - 3) << 16) | (dist - 1));
-      o += len;
+      // back to the block-level reader at the position the symbol loop stopped
+      INF_CLK(1);
+      const u64 pos = sr.pos();
+      r.init(in, n, pos >> 3);
+      r.skip((u32)(pos & 7));
+      INF_CLK(5);
     }
     if (o > SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; }
     if (status) break;
@@ -736,6 +850,8 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
     if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
   }
 #undef ZLES_EMIT
+  INF_CLK(0);
+  INF_CNT(3, nt);
   if (lane < (nt & 31)) tok[(nt & ~31u) + lane] = mytok;
   if (lane == 0) {
     res->end_pos = end_pos;

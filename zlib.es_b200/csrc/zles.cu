@@ -1294,4 +1294,12 @@ extern "C" int zles_debug_lz_clocks(unsigned long long *out16, int reset) {
   }
   return ZLES_OK;
 }
+extern "C" int zles_debug_inf_clocks(unsigned long long *out8, int reset) {
+  if (out8) CK(cudaMemcpyFromSymbol(out8, g_inf_clk, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0};
+    CK(cudaMemcpyToSymbol(g_inf_clk, z, sizeof z));
+  }
+  return ZLES_OK;
+}
 #endif

@@ -704,18 +704,15 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
   InfWarpSmem *S = &T->w;
   TokReader r;
   r.init(in, n, in_pos);
-  u32 o = 0, nt = 0, mytok = 0;
+  u32 o = 0, nt = 0;
   u32 status = 0, flags = 0;
   u64 end_pos = 0;
   INF_CLK_DECL;
-  // token t goes to lane (t & 31); `turn` counts down to this lane's turn, `left` to the next 128-byte store
-  u32 turn = lane, left = 32;
-#define ZLES_EMIT(t)                                         \
-  do {                                                       \
-    if (turn == 0) mytok = (t);                              \
-    turn = (turn - 1) & 31;                                  \
-    nt++;                                                    \
-    if (--left == 0) { tok[nt - 32 + lane] = mytok; left = 32; } \
+  // a single token, outside the parallel rounds of the symbol loop
+#define ZLES_EMIT(t)                 \
+  do {                               \
+    if (lane == 0) tok[nt] = (t);    \
+    nt++;                            \
   } while (0)
   for (;;) {
     r.refill();
@@ -786,19 +783,52 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
         if (l1 == 0) pack = 0;
         if (e & TK_EOB) pack |= 0x100;
         const u32 tokv = is_len ? (0x80000000u | ((len - 3) << 16) | (dist - 1)) : (len & 0xff);
+        // The chain: lane 0 is a token start; a token of nb bits at lane c makes lane c + nb one.  A token that
+        // ends the round (end of block, or a code the fast tables do not hold) leads nowhere.
+        const u32 nb = pack & 0xff;
+        const bool stop = nb == 0 || (pack & 0x100);
+        const u32 step = (!stop && lane + nb < 32) ? 1u << (lane + nb) : 0;
+        u32 R = 1;
+        for (;;) {
+          const u32 add = __reduce_or_sync(ZLES_FULL, ((R >> lane) & 1) ? step : 0u);
+          if ((add & ~R) == 0) break;
+          R |= add;
+        }
+        const u32 last = 31u - (u32)__clz((int)R);                        // the chain's last member
+        const u32 plast = __shfl_sync(ZLES_FULL, pack, (int)last);
+        const bool last_stops = (plast & 0xff) == 0 || (plast & 0x100);
+        const u32 plain = last_stops ? R & ~(1u << last) : R;              // the members that are ordinary tokens
+        const bool mine = (plain >> lane) & 1;
+        const u32 sum = __reduce_add_sync(ZLES_FULL, mine ? (is_len ? len : 1u) : 0u);
         u32 cur = 0;
         bool slow = false;
-        for (;;) {
-          const u32 pk = __shfl_sync(ZLES_FULL, pack, (int)cur);
-          const u32 nb = pk & 0xff;
-          if (nb == 0) { slow = true; break; }
-          if (pk & 0x100) { cur += nb; eob = true; break; }
-          if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
-          const u32 t = __shfl_sync(ZLES_FULL, tokv, (int)cur);
-          ZLES_EMIT(t);
-          o += (t >> 31) ? ((t >> 16) & 0x1ff) + 3 : 1;
-          cur += nb;
-          if (cur >= 32) break;
+        if (o + sum <= SUB) {
+          // every token of the round starts below SUB (what the reference checks token by token)
+          if (mine) tok[nt + (u32)__popc(plain & lanemask_lt())] = tokv;
+          nt += (u32)__popc(plain);
+          o += sum;
+          if (!last_stops) cur = last + (plast & 0xff);
+          else if (plast & 0x100) {
+            cur = last + (plast & 0xff);
+            eob = true;
+          } else {
+            cur = last;
+            slow = true;
+          }
+        } else {
+          // would pass SUB (not one of our blocks): token by token, to stop exactly where the reference's check does
+          for (;;) {
+            const u32 pk = __shfl_sync(ZLES_FULL, pack, (int)cur);
+            const u32 kb = pk & 0xff;
+            if (kb == 0) { slow = true; break; }
+            if (pk & 0x100) { cur += kb; eob = true; break; }
+            if (o >= SUB) { status = SEG_E_CORRUPT; flags |= SEGF_OVERFLOW; break; }
+            const u32 t = __shfl_sync(ZLES_FULL, tokv, (int)cur);
+            ZLES_EMIT(t);
+            o += (t >> 31) ? ((t >> 16) & 0x1ff) + 3 : 1;
+            cur += kb;
+            if (cur >= 32) break;
+          }
         }
         sr.advance(cur);
         if (slow) {  // one token with a code longer than the root table (or an invalid one), the canonical way
@@ -852,7 +882,6 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
 #undef ZLES_EMIT
   INF_CLK(0);
   INF_CNT(3, nt);
-  if (lane < (nt & 31)) tok[(nt & ~31u) + lane] = mytok;
   if (lane == 0) {
     res->end_pos = end_pos;
     res->out_len = o;

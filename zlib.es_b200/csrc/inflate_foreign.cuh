@@ -302,11 +302,14 @@ struct SymState {
   u16 *base;    // the run's symbols
   u16 *ring;
   u32 o;
+  u32 refs;     // set once a source before the run was seen (a window reference was written)
 };
 
 // Same as res_tokens, on 16-bit symbols; a source position before the run (negative) yields a window reference.
+// RING = entries of the warp's shared-memory mirror (a power of two; a source is read from it when it is still there).
+template <u32 RING = SYM_RING>
 __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__ tok, u32 nt) {
-  constexpr u32 RM = SYM_RING - 1;
+  constexpr u32 RM = RING - 1;
   const u32 lane = lane_id();
   u16 *base = st.base, *ring = st.ring;
   u32 o = st.o;
@@ -344,7 +347,8 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
       m &= m - 1;
       const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
       const int sj = (int)pj - (int)dj;  // may be negative: before the run
-      const bool in_ring = sj >= 0 && o + total - (u32)sj <= SYM_RING;
+      if (sj < 0) st.refs = 1;
+      const bool in_ring = sj >= 0 && o + total - (u32)sj <= RING;
       for (u32 q = lane; q < lj; q += 32) {
         const int s = sj + (int)(dj >= lj ? q : q % dj);
         u16 b;
@@ -360,8 +364,9 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
   st.o = o;
 }
 
+template <u32 RING = SYM_RING>
 __device__ __forceinline__ void sym_bytes(SymState &st, const u8 *__restrict__ srcp, u32 len) {
-  constexpr u32 RM = SYM_RING - 1;
+  constexpr u32 RM = RING - 1;
   for (u32 q = lane_id(); q < len; q += 32) {
     const u16 v = srcp[q];
     st.base[st.o + q] = v;
@@ -382,6 +387,7 @@ k_run_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ cha
   st.base = sym + run_off[r];
   st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SYM_RING;
   st.o = 0;
+  st.refs = 0;
   for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
     const FbChainEnt e = chain[i];
     if (e.stored) sym_bytes(st, in + e.a, e.b);
@@ -416,6 +422,69 @@ __global__ void __launch_bounds__(256) k_sym_finalize(const u16 *__restrict__ sy
       const u16 v = sym[i];
       out[i] = v < SYM_REF ? (u8)v : (prev ? prev[v & 0x7fff] : (u8)0);
     }
+  }
+}
+
+// ---- OUR streams when there are too few 128 KiB chunks to fill the GPU with one warp each (k_inf_resolve): the same
+// two-pass idea at block granularity.  k_seg_sym resolves every 32 KiB block on its own warp into 16-bit symbols, a
+// byte that comes from the previous block of the chunk staying symbolic; k_chunk_final then makes the (up to four)
+// blocks of a chunk concrete in order, each a fully parallel pass over 32 KiB.  Four times the warps of k_inf_resolve.
+constexpr u32 SEG_RING = 4096;  // a small mirror keeps many warps per SM; text batches produce ~200 bytes
+constexpr int SEG_SMEM = (int)(RES_WARPS * SEG_RING * 2);
+__global__ void __launch_bounds__(RES_THREADS)
+k_seg_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg,
+          const u8 *__restrict__ in, const InfRes *__restrict__ res, u16 *sym, u32 *problems) {
+  ZLES_SMEM_DECL(smem_raw);
+  const u32 e = blockIdx.x * RES_WARPS + warp_id();
+  if (e >= nseg) return;
+  const u32 sidx = seg_list ? seg_list[e] : e;
+  const InfRes r = res[sidx];
+  // this kernel also runs optimistically on candidates that k_inf_check will turn down
+  if ((r.status != SEG_SYNC && r.status != SEG_FINAL) || r.out_len > SUB) {
+    if (lane_id() == 0) atomicOr(problems, 1u);
+    return;
+  }
+  SymState st;
+  st.base = sym + (size_t)e * SUB;
+  st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SEG_RING;
+  st.o = 0;
+  st.refs = 0;
+  if (r.flags & SEGF_STORED) {
+    const u64 back = r.out_len + (r.status == SEG_SYNC ? 5 : 0);
+    if (r.end_pos < back) { if (lane_id() == 0) atomicOr(problems, 1u); return; }
+    sym_bytes<SEG_RING>(st, in + (r.end_pos - back), (u32)r.out_len);
+  } else {
+    sym_tokens<SEG_RING>(st, tokens + (size_t)sidx * SUB, umin(ntok[sidx], SUB));  // phase A made sure they stand for out_len <= SUB bytes
+  }
+  // the first block of a chunk has nothing before it: a reference there is not something our encoder writes
+  if (st.refs && (e % SUBS_PER_CHUNK) == 0 && lane_id() == 0) atomicOr(problems, 1u);
+}
+
+constexpr int FIN_THREADS = 512;
+__global__ void __launch_bounds__(FIN_THREADS)
+k_chunk_final(const u16 *__restrict__ sym, const u32 *__restrict__ seg_list, u32 nseg, const InfRes *__restrict__ res, u8 *out, u64 cap,
+              u32 *problems) {
+  const u32 c = blockIdx.x;
+  for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
+    const u32 e = c * SUBS_PER_CHUNK + k;
+    if (e >= nseg) break;
+    const u32 sidx = seg_list ? seg_list[e] : e;
+    const InfRes r = res[sidx];
+    if ((r.status != SEG_SYNC && r.status != SEG_FINAL) || r.out_len > SUB) break;  // flagged by k_seg_sym
+    const u64 off = (u64)e * SUB;
+    u32 len = (u32)r.out_len;
+    if (off + len > cap) {  // output buffer too small
+      if (threadIdx.x == 0) atomicOr(problems, 2u);
+      len = off >= cap ? 0 : (u32)(cap - off);
+    }
+    const u16 *s = sym + (size_t)e * SUB;
+    const u8 *prev = out + off - SUB;  // the previous block of the chunk (only dereferenced when k > 0)
+    u8 *dst = out + off;
+    for (u32 i = threadIdx.x; i < len; i += FIN_THREADS) {
+      const u32 v = s[i];
+      dst[i] = v < SYM_REF ? (u8)v : (k ? prev[v & 0x7fff] : (u8)0);
+    }
+    __syncthreads();  // the next block reads what this one wrote
   }
 }
 

@@ -222,6 +222,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_tokens)");
   e = zrt_set_smem(k_run_resolve, SYM_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_run_resolve)");
+  e = zrt_set_smem(k_seg_sym, SEG_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_seg_sym)");
   e = zrt_set_smem(k_blk_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
@@ -803,6 +805,26 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   return 0;
 }
 
+// Phase B of our own streams: the copies of nseg segments (seg_list, or candidates 0..nseg-1 when null) into d_out;
+// problem bits go to ctl->ok_res.  Many chunks: one warp per 128 KiB chunk (k_inf_resolve).  Few chunks (< 256 MiB of
+// output): one warp per 32 KiB block into 16-bit symbols, then the blocks of each chunk made concrete in order
+// (k_seg_sym + k_chunk_final) — four times as many warps, for 2 bytes per output byte of scratch.
+constexpr u32 SYM_PATH_MAX_CHUNKS = 2048;
+static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8 *d_in, u8 *d_out, size_t cap) {
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  const u32 nchunks = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+  if (nchunks <= SYM_PATH_MAX_CHUNKS && c->fsym.reserve((size_t)nseg * SUB * 2) == 0) {
+    LAUNCH(c, k_seg_sym, (nseg + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
+           (const u32 *)c->ntok.as<u32>(), d_seg_list, nseg, d_in, (const InfRes *)c->res.as<InfRes>(), c->fsym.as<u16>(), &ctl->ok_res);
+    LAUNCH(c, k_chunk_final, nchunks, FIN_THREADS, 0, (const u16 *)c->fsym.as<u16>(), d_seg_list, nseg, (const InfRes *)c->res.as<InfRes>(),
+           d_out, (u64)cap, &ctl->ok_res);
+    return 0;
+  }
+  LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
+         (const u32 *)c->ntok.as<u32>(), d_seg_list, nseg, d_in, (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap, &ctl->ok_res);
+  return 0;
+}
+
 // Steps 2.. of inflate.  On success *out_len = decoded size.  ZLES_E_OUTPUT_FULL: *out_len = size needed.
 static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 ncand_all, u32 cand_cap, u8 *d_out, size_t cap,
                           size_t *out_len, bool has_final = true) {
@@ -820,12 +842,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
            c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
     LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
            (u64)n, has_final ? 1u : 0u, &ctl->ok, &ctl->total);
-    const u32 nchunks = (ncand + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
     const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only
-    if (room)
-      LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
-             (const u32 *)c->ntok.as<u32>(), (const u32 *)nullptr, ncand, d_in, (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap,
-             &ctl->ok_res);
+    if (room) RET(launch_phase_b(c, nullptr, ncand, d_in, d_out, cap));
     CK(zrt_last_error());
     InfCtl h;
     RET(read_ctl(c, &h));
@@ -870,10 +888,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
         CK(zrt_h2d(c->seg_pos.p, list.data(), (size_t)nseg * 4, c->stream));
         CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
         CK(zrt_sync(c->stream));  // list is host heap memory
-        const u32 nch = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
-        LAUNCH(c, k_inf_resolve, (nch + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
-               (const u32 *)c->ntok.as<u32>(), (const u32 *)c->seg_pos.as<u32>(), nseg, d_in, (const InfRes *)c->res.as<InfRes>(), d_out,
-               (u64)cap, &ctl->ok_res);
+        RET(launch_phase_b(c, (const u32 *)c->seg_pos.as<u32>(), nseg, d_in, d_out, cap));
         CK(zrt_last_error());
         RET(read_ctl(c, &h));
         if (h.ok_res == 0) return 0;

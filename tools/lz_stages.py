@@ -57,5 +57,6 @@ if __name__ == "__main__":
     torch.cuda.synchronize()
     L.zles_debug_inf_clocks(io, 0)
     nseg = (n + 32767) // 32768
+    print("  k_inf_tokens4: %d blocks decoded four-way, %d fell back to one warp after trying, %.2f stitch continuations per block" % (io[6], io[7], io[4] / nseg))
     print("  k_inf_tokens per segment: header+tables %.0f cycles, symbol loop %.0f cycles, reader re-seating %.0f cycles; %.0f tokens, %.0f rounds (%.2f tokens/round, %.0f cycles/round), %.1f tokens decoded alone"
           % (io[0] / nseg, io[1] / nseg, io[5] / nseg, io[3] / nseg, io[2] / nseg, io[3] / max(io[2], 1), io[1] / max(io[2], 1), io[4] / nseg))

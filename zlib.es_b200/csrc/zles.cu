@@ -27,6 +27,7 @@
 #include "huffman.cuh"
 #include "inflate.cuh"
 #include "inflate_foreign.cuh"
+#include "inflate_spec.cuh"
 #include "lz77.cuh"
 #include "pack.cuh"
 
@@ -226,6 +227,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_seg_sym)");
   e = zrt_set_smem(k_blk_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
+  e = zrt_set_smem(k_inf_tokens4, SPEC_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens4)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens)");
   e = zrt_set_smem(k_inflate_batch, INF_SMEM);
@@ -810,6 +813,7 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
 // output): one warp per 32 KiB block into 16-bit symbols, then the blocks of each chunk made concrete in order
 // (k_seg_sym + k_chunk_final) — four times as many warps, for 2 bytes per output byte of scratch.
 constexpr u32 SYM_PATH_MAX_CHUNKS = 2048;
+constexpr u32 SPEC_MAX_SEGS = 8192;  // phase A with four warps per block up to 256 MiB of output
 static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8 *d_in, u8 *d_out, size_t cap) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   const u32 nchunks = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
@@ -838,8 +842,15 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
   if (fast) {
     // 2. phase A on every candidate, acceptance check, and — optimistically — phase B with candidate j
     //    taken as block j of the stream (true unless a marker pattern occurs inside compressed data)
-    LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
-           c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+    // few blocks: four warps per block, the quarters decoded speculatively (inflate_spec.cuh); many: one warp per block
+    if (ncand <= SPEC_MAX_SEGS) {
+      const u32 grid = ncand < (u32)c->sm_count * 16 ? ncand : (u32)c->sm_count * 16;
+      LAUNCH(c, k_inf_tokens4, grid, SPEC_THREADS, SPEC_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand, c->tokens.as<u32>(),
+             c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+    } else {
+      LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
+             c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+    }
     LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
            (u64)n, has_final ? 1u : 0u, &ctl->ok, &ctl->total);
     const bool room = (u64)(ncand - 1) * SUB < (u64)cap + 1;  // otherwise the result cannot fit: size query only

@@ -359,14 +359,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       u64 a = 0, bsum = 0;
       const u32 j0 = tid * 32;
       if (j0 < own_len) {
-        const u32 cnt = umin(32u, own_len - j0);
-        u32 sa = 0, sb = 0;
-        for (u32 j = 0; j < cnt; j++) {
-          u32 d = data[hist_len + j0 + j];
-          sa += d;
-          sb += (own_len - j0 - j) * d;
+        // 32 bytes as two 16-byte vectors; bytes past the block's end are zero (the pad) and add nothing.
+        // sum (W - i) d[i] = W * sum d[i] - sum i d[i], the two sums by dp4a
+        const uint4 *v = reinterpret_cast<const uint4 *>(data + hist_len + j0);
+        const u32 W = own_len - j0;
+        u32 sa = 0, si = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint4 x = v[h];
+          sa = __dp4a(x.x, 0x01010101u, sa); sa = __dp4a(x.y, 0x01010101u, sa);
+          sa = __dp4a(x.z, 0x01010101u, sa); sa = __dp4a(x.w, 0x01010101u, sa);
+          const u32 o4 = 0x10101010u * (u32)h;  // byte offsets 16 h + i
+          si = __dp4a(x.x, 0x03020100u + o4, si); si = __dp4a(x.y, 0x07060504u + o4, si);
+          si = __dp4a(x.z, 0x0b0a0908u + o4, si); si = __dp4a(x.w, 0x0f0e0d0cu + o4, si);
         }
-        a = sa; bsum = sb;
+        a = sa; bsum = (u64)W * sa - si;
       }
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {

@@ -266,7 +266,7 @@ def run_ours(args):
     tok_ms += tok4_ms
     tok_n += tok4_n
     res_ms, res_n = c.kernel_time("k_inf_resolve")  # phase B: one of the two forms runs (zles.cu launch_phase_b)
-    sym_ms, _ = c.kernel_time("k_seg_sym")
+    sym_ms, _ = c.kernel_time("k_piece_sym")
     fin_ms, _ = c.kernel_time("k_chunk_final")
     res_ms += sym_ms + fin_ms
     pack_ms, pack_n = c.kernel_time("k_pack")
@@ -338,8 +338,8 @@ def run_ours(args):
                     "how": "zles_deflate + zles_inflate on pinned host buffers, one independent 64 MiB stream per GPU"},
             "gpu_launches": launches_total,
             "kernels_ms_per_step": {"k_lz": round(lz_ms / args.steps, 4), "k_pack": round(pack_ms / args.steps, 4),
-                                    "phase_a(k_inf_tokens|k_inf_tokens4)": round(tok_ms / args.steps, 4), "phase_b(k_inf_resolve|k_seg_sym+k_chunk_final)": round(res_ms / args.steps, 4),
-                                    "k_seg_sym": round(sym_ms / args.steps, 4), "k_chunk_final": round(fin_ms / args.steps, 4)},
+                                    "phase_a(k_inf_tokens|k_inf_tokens4)": round(tok_ms / args.steps, 4), "phase_b(k_inf_resolve|k_piece_sym+k_chunk_final)": round(res_ms / args.steps, 4),
+                                    "k_piece_sym": round(sym_ms / args.steps, 4), "k_chunk_final": round(fin_ms / args.steps, 4)},
             "roofline": {"bound": "hbm", "kernel": "k_lz", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": ncu_traffic(), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo)},

@@ -331,7 +331,17 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
     const u32 total = __shfl_sync(ZLES_FULL, inc, 31);
     if (valid && !isM) { base[pos] = (u16)t; ring[pos & RM] = (u16)t; }
     const bool indep = isM && len < RES_LONG && dist <= pos && pos - dist + len <= o;  // source inside the run, before this batch
-    const u32 later = __ballot_sync(ZLES_FULL, isM && !indep);
+    const bool before = isM && len < RES_LONG && pos + len <= dist;                     // source entirely before the run: no load at all
+    const u32 later = __ballot_sync(ZLES_FULL, isM && !indep && !before);
+    if (__any_sync(ZLES_FULL, before)) {
+      st.refs = 1;
+      if (before) {
+        const u32 w0 = SYM_WIN + pos - dist;  // window offset of the first source byte (dist <= 32768)
+#pragma unroll
+        for (u32 q = 0; q < RES_LONG - 1; q++)
+          if (q < len) { const u16 v = (u16)(SYM_REF | (w0 + q)); base[pos + q] = v; ring[(pos + q) & RM] = v; }
+      }
+    }
     if (indep) {
       const u32 src = pos - dist;
       u16 v[RES_LONG - 1];
@@ -426,65 +436,117 @@ __global__ void __launch_bounds__(256) k_sym_finalize(const u16 *__restrict__ sy
 }
 
 // ---- OUR streams when there are too few 128 KiB chunks to fill the GPU with one warp each (k_inf_resolve): the same
-// two-pass idea at block granularity.  k_seg_sym resolves every 32 KiB block on its own warp into 16-bit symbols, a
-// byte that comes from the previous block of the chunk staying symbolic; k_chunk_final then makes the (up to four)
-// blocks of a chunk concrete in order, each a fully parallel pass over 32 KiB.  Four times the warps of k_inf_resolve.
-constexpr u32 SEG_RING = 4096;  // a small mirror keeps many warps per SM; text batches produce ~200 bytes
+// two-pass idea at a finer grain.  Phase A (k_inf_tokens4) leaves every 32 KiB block as up to four pieces — token
+// count and bytes each, pinfo — and k_piece_sym resolves every piece on its own warp into 16-bit symbols, a byte
+// that comes from before the piece (<= 32 KiB back) staying symbolic; k_chunk_final then makes the pieces of a chunk
+// concrete in order, each a fully parallel pass.  Sixteen times the warps of k_inf_resolve.
+constexpr u32 SEG_RING = 2048;  // a small mirror keeps many warps per SM; text batches produce ~200 bytes
 constexpr int SEG_SMEM = (int)(RES_WARPS * SEG_RING * 2);
+constexpr u32 SEG_PIECES = 4;
+
+// piece p of the segment with result r: its tokens [tok_off, +cnt) and bytes [out_off, +bytes); false = inconsistent
+__device__ __forceinline__ bool seg_piece(const u32 *__restrict__ pinfo, u32 sidx, const InfRes &r, u32 nt, u32 p, u32 &tok_off, u32 &cnt,
+                                          u32 &out_off, u32 &bytes) {
+  tok_off = 0; out_off = 0; cnt = 0; bytes = 0;
+  if (!pinfo) {  // phase A ran one warp per block: the block is one piece
+    if (p == 0) { cnt = umin(nt, SUB); bytes = (u32)r.out_len; }
+    return true;
+  }
+  const u32 *pi = pinfo + (size_t)sidx * 2 * SEG_PIECES;
+  for (u32 k = 0; k < p; k++) { tok_off += pi[2 * k]; out_off += pi[2 * k + 1]; }
+  cnt = pi[2 * p];
+  bytes = pi[2 * p + 1];
+  return tok_off <= SUB && cnt <= SUB - tok_off && out_off <= SUB && bytes <= SUB - out_off && out_off + bytes <= r.out_len;
+}
+
 __global__ void __launch_bounds__(RES_THREADS)
-k_seg_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ seg_list, u32 nseg,
-          const u8 *__restrict__ in, const InfRes *__restrict__ res, u16 *sym, u32 *problems) {
+k_piece_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ pinfo, const u32 *__restrict__ seg_list, u32 nseg,
+            const u8 *__restrict__ in, const InfRes *__restrict__ res, u16 *sym, u8 *out, u64 cap, u32 *problems) {
   ZLES_SMEM_DECL(smem_raw);
-  const u32 e = blockIdx.x * RES_WARPS + warp_id();
+  const u32 g = blockIdx.x * RES_WARPS + warp_id();
+  const u32 e = g / SEG_PIECES, p = g % SEG_PIECES;
   if (e >= nseg) return;
   const u32 sidx = seg_list ? seg_list[e] : e;
   const InfRes r = res[sidx];
   // this kernel also runs optimistically on candidates that k_inf_check will turn down
   if ((r.status != SEG_SYNC && r.status != SEG_FINAL) || r.out_len > SUB) {
-    if (lane_id() == 0) atomicOr(problems, 1u);
+    if (p == 0 && lane_id() == 0) atomicOr(problems, 1u);
     return;
   }
   SymState st;
-  st.base = sym + (size_t)e * SUB;
   st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SEG_RING;
   st.o = 0;
   st.refs = 0;
-  if (r.flags & SEGF_STORED) {
+  if (r.flags & SEGF_STORED) {  // a stored block is concrete already: its payload goes straight to the output, four warps a block
     const u64 back = r.out_len + (r.status == SEG_SYNC ? 5 : 0);
-    if (r.end_pos < back) { if (lane_id() == 0) atomicOr(problems, 1u); return; }
-    sym_bytes<SEG_RING>(st, in + (r.end_pos - back), (u32)r.out_len);
-  } else {
-    sym_tokens<SEG_RING>(st, tokens + (size_t)sidx * SUB, umin(ntok[sidx], SUB));  // phase A made sure they stand for out_len <= SUB bytes
+    if (r.end_pos < back) { if (p == 0 && lane_id() == 0) atomicOr(problems, 1u); return; }
+    const u8 *src = in + (r.end_pos - back);
+    const u64 off = (u64)e * SUB;
+    u32 len = (u32)r.out_len;
+    if (off + len > cap) {
+      if (p == 0 && lane_id() == 0) atomicOr(problems, 2u);
+      len = off >= cap ? 0 : (u32)(cap - off);
+    }
+    for (u32 i = p * 32 + lane_id(); i < len; i += SEG_PIECES * 32) out[off + i] = src[i];
+    return;
   }
-  // the first block of a chunk has nothing before it: a reference there is not something our encoder writes
-  if (st.refs && (e % SUBS_PER_CHUNK) == 0 && lane_id() == 0) atomicOr(problems, 1u);
+  u32 tok_off, cnt, out_off, bytes;
+  if (!seg_piece(pinfo, sidx, r, ntok[sidx], p, tok_off, cnt, out_off, bytes)) {
+    if (lane_id() == 0) atomicOr(problems, 1u);
+    return;
+  }
+  if (cnt == 0) return;
+  st.base = sym + (size_t)e * SUB + out_off;
+  sym_tokens<SEG_RING>(st, tokens + (size_t)sidx * SUB + tok_off, cnt);  // phase A made sure they stand for `bytes` bytes
 }
 
 constexpr int FIN_THREADS = 512;
 __global__ void __launch_bounds__(FIN_THREADS)
-k_chunk_final(const u16 *__restrict__ sym, const u32 *__restrict__ seg_list, u32 nseg, const InfRes *__restrict__ res, u8 *out, u64 cap,
-              u32 *problems) {
+k_chunk_final(const u16 *__restrict__ sym, const u32 *__restrict__ ntok, const u32 *__restrict__ pinfo, const u32 *__restrict__ seg_list, u32 nseg,
+              const InfRes *__restrict__ res, u8 *out, u64 cap, u32 *problems) {
   const u32 c = blockIdx.x;
+  u8 *cbase = out + (u64)c * CHUNK;
   for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
     const u32 e = c * SUBS_PER_CHUNK + k;
     if (e >= nseg) break;
     const u32 sidx = seg_list ? seg_list[e] : e;
     const InfRes r = res[sidx];
-    if ((r.status != SEG_SYNC && r.status != SEG_FINAL) || r.out_len > SUB) break;  // flagged by k_seg_sym
-    const u64 off = (u64)e * SUB;
-    u32 len = (u32)r.out_len;
-    if (off + len > cap) {  // output buffer too small
-      if (threadIdx.x == 0) atomicOr(problems, 2u);
-      len = off >= cap ? 0 : (u32)(cap - off);
+    if ((r.status != SEG_SYNC && r.status != SEG_FINAL) || r.out_len > SUB) break;  // flagged by k_piece_sym
+    if (r.flags & SEGF_STORED) continue;  // written by k_piece_sym (an earlier launch)
+    for (u32 p = 0; p < SEG_PIECES; p++) {
+      u32 tok_off, cnt, out_off, bytes;
+      if (!seg_piece(pinfo, sidx, r, ntok[sidx], p, tok_off, cnt, out_off, bytes)) break;  // flagged by k_piece_sym
+      if (bytes == 0) continue;
+      const u32 pstart = k * SUB + out_off;            // where the piece starts in the chunk
+      const u64 off = (u64)c * CHUNK + pstart;
+      u32 len = bytes;
+      if (off + len > cap) {  // output buffer too small
+        if (threadIdx.x == 0) atomicOr(problems, 2u);
+        len = off >= cap ? 0 : (u32)(cap - off);
+      }
+      const u16 *s = sym + (size_t)e * SUB + out_off;
+      u32 bad = 0;
+      // four independent elements per thread and round: the loads of a round are all in flight together
+      for (u32 i0 = threadIdx.x; i0 < len; i0 += 4 * FIN_THREADS) {
+        u32 v[4];
+        u8 b[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const u32 i = i0 + u * FIN_THREADS; v[u] = i < len ? s[i] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          b[u] = (u8)v[u];
+          if (v[u] >= SYM_REF) {  // byte (v & 0x7fff) of the 32 KiB before the piece
+            const int q = (int)pstart + (int)(v[u] & 0x7fff) - (int)SYM_WIN;
+            if (q < 0) { bad = 1; b[u] = 0; }  // before the chunk: not something our encoder writes
+            else b[u] = cbase[q];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const u32 i = i0 + u * FIN_THREADS; if (i < len) cbase[pstart + i] = b[u]; }
+      }
+      if (bad) atomicOr(problems, 1u);
+      __syncthreads();  // the next piece reads what this one wrote
     }
-    const u16 *s = sym + (size_t)e * SUB;
-    const u8 *prev = out + off - SUB;  // the previous block of the chunk (only dereferenced when k > 0)
-    u8 *dst = out + off;
-    for (u32 i = threadIdx.x; i < len; i += FIN_THREADS) {
-      const u32 v = s[i];
-      dst[i] = v < SYM_REF ? (u8)v : (k ? prev[v & 0x7fff] : (u8)0);
-    }
-    __syncthreads();  // the next block reads what this one wrote
   }
 }
 

@@ -190,8 +190,20 @@ __device__ __forceinline__ void spec_run(const TokWarpSmem *T, const u8 *in, u64
   fin = pos;
 }
 
+// a block decoded by the one-warp decoder is one piece (lane 0 of the warp that decoded it; res/ntok are its own writes)
+__device__ __forceinline__ void spec_qinfo_whole(u32 *qinfo, u32 j, const InfRes *res, const u32 *ntok) {
+  __syncwarp();
+  if (lane_id() == 0) {
+    u32 *qi = qinfo + (size_t)j * 2 * SPEC_WARPS;
+    qi[0] = ntok[j];
+    qi[1] = (u32)umin64(res[j].out_len, 0xffffffffull);
+    for (u32 k = 1; k < SPEC_WARPS; k++) { qi[2 * k] = 0; qi[2 * k + 1] = 0; }
+  }
+}
+
 __global__ void __launch_bounds__(SPEC_THREADS)
-k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res, u32 *counter) {
+k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res, u32 *qinfo,
+              u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);
   SpecShared *Sh = reinterpret_cast<SpecShared *>(smem_raw);
   TokWarpSmem *T = &Sh->T;
@@ -234,7 +246,10 @@ k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos,
     }
     __syncthreads();
     if (Sh->mode == 0) {  // not one dynamic block of a useful size: the one-warp decoder
-      if (w == 0) inf_segment_tokens(T, in, n, in_pos, tok, res + j, ntok + j);
+      if (w == 0) {
+        inf_segment_tokens(T, in, n, in_pos, tok, res + j, ntok + j);
+        spec_qinfo_whole(qinfo, j, res, ntok);
+      }
       continue;
     }
 
@@ -350,12 +365,27 @@ k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos,
           res[j].status = status;
           res[j].flags = 0;
           ntok[j] = total_tok;
+          // the pieces in stream order, for a phase B that gives every piece its own warp (k_piece_sym)
+          u32 *qi = qinfo + (size_t)j * 2 * SPEC_WARPS;
+          u32 slot = 0;
+#pragma unroll
+          for (int k = 0; k < SPEC_WARPS; k++) {
+            if (skip[k] == 0xffffffffu) continue;
+            qi[2 * slot] = cnt[k];
+            qi[2 * slot + 1] = Sh->ob[k] - Sh->skipb[k];
+            slot++;
+          }
+          for (; slot < SPEC_WARPS; slot++) { qi[2 * slot] = 0; qi[2 * slot + 1] = 0; }
         }
       }
     }
     __syncthreads();
     if (Sh->mode == 0) {
-      if (w == 0) { INF_CNT(7, 1); inf_segment_tokens(T, in, n, in_pos, tok, res + j, ntok + j); }
+      if (w == 0) {
+        INF_CNT(7, 1);
+        inf_segment_tokens(T, in, n, in_pos, tok, res + j, ntok + j);
+        spec_qinfo_whole(qinfo, j, res, ntok);
+      }
       continue;
     }
     if (w == 0) INF_CNT(6, 1);

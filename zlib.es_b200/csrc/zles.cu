@@ -107,7 +107,8 @@ struct zles_ctx {
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
-  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain, fsym, fwin;
+  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain, fsym, fwin, pinfo;
+  bool pinfo_valid = false;  // phase A left the blocks as pieces (k_inf_tokens4) for a piece-parallel phase B
   // adler / misc
   DevBuf acc;
   // staging for the host forms
@@ -223,8 +224,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_tokens)");
   e = zrt_set_smem(k_run_resolve, SYM_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_run_resolve)");
-  e = zrt_set_smem(k_seg_sym, SEG_SMEM);
-  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_seg_sym)");
+  e = zrt_set_smem(k_piece_sym, SEG_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_piece_sym)");
   e = zrt_set_smem(k_blk_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
   e = zrt_set_smem(k_inf_tokens4, SPEC_SMEM);
@@ -266,7 +267,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_set_device(c->device);
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
-                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
   timing_collect(c);
@@ -810,18 +811,21 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
 
 // Phase B of our own streams: the copies of nseg segments (seg_list, or candidates 0..nseg-1 when null) into d_out;
 // problem bits go to ctl->ok_res.  Many chunks: one warp per 128 KiB chunk (k_inf_resolve).  Few chunks (< 256 MiB of
-// output): one warp per 32 KiB block into 16-bit symbols, then the blocks of each chunk made concrete in order
-// (k_seg_sym + k_chunk_final) — four times as many warps, for 2 bytes per output byte of scratch.
+// output): one warp per piece of a block (phase A leaves up to four) into 16-bit symbols, then the pieces of each
+// chunk made concrete in order (k_piece_sym + k_chunk_final) — sixteen times as many warps, for 2 bytes of scratch
+// per output byte.
 constexpr u32 SYM_PATH_MAX_CHUNKS = 2048;
 constexpr u32 SPEC_MAX_SEGS = 8192;  // phase A with four warps per block up to 256 MiB of output
 static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8 *d_in, u8 *d_out, size_t cap) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   const u32 nchunks = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
   if (nchunks <= SYM_PATH_MAX_CHUNKS && c->fsym.reserve((size_t)nseg * SUB * 2) == 0) {
-    LAUNCH(c, k_seg_sym, (nseg + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
-           (const u32 *)c->ntok.as<u32>(), d_seg_list, nseg, d_in, (const InfRes *)c->res.as<InfRes>(), c->fsym.as<u16>(), &ctl->ok_res);
-    LAUNCH(c, k_chunk_final, nchunks, FIN_THREADS, 0, (const u16 *)c->fsym.as<u16>(), d_seg_list, nseg, (const InfRes *)c->res.as<InfRes>(),
-           d_out, (u64)cap, &ctl->ok_res);
+    const u32 *pinfo = c->pinfo_valid ? (const u32 *)c->pinfo.as<u32>() : nullptr;
+    const u32 nwarps = nseg * SEG_PIECES;
+    LAUNCH(c, k_piece_sym, (nwarps + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
+           (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, nseg, d_in, (const InfRes *)c->res.as<InfRes>(), c->fsym.as<u16>(), d_out, (u64)cap, &ctl->ok_res);
+    LAUNCH(c, k_chunk_final, nchunks, FIN_THREADS, 0, (const u16 *)c->fsym.as<u16>(), (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, nseg,
+           (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap, &ctl->ok_res);
     return 0;
   }
   LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
@@ -836,7 +840,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
   bool fast = ncand_all >= 1 && ncand_all <= cand_cap;
   const u32 ncand = ncand_all;
   if (fast) {  // workspace for phase A; failing to get it only costs the fast path
-    if (c->tokens.reserve((size_t)ncand * SUB * 4) || c->ntok.reserve((size_t)ncand * 4) || c->res.reserve((size_t)ncand * sizeof(InfRes)))
+    if (c->tokens.reserve((size_t)ncand * SUB * 4) || c->ntok.reserve((size_t)ncand * 4) || c->res.reserve((size_t)ncand * sizeof(InfRes)) ||
+        c->pinfo.reserve((size_t)ncand * 2 * SEG_PIECES * 4))
       fast = false;
   }
   if (fast) {
@@ -846,8 +851,10 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     if (ncand <= SPEC_MAX_SEGS) {
       const u32 grid = ncand < (u32)c->sm_count * 16 ? ncand : (u32)c->sm_count * 16;
       LAUNCH(c, k_inf_tokens4, grid, SPEC_THREADS, SPEC_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand, c->tokens.as<u32>(),
-             c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+             c->ntok.as<u32>(), c->res.as<InfRes>(), c->pinfo.as<u32>(), &ctl->counter);
+      c->pinfo_valid = true;
     } else {
+      c->pinfo_valid = false;
       LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
              c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
     }

@@ -597,41 +597,43 @@ struct TokReader {
   __device__ __forceinline__ bool past_end() const { return bitpos() > (n << 3); }  // consumed bits the buffer does not have
 };
 
-// Reader of the symbol loop of phase A.  The warp holds the next 128 unread bits of the stream, from a word
-// boundary, in four warp-uniform registers; `boff` bits of W0 are consumed.  Lane i looks at the stream at bit
-// offset boff + i, so the 32 lanes decode the tokens that would start at the next 32 bit positions all at once
-// (inf_segment_tokens); the words come from TokReader's 128-byte warp window.
+// Reader of the symbol loop of phase A.  The warp holds 256 bytes of the stream, one word (two) per lane; lane i looks
+// at the stream at bit offset P + i, so the 32 lanes decode the tokens that would start at the next 32 bit positions
+// all at once (inf_segment_tokens, inflate_spec.cuh).
 struct SpecReader : TokReader {
-  u32 W0, W1, W2, W3;
-  u32 boff;
+  u32 P;  // bit offset of the current position from word `wabs` (lane l holds word wabs + l in win, wabs + 32 + l in win_next)
 
   __device__ __forceinline__ void begin(const u8 *in_, u64 n_, u64 bit_pos) {  // bit_pos relative to in_
     in = in_; n = n_;
     skew = (u32)((uintptr_t)in_ & 3);
     words = reinterpret_cast<const u32 *>(in_ - skew);
     const u64 a = bit_pos + ((u64)skew << 3);
-    const u64 w0 = a >> 5;
-    boff = (u32)(a & 31);
-    wabs = w0 & ~(u64)31;
-    wi = (u32)(w0 - wabs);
+    wabs = (a >> 5) & ~(u64)31;
+    P = (u32)(a - (wabs << 5));
     win = load_word(wabs + lane_id());
     win_next = load_word(wabs + 32 + lane_id());
-    W0 = next_word(); W1 = next_word(); W2 = next_word(); W3 = next_word();
   }
-  __device__ __forceinline__ u64 pos() const { return ((wabs + wi - 4) << 5) + boff - ((u64)skew << 3); }
-  __device__ __forceinline__ void advance(u32 c) {  // warp-uniform
-    boff += c;
-    while (boff >= 32) {
-      W0 = W1; W1 = W2; W2 = W3;
-      W3 = next_word();
-      boff -= 32;
+  __device__ __forceinline__ u64 pos() const { return (wabs << 5) + P - ((u64)skew << 3); }
+  __device__ __forceinline__ void advance(u32 c) {  // warp-uniform, c < 1024
+    P += c;
+    if (P >= 1024) {  // the first window is used up: slide (once per 128 bytes of stream)
+      win = win_next;
+      wabs += 32;
+      win_next = load_word(wabs + 32 + lane_id());
+      P -= 1024;
     }
   }
-  // the 64 bits at offset boff + s, s <= 31
+  __device__ __forceinline__ u32 word(u32 idx) const {  // idx warp-uniform, < 64
+    return __shfl_sync(ZLES_FULL, idx < 32 ? win : win_next, (int)(idx & 31));
+  }
+  // the 64 bits at offset P + s, s <= 31: they lie in the four words from P's word on, which every lane gets by
+  // shuffle (no per-round shifting of a register window, no loop)
   __device__ __forceinline__ void at(u32 s, u32 &lo, u32 &hi) const {
-    const u32 t = boff + s;
+    const u32 j0 = P >> 5;
+    const u32 X0 = word(j0), X1 = word(j0 + 1), X2 = word(j0 + 2), X3 = word(j0 + 3);
+    const u32 t = (P & 31) + s;
     const bool up = t >= 32;
-    const u32 a = up ? W1 : W0, b = up ? W2 : W1, c = up ? W3 : W2;
+    const u32 a = up ? X1 : X0, b = up ? X2 : X1, c = up ? X3 : X2;
     lo = __funnelshift_r(a, b, t);  // shift taken modulo 32
     hi = __funnelshift_r(b, c, t);
   }

@@ -46,6 +46,18 @@ def test_deflate_roundtrip(c, name, n):
     P.roundtrip(c, data, check_size=name in ("RAW", "REPEAT", "G3", "G5") or n <= 4096)
 
 
+def test_host_deflate_in_slabs(c):
+    # long enough for the host-buffer deflate to run slab by slab (the emulator has 4 SMs: slabs of 8 blocks): every
+    # slab is laid out, packed and copied out on its own; the stream must equal the device-resident form's
+    data = T.gen("G5", 300000) + T.fixture_raw()[:200000] + bytes(70000) + T.gen("G3", 40000)
+    z = P.roundtrip(c, data, check_size=False, oracle_decode=False)
+    import numpy as np
+    out = np.zeros(len(z) - 1, dtype=np.uint8)  # one byte short: the size query protocol still holds
+    with pytest.raises(Exception) as e:  # ZLES_E_OUTPUT_FULL (the caller's buffer is one byte short)
+        c.deflate_into(data, out)
+    assert getattr(e.value, "code", None) == 16
+
+
 def test_fixture_roundtrip_and_size(c):
     z = P.roundtrip(c, T.fixture_raw())
     assert len(z) <= 1.03 * T.V["fixture"]["oracle_deflate_size"] if "oracle_deflate_size" in T.V["fixture"] else True

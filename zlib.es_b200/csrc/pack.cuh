@@ -86,6 +86,29 @@ __global__ void __launch_bounds__(1024) k_layout(const LayoutParams P) {
 }
 constexpr u32 LAYOUT_SMEM = 256 + 64 * 8;
 
+// Byte offsets of the blocks [b0, b1) continuing from *carry (the end of the previous slab): lets the host-buffer
+// deflate pack and copy out a slab while the matcher works on the next one (zles_deflate).  Single CTA.
+__global__ void __launch_bounds__(1024) k_layout_slab(const u32 *__restrict__ blk_bits, u32 b0, u32 b1, u32 nblocks, u32 last_is_final,
+                                                      u64 *carry_io, u64 *blk_off, u64 *slab_end) {
+  ZLES_SMEM_DECL(smem_raw);
+  u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
+  u64 carry = *carry_io;
+  __syncthreads();  // everybody has read the carry before thread 0 rewrites it
+  for (u32 base = b0; base < b1; base += 1024) {
+    const u32 b = base + threadIdx.x;
+    const u32 bytes = b < b1 ? seg_bytes(blk_bits[b], last_is_final && b + 1 == nblocks) : 0;
+    u32 total;
+    const u32 ex = block_exscan(bytes, scratch, &total);
+    if (b < b1) blk_off[b] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) {
+    blk_off[b1] = carry;
+    *carry_io = carry;
+    *slab_end = carry;
+  }
+}
+
 struct PackParams {
   const u32 *tokens;       // [nblocks][SUB]
   const u32 *ntok;         // [nblocks]
@@ -93,6 +116,7 @@ struct PackParams {
   const u32 *blk_bits;     // [nblocks]
   const u64 *blk_off;      // [nblocks + 1]
   u32 nblocks;
+  u32 first_block = 0;     // this launch packs blocks first_block + blockIdx.x
   u32 last_is_final;
   u8 *out;                 // destination of this shard's first byte (local or peer memory)
   const u8 *in;            // the shard's input (stored blocks copy from it)
@@ -280,7 +304,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(const PackParams P) {
   u32 *stage = reinterpret_cast<u32 *>(smem_raw);
   u32 *ctab = stage + PACK_STAGE_WORDS;  // [320]
   u32 *scratch = ctab + 320;
-  const u32 b = blockIdx.x;
+  const u32 b = P.first_block + blockIdx.x;
   if (b >= P.nblocks) return;
   PackState st;
   pack_begin(st, stage, scratch, P.out + P.blk_off[b]);

@@ -114,6 +114,8 @@ struct zles_ctx {
   // staging for the host forms
   DevBuf d_in, d_out, d_off_in, d_off_out, d_len, d_status;
   HostMail *mail = nullptr;  // pinned
+  u64 *slab_mail = nullptr;  // pinned: where each slab of a pipelined host-buffer deflate ends (bytes)
+  size_t slab_mail_cap = 0;
   CorpusTable *d_corpus = nullptr;
   // per-kernel timing
   bool timing = false;
@@ -270,6 +272,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
                     &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
+  if (c->slab_mail) zrt_host_free(c->slab_mail);
+  c->slab_mail = nullptr;
   timing_collect(c);
   for (zrt_event_t e : c->event_pool) zrt_event_destroy(e);
   if (c->d_corpus) zrt_free(c->d_corpus);
@@ -402,7 +406,18 @@ extern "C" size_t zles_deflate_bound(size_t n) {
 
 // h_src != nullptr: d_in is a staging buffer that is filled from host memory slab by slab on the copy
 // stream while the matcher already works on earlier slabs (blocks are independent per 128 KiB chunk).
-static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info, const u8 *h_src = nullptr) {
+// Host-buffer deflate only: where the packed stream goes (device staging and the caller's buffer).  When the input is
+// long enough to be cut into slabs, every slab is laid out, packed and copied to the host while the matcher works on
+// the next one; `done` says so, `overflow` that the caller's buffer was too small.
+struct DeflatePipe {
+  u8 *d_out;      // device staging for the raw deflate bytes (room for zles_deflate_bound)
+  u8 *h_out;      // caller's buffer for them
+  size_t h_cap;   // its capacity in bytes
+  bool done = false, overflow = false;
+};
+
+static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info, const u8 *h_src = nullptr,
+                          DeflatePipe *pipe = nullptr) {
   c->p1_valid = false;
   if (!is_last && (n % CHUNK) != 0) return ZLES_E_ARG;
   if (!is_last && n == 0) {  // an empty shard in front of the last one contributes nothing
@@ -445,11 +460,39 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.min_checks = c->min_checks;
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
-  // slabs of 2 waves of CTAs (a multiple of the SM count keeps the tail of every launch short), whole chunks
-  u32 slab = h_src ? (2u * (u32)c->sm_count / SUBS_PER_CHUNK) * SUBS_PER_CHUNK : nblocks;
-  if (slab == 0 || nblocks < 2 * slab) slab = nblocks;
-  for (u32 b0 = 0; b0 < nblocks; b0 += slab) {
-    const u32 b1 = b0 + slab < nblocks ? b0 + slab : nblocks;
+  // Host input arrives slab by slab: one wave of CTAs first (the matcher starts as soon as 4.6 MiB are on the device),
+  // then 2, then 4 waves per slab (a multiple of the SM count keeps the tail of every launch short); whole chunks.
+  std::vector<u32> slab_begin;  // first block of every slab, and nblocks at the end
+  {
+    const u32 wave = ((u32)c->sm_count / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+    if (!h_src || wave == 0 || nblocks < 4 * wave) {
+      slab_begin = {0, nblocks};
+    } else {
+      u32 b = 0, sz = wave;
+      while (b < nblocks) {
+        slab_begin.push_back(b);
+        b += sz;
+        if (sz < 4 * wave) sz *= 2;
+      }
+      if (nblocks - slab_begin.back() < wave && slab_begin.size() > 1) slab_begin.pop_back();  // no sliver at the end
+      slab_begin.push_back(nblocks);
+    }
+  }
+  const u32 nslabs = (u32)slab_begin.size() - 1;
+  const bool piped = pipe && h_src && nslabs > 1;
+  std::vector<zrt_event_t> slab_ev;
+  if (piped) {
+    if (c->slab_mail_cap < nslabs) {
+      if (c->slab_mail) zrt_host_free(c->slab_mail);
+      c->slab_mail = nullptr;
+      c->slab_mail_cap = 0;
+      CK(zrt_host_alloc(reinterpret_cast<void **>(&c->slab_mail), (size_t)nslabs * 8));
+      c->slab_mail_cap = nslabs;
+    }
+    CK(zrt_memset(c->summary.p, 0, 64, c->stream));  // summary[4] carries the running offset between slabs
+  }
+  for (u32 si = 0; si < nslabs; si++) {
+    const u32 b0 = slab_begin[si], b1 = slab_begin[si + 1];
     if (h_src) {
       const size_t off = (size_t)b0 * SUB, len = (size_t)umin64((u64)(b1 - b0) * SUB, (u64)n - off);
       if (len) CK(zrt_h2d(const_cast<u8 *>(d_in) + off, h_src + off, len, c->copy_stream));
@@ -463,6 +506,44 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
            c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);
+    if (piped) {  // this slab's offsets, its bits, and where it ends (for the host, which copies it out below)
+      LAUNCH(c, k_layout_slab, 1, 1024, LAYOUT_SMEM, (const u32 *)c->blk_bits.as<u32>(), b0, b1, nblocks, is_last ? 1u : 0u,
+             c->summary.as<u64>() + 4, c->blk_off.as<u64>(), c->summary.as<u64>() + 5);
+      PackParams pp;
+      pp.tokens = c->tokens.as<u32>();
+      pp.ntok = c->ntok.as<u32>();
+      pp.codes = c->codes.as<BlockCodes>();
+      pp.blk_bits = c->blk_bits.as<u32>();
+      pp.blk_off = c->blk_off.as<u64>();
+      pp.nblocks = nblocks;
+      pp.first_block = b0;
+      pp.last_is_final = is_last ? 1u : 0u;
+      pp.out = pipe->d_out;
+      pp.in = d_in;
+      pp.n = n;
+      LAUNCH(c, k_pack, b1 - b0, PACK_THREADS, PACK_SMEM, pp);
+      CK(zrt_d2h(c->slab_mail + si, c->summary.as<u64>() + 5, 8, c->stream));
+      zrt_event_t ev = timing_event(c);
+      CK(zrt_event_record(ev, c->stream));
+      slab_ev.push_back(ev);
+    }
+  }
+  if (piped) {
+    // the GPU works through the slabs in order; as each one's end offset arrives, its bytes go to the caller's buffer
+    u64 prev = 0;
+    for (u32 si = 0; si < nslabs; si++) {
+      CK(zrt_event_sync(slab_ev[si]));
+      const u64 end = c->slab_mail[si];
+      if (end > pipe->h_cap) pipe->overflow = true;
+      if (!pipe->overflow && end > prev) CK(zrt_d2h(pipe->h_out + prev, pipe->d_out + prev, (size_t)(end - prev), c->copy_stream));
+      prev = end;
+      c->event_pool.push_back(slab_ev[si]);
+    }
+    zrt_event_t ev = timing_event(c);
+    CK(zrt_event_record(ev, c->copy_stream));
+    CK(zrt_stream_wait_event(c->stream, ev));
+    c->event_pool.push_back(ev);
+    pipe->done = true;
   }
 
   LayoutParams yp;
@@ -582,13 +663,24 @@ extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *o
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
   zles_shard_info info;
-  RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info, in));  // the host-to-device copy is pipelined with the matcher
+  DeflatePipe pipe;
+  DeflatePipe *pp = nullptr;
+  if (out && cap >= 6 && c->d_out.reserve(zles_deflate_bound(n) + 16) == 0) {  // raw deflate bytes go to out + 2 .. cap - 4
+    pipe.d_out = c->d_out.as<u8>() + 2;
+    pipe.h_out = out + 2;
+    pipe.h_cap = cap - 6;
+    pp = &pipe;
+  }
+  // the host-to-device copy is pipelined with the matcher, and (long inputs) packing and the copy back with it too
+  RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info, in, pp));
   const size_t need = (size_t)info.comp_bytes + 6;
   *out_len = need;
   if (!out || cap < need) return ZLES_E_OUTPUT_FULL;
-  RET(c->d_out.reserve(need + 16));
-  RET(deflate_phase2(c, c->d_out.as<u8>() + 2));
-  CK(zrt_d2h(out + 2, c->d_out.as<u8>() + 2, info.comp_bytes, c->stream));
+  if (!pipe.done || pipe.overflow) {
+    RET(c->d_out.reserve(need + 16));
+    RET(deflate_phase2(c, c->d_out.as<u8>() + 2));
+    CK(zrt_d2h(out + 2, c->d_out.as<u8>() + 2, info.comp_bytes, c->stream));
+  }
   put_zlib_header(out);
   put_be32(out + need - 4, zles_adler32_combine_shards(&info, 1));
   CK(zrt_sync(c->stream));

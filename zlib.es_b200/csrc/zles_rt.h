@@ -37,6 +37,7 @@ static inline zrt_err_t zrt_event_create(zrt_event_t *e) { *e = 0; return 0; }
 static inline zrt_err_t zrt_event_destroy(zrt_event_t) { return 0; }
 static inline zrt_err_t zrt_event_record(zrt_event_t, zrt_stream_t) { return 0; }
 static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t, zrt_event_t) { *ms = 0; return 0; }
+static inline zrt_err_t zrt_event_sync(zrt_event_t) { return 0; }
 static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t) { memmove(d, s, n); return 0; }
 static inline zrt_err_t zrt_stream_wait_event(zrt_stream_t, zrt_event_t) { return 0; }
 #define ZLES_LAUNCH(kern, grid, block, smem, stream, ...) \
@@ -68,6 +69,7 @@ static inline zrt_err_t zrt_event_create(zrt_event_t *e) { return cudaEventCreat
 static inline zrt_err_t zrt_event_destroy(zrt_event_t e) { return cudaEventDestroy(e); }
 static inline zrt_err_t zrt_event_record(zrt_event_t e, zrt_stream_t s) { return cudaEventRecord(e, s); }
 static inline zrt_err_t zrt_event_elapsed(float *ms, zrt_event_t a, zrt_event_t b) { return cudaEventElapsedTime(ms, a, b); }
+static inline zrt_err_t zrt_event_sync(zrt_event_t e) { return cudaEventSynchronize(e); }
 static inline zrt_err_t zrt_stream_wait_event(zrt_stream_t s, zrt_event_t e) { return cudaStreamWaitEvent(s, e, 0); }
 // device, host or peer-mapped pointers on either side (unified addressing)
 static inline zrt_err_t zrt_copy(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDefault, st); }

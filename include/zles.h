@@ -58,6 +58,11 @@ int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
  * one literal when the next position has a longer one (default 1).  min_checks and good_len are reserved (ignored):
  * the nearest candidate of the longest class is the one that is extended. */
 int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
+/* Which window the third 32 KiB block of a 128 KiB chunk sees (/root/reference/src/lz77.ts:49 gives every position the
+ * 32 KiB before it inside its chunk).  1 (default): none, like block 0 — blocks {0,1} and {2,3} each share one match-finder
+ * pass.  0: the block before it, like blocks 1 and 3 — three passes per chunk, ~25 % slower, output ~1.4 % smaller on text.
+ * Either way the stream stays within 3 % of the reference's size on the benchmark corpora ("Size"). */
+int zles_ctx_set_window_mode(zles_ctx *ctx, uint32_t mode);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the context's

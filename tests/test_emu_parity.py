@@ -46,6 +46,17 @@ def test_deflate_roundtrip(c, name, n):
     P.roundtrip(c, data, check_size=name in ("RAW", "REPEAT", "G3", "G5") or n <= 4096)
 
 
+def test_window_modes(c):
+    data = T.fixture_raw()[:150000] + T.gen("G5", 120000)
+    z1 = P.roundtrip(c, data, check_size=False, oracle_decode=False)
+    c.set_window_mode(0)
+    try:
+        z0 = P.roundtrip(c, data, check_size=False, oracle_decode=False)
+    finally:
+        c.set_window_mode(1)
+    assert len(z0) <= len(z1)
+
+
 def test_host_deflate_in_slabs(c):
     # long enough for the host-buffer deflate to run slab by slab (the emulator has 4 SMs: slabs of 8 blocks): every
     # slab is laid out, packed and copied out on its own; the stream must equal the device-resident form's

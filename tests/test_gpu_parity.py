@@ -76,6 +76,19 @@ def test_ragged_lengths(c, n):
     P.roundtrip(c, T.gen("G5", n))
 
 
+def test_window_modes(c):
+    # zles_ctx_set_window_mode: 1 (default) sorts blocks {0,1} and {2,3} of a chunk together; 0 gives block 2 the block
+    # before it as window (three sorts per chunk): smaller or equal output, same decoders, same size bound
+    data = T.fixture_raw() + T.gen("G5", 300000)
+    z1 = P.roundtrip(c, data)
+    c.set_window_mode(0)
+    try:
+        z0 = P.roundtrip(c, data)
+    finally:
+        c.set_window_mode(1)
+    assert len(z0) <= len(z1)
+
+
 def test_long_matches_and_overlaps(c):
     for d in (bytes(300000), b"a" * 70000, b"ab" * 50000, b"abc" * 40000, T.repeat_input() * 40, bytes(range(256)) * 600):
         P.roundtrip(c, d, check_size=False)

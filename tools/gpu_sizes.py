@@ -7,6 +7,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import torch, zles
 import vectors as T
 c = zles.Codec(0)
+if len(sys.argv) > 1:
+    c.set_window_mode(int(sys.argv[1]))
 oracle8 = {"text": 3405877, "binary": 2629584, "random": 8397052, "mixed": 3342227}
 n = 8 << 20
 for kind, label in [(0, "text"), (1, "binary"), (2, "random"), (3, "mixed")]:

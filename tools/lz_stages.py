@@ -1,6 +1,6 @@
 """Per-stage cycle breakdown of k_lz (profiling build, -DZLES_STAGE_CLOCKS; not the product library).
 
-usage: python tools/lz_stages.py [kind=0 text|1 binary|2 random|3 mixed] [MiB=64] [scan deep]
+usage: python tools/lz_stages.py [kind=0 text|1 binary|2 random|3 mixed] [MiB=64] [scan deep [window_mode]]
 Builds build/libzles_prof.so on first use (here, before gpurun), then runs one warm deflate and prints the
 share of each stage in thread 0's cycles summed over all CTAs.
 """
@@ -32,6 +32,8 @@ if __name__ == "__main__":
     n = (int(sys.argv[2]) if len(sys.argv) > 2 else 64) << 20
     if len(sys.argv) > 4:  # search level: scan width, extensions
         c.set_level(int(sys.argv[3]), int(sys.argv[4]), 8, True)
+    if len(sys.argv) > 5:  # window mode (zles_ctx_set_window_mode)
+        c.set_window_mode(int(sys.argv[5]))
     src = torch.empty(n, dtype=torch.uint8, device="cuda"); c.dev_corpus(kind, 0, src.data_ptr(), n)
     cap = c.deflate_bound(n); comp = torch.empty(cap, dtype=torch.uint8, device="cuda")
     c.dev_deflate(src.data_ptr(), n, comp.data_ptr(), cap)
@@ -42,7 +44,7 @@ if __name__ == "__main__":
     torch.cuda.synchronize()
     L.zles_debug_lz_clocks(out, 0)
     tot = sum(out[:12])
-    print("kind", kind, "MiB", n >> 20, "level", sys.argv[3:5], "comp", clen, "ratio %.4f" % (n / clen), "cycles per 32 KiB block: %.0f" % (tot / (n / 32768)))
+    print("kind", kind, "MiB", n >> 20, "level", sys.argv[3:6], "comp", clen, "ratio %.4f" % (n / clen), "cycles per 32 KiB block: %.0f" % (tot / (n / 32768)))
     for i, nm in enumerate(NAMES):
         print("  %-16s %6.2f %%   %8.0f cycles/block" % (nm, 100.0 * out[i] / tot, out[i] / (n / 32768)))
     w = sum(out[12:15]) or 1

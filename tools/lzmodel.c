@@ -62,7 +62,7 @@ int main(int argc, char **argv) {
   for (long cs = 0; cs < n; cs += CHUNK) {
     long ce = cs + CHUNK < n ? cs + CHUNK : n; memset(cfl, 0, sizeof cfl); memset(cfd, 0, sizeof cfd); chunk_sep_bits = 0;
     for (long bs = cs; bs < ce; bs += SUB) {
-      uint32_t own = (uint32_t)((bs + SUB < ce ? bs + SUB : ce) - bs), hist = bs > cs ? SUB : 0, L = hist + own;
+      uint32_t own = (uint32_t)((bs + SUB < ce ? bs + SUB : ce) - bs), hist = (getenv("PAIRS") ? (((bs - cs) / SUB) & 1) : (bs > cs)) ? SUB : 0, L = hist + own;
       const uint8_t *b = d + bs - hist; uint32_t N = L >= 3 ? L - 2 : 0;
       for (uint32_t p = 0; p < N; p++) { uint32_t k = key3(b, p); srt[p] = ((uint64_t)(exact ? k : hash16(k)) << 32) | p; }
       qsort(srt, N, 8, cmp_u64); for (uint32_t i = 0; i < N; i++) X[i] = (uint32_t)srt[i];

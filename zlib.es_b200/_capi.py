@@ -35,6 +35,7 @@ PROTOTYPES = {
     "zles_ctx_destroy": (None, [c_vp]),
     "zles_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "zles_ctx_set_level": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
+    "zles_ctx_set_window_mode": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
     "zles_ctx_launches": (ctypes.c_uint64, [c_vp]),
     "zles_ctx_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "zles_ctx_kernel_time": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),

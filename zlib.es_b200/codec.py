@@ -71,6 +71,10 @@ class Codec:
             msg += ": " + self.L.zles_last_cuda_error().decode()
         raise ZlesError(rc, msg)
 
+    def set_window_mode(self, mode: int):
+        """0: every block but a chunk's first sees the 32 KiB before it; 1: a chunk's third block sees none (faster)."""
+        self._check(self.L.zles_ctx_set_window_mode(self.h, mode))
+
     def set_level(self, max_checks: int, min_checks: int, good_len: int, lazy: bool = True):
         self._check(self.L.zles_ctx_set_level(self.h, max_checks, min_checks, good_len, 1 if lazy else 0))
 

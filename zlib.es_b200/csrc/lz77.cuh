@@ -74,6 +74,9 @@ struct LzParams {
   u32 min_checks;     // reserved (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
   u32 good_len;       // reserved (reference: FAST_REPEAT_LENGTH = 8, src/lz77.ts:9)
   u32 lazy;           // 1: defer a match by one literal when the next position has a longer one
+  u32 *unit_ctr = nullptr;  // zeroed before the launch: units are handed out from it, the two-block ones first
+  u32 pair_mode = 1;  // 1: two sorts per chunk — blocks {0,1} and {2,3}: block 2 has no window (the default);
+                      // 0: three — {0,1}, then {2} and {3} each with the block before as window (smaller output, slower)
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
 };
 
@@ -335,16 +338,41 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u32 *Y = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // sort pass buffer, 2 * SUB entries
   u32 *R = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // then the match results, SUB entries
 
-  for (u32 b = P.first_block + blockIdx.x; b < P.nblocks; b += gridDim.x) {
-    u64 own_off = (u64)b * SUB;
-    u32 own_len, hist_len;
+  // A unit of work is one sort: up to 64 KiB in shared memory = [window | own blocks].  The first two blocks of a
+  // chunk share one sort (block 0 has no window, block 1's window is block 0: one sorted array serves both); blocks
+  // 2 and 3 each take a sort with the block before as window (pair_mode 0), or share one without window for block 2
+  // (pair_mode 1).  Batch mode: one block per unit, as its table entry says.
+  const u32 upc = P.table ? 1u : (P.pair_mode ? 2u : 3u);  // units per chunk
+  const u32 c_begin = P.first_block / SUBS_PER_CHUNK, c_end = (P.nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+  const u32 nunits = P.table ? P.nblocks - P.first_block : (c_end - c_begin) * upc;
+  for (;;) {
+    // units come from a counter (their cost differs: two blocks or one); all two-block units are handed out first
+    __syncthreads();
+    if (tid == 0) *slice_ctr = atomicAdd(P.unit_ctr, 1u);
+    __syncthreads();
+    const u32 ui = *slice_ctr;
+    if (ui >= nunits) break;
+    u32 v;  // table mode: the block; otherwise chunk * upc + unit within the chunk
+    if (P.table) v = P.first_block + ui;
+    else if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
+    else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
+    u64 own_off;
+    u32 own_len, hist_len, bfirst;
     if (P.table) {
-      const BatchBlk t = P.table[b];
-      own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len;
+      const BatchBlk t = P.table[v];
+      own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len; bfirst = v;
     } else {
-      own_len = (u32)umin64((u64)SUB, P.n - own_off);
-      hist_len = (b % SUBS_PER_CHUNK) ? SUB : 0;  // window = previous SUB of the same chunk
+      const u32 chunk = v / upc, k = v % upc;
+      u32 sb0, nsb;
+      if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
+      else if (P.pair_mode) { sb0 = 2; nsb = 2; hist_len = 0; }
+      else { sb0 = k + 1; nsb = 1; hist_len = SUB; }  // window = previous SUB of the same chunk
+      bfirst = chunk * SUBS_PER_CHUNK + sb0;
+      if (bfirst >= P.nblocks) continue;  // the stream's last chunk is short (uniform over the CTA)
+      own_off = (u64)bfirst * SUB;
+      own_len = (u32)umin64((u64)nsb * SUB, P.n - own_off);
     }
+    const u32 nsub = own_len > SUB ? 2u : 1u;  // deflate blocks in this unit
     const u32 L = hist_len + own_len;
 
     LZ_CLK(scratch, -1);
@@ -354,19 +382,20 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     __syncthreads();
     LZ_CLK(scratch, 0);
 
-    // S1: Adler-32 partial sums of the block's own bytes (K8 fused into the load)
-    {
+    // S1: Adler-32 partial sums of every own block (K8 fused into the load)
+    for (u32 sbi = 0; sbi < nsub; sbi++) {
+      const u32 sbase = sbi * SUB, slen = umin(SUB, own_len - sbase);
       u64 a = 0, bsum = 0;
       const u32 j0 = tid * 32;
-      if (j0 < own_len) {
-        // 32 bytes as two 16-byte vectors; bytes past the block's end are zero (the pad) and add nothing.
-        // sum (W - i) d[i] = W * sum d[i] - sum i d[i], the two sums by dp4a
-        const uint4 *v = reinterpret_cast<const uint4 *>(data + hist_len + j0);
-        const u32 W = own_len - j0;
+      if (j0 < slen) {
+        // 32 bytes as two 16-byte vectors; bytes past the unit's end are zero (the pad) and add nothing (a block that
+        // is not the unit's last is full).  sum (W - i) d[i] = W * sum d[i] - sum i d[i], the two sums by dp4a
+        const uint4 *v4 = reinterpret_cast<const uint4 *>(data + hist_len + sbase + j0);
+        const u32 W = slen - j0;
         u32 sa = 0, si = 0;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const uint4 x = v[h];
+          const uint4 x = v4[h];
           sa = __dp4a(x.x, 0x01010101u, sa); sa = __dp4a(x.y, 0x01010101u, sa);
           sa = __dp4a(x.z, 0x01010101u, sa); sa = __dp4a(x.w, 0x01010101u, sa);
           const u32 o4 = 0x10101010u * (u32)h;  // byte offsets 16 h + i
@@ -386,11 +415,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         *slice_ctr = 0;  // consumed in S3, several barriers from here
         u64 ta = 0, tb = 0;
         for (int i = 0; i < LZ_WARPS; i++) { ta += red[i]; tb += red[LZ_WARPS + i]; }
-        P.adler_part[2 * (size_t)b] = ta;
-        P.adler_part[2 * (size_t)b + 1] = tb;
+        P.adler_part[2 * (size_t)(bfirst + sbi)] = ta;
+        P.adler_part[2 * (size_t)(bfirst + sbi) + 1] = tb;
       }
-      LZ_CLK(scratch, 1);
+      __syncthreads();  // red is reused by the next block
     }
+    LZ_CLK(scratch, 1);
 
     // S2: stable radix sort of positions by hash16(key3)
     const u32 N = L >= 3 ? L - 2 : 0;
@@ -494,7 +524,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         const bool hit = own && best >= 0x80u;
         if (__any_sync(ZLES_FULL, hit)) {
           const u32 c = hit ? (u32)X[k - (64 - (best & 0x7fu))] : p;
-          const u32 maxlen = umin(MAX_MATCH, L - p);
+          // a match ends with its deflate block: the unit's first block ends at hist_len + SUB
+          const u32 bend = (nsub == 2 && p < SUB) ? SUB : L;
+          const u32 maxlen = umin(MAX_MATCH, bend - p);
           u32 len = 2u + (u32)__popc(best & 0x80808080u);
           if (__any_sync(ZLES_FULL, hit && len == 6)) {
             const u64 x = lz_ld64(data, p + 6) ^ lz_ld64(data, c + 6);
@@ -521,8 +553,13 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     __syncthreads();
     LZ_CLK(scratch, 8);
 
+    // S4/S5 once per deflate block of the unit (the match results stay in the scratch; XR takes one block's at a time)
+    const u32 unit_own = own_len;
+    for (u32 sbi = 0; sbi < nsub; sbi++) {
+    const u32 sbase = sbi * SUB, bcur = bfirst + sbi, dbase = hist_len + sbase;
+    const u32 own_len = umin(SUB, unit_own - sbase);  // this block's bytes (shadows the unit's)
     // S4: match results into shared memory (over the sorted array), then the parse
-    for (u32 i = tid; i < own_len; i += LZ_THREADS) XR[i] = R[i];
+    for (u32 i = tid; i < own_len; i += LZ_THREADS) XR[i] = R[sbase + i];
     bm[tid] = 0;
     for (u32 i = tid; i < LZ_HCOPIES * LZ_NSYM; i += LZ_THREADS) hcopies[i] = 0;
     __syncthreads();
@@ -578,7 +615,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       u32 word = bm[tid];
       u32 total;
       u32 o = block_exscan((u32)__popc(word), scratch, &total);
-      u32 *tok = P.tokens + (size_t)b * SUB;
+      u32 *tok = P.tokens + (size_t)bcur * SUB;
       u32 *hc = hcopies + (w % LZ_HCOPIES) * LZ_NSYM;
       while (word) {
         const u32 bit = (u32)(__ffs((int)word) - 1);
@@ -594,7 +631,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
           atomicAdd(hc + 288 + ds, 1u);
           tok[o] = tok_match(len, dist);
         } else {
-          const u32 d = data[hist_len + pos];
+          const u32 d = data[dbase + pos];
           atomicAdd(hc + d, 1u);
           tok[o] = d;
         }
@@ -604,10 +641,12 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       if (tid < LZ_NSYM) {
         u32 s = 0;
         for (u32 c = 0; c < LZ_HCOPIES; c++) s += hcopies[c * LZ_NSYM + tid];
-        P.hist[(size_t)b * LZ_NSYM + tid] = s;
+        P.hist[(size_t)bcur * LZ_NSYM + tid] = s;
       }
-      if (tid == 0) P.ntok[b] = total;
+      if (tid == 0) P.ntok[bcur] = total;
     }
+    __syncthreads();
+    }  // blocks of the unit
     __syncthreads();
     LZ_CLK(scratch, 11);
   }

@@ -337,8 +337,10 @@ __global__ void __launch_bounds__(1024) k_batch_count(const u64 *__restrict__ in
   if (threadIdx.x == 0) blk_first[count] = carry;
 }
 
+// pair_mode: the window policy of LzParams (1: a chunk's third block has no window), so that a buffer of a batch
+// compresses to the same bytes as on its own
 __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_off, u32 count, const u64 *__restrict__ blk_first,
-                                                     BatchBlk *table) {
+                                                     BatchBlk *table, u32 pair_mode) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const u64 beg = in_off[i], len = in_off[i + 1] - beg;
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_
     BatchBlk t;
     t.in_off = beg + k * SUB;
     t.own_len = (u32)umin64((u64)SUB, len - k * SUB);
-    t.hist_len = (k % SUBS_PER_CHUNK) ? SUB : 0;
+    const u32 kc = (u32)(k % SUBS_PER_CHUNK);
+    t.hist_len = (kc == 0 || (pair_mode && kc == 2)) ? 0 : SUB;
     table[b0 + k] = t;
   }
 }

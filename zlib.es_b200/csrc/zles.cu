@@ -104,6 +104,8 @@ struct zles_ctx {
   uint64_t launches = 0;
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
+  u32 pair_mode = 1;  // zles_ctx_set_window_mode
+  DevBuf unit_ctr;    // k_lz hands its units out from this counter
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
@@ -269,7 +271,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_set_device(c->device);
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
-                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo, &c->unit_ctr,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
   for (DevBuf *b : bufs) b->release();
   if (c->slab_mail) zrt_host_free(c->slab_mail);
@@ -298,6 +300,12 @@ extern "C" int zles_ctx_set_level(zles_ctx *c, uint32_t max_checks, uint32_t min
   c->min_checks = min_checks ? min_checks : 1;
   c->good_len = good_len;
   c->lazy = lazy ? 1 : 0;
+  return 0;
+}
+
+extern "C" int zles_ctx_set_window_mode(zles_ctx *c, uint32_t mode) {
+  if (!c || mode > 1) return ZLES_E_ARG;
+  c->pair_mode = mode;
   return 0;
 }
 
@@ -460,6 +468,9 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.min_checks = c->min_checks;
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
+  lp.pair_mode = c->pair_mode;
+  RET(c->unit_ctr.reserve(4));
+  lp.unit_ctr = c->unit_ctr.as<u32>();
   // Host input arrives slab by slab: one wave of CTAs first (the matcher starts as soon as 4.6 MiB are on the device),
   // then 2, then 4 waves per slab (a multiple of the SM count keeps the tail of every launch short); whole chunks.
   std::vector<u32> slab_begin;  // first block of every slab, and nblocks at the end
@@ -503,6 +514,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     }
     lp.first_block = b0;
     lp.nblocks = b1;
+    CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
            c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);
@@ -1238,7 +1250,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   RET(c->codes.reserve((size_t)nblocks * sizeof(BlockCodes)));
   RET(c->blk_bits.reserve((size_t)nblocks * 4));
   c->p1_valid = false;
-  LAUNCH(c, k_batch_table, (count + 255) / 256, 256, 0, d_in_off, count, (const u64 *)d_blk_first, d_tab);
+  LAUNCH(c, k_batch_table, (count + 255) / 256, 256, 0, d_in_off, count, (const u64 *)d_blk_first, d_tab, c->pair_mode);
 
   LzParams lp;
   lp.in = d_in;
@@ -1254,6 +1266,9 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
   lp.table = d_tab;
+  RET(c->unit_ctr.reserve(4));
+  lp.unit_ctr = c->unit_ctr.as<u32>();
+  CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
   LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
   LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), 0u, nblocks,
          c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)0, (const BatchBlk *)d_tab);

@@ -44,8 +44,8 @@ namespace zles {
 constexpr int LZ_THREADS = 1024;
 constexpr int LZ_WARPS = LZ_THREADS / 32;
 constexpr u32 LZ_PAD = 320;
-constexpr u32 LZ_NWALK = 128;
-constexpr u32 LZ_RANGE = SUB / LZ_NWALK;  // 256 positions per speculative walker
+constexpr u32 LZ_NWALK = 256;
+constexpr u32 LZ_RANGE = SUB / LZ_NWALK;  // 128 positions per speculative walker
 constexpr u32 LZ_HCOPIES = 8;
 constexpr u32 LZ_NSYM = 320;  // [0,288) literal/length symbols, [288,320) distance symbols
 
@@ -559,7 +559,18 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     const u32 sbase = sbi * SUB, bcur = bfirst + sbi, dbase = hist_len + sbase;
     const u32 own_len = umin(SUB, unit_own - sbase);  // this block's bytes (shadows the unit's)
     // S4: match results into shared memory (over the sorted array), then the parse
-    for (u32 i = tid; i < own_len; i += LZ_THREADS) XR[i] = R[sbase + i];
+    {  // 16 bytes per load: the copy is bound by the round trips to L2, not by their width
+      const uint4 *src4 = reinterpret_cast<const uint4 *>(R + sbase);
+      uint4 *dst4 = reinterpret_cast<uint4 *>(XR);
+      const u32 n4 = (own_len + 3) >> 2;  // R has room for 2 * SUB entries: reading up to 3 entries past own_len is harmless
+      for (u32 i0 = 0; i0 < n4; i0 += 8 * LZ_THREADS) {  // eight loads in flight per thread, then the stores
+        uint4 v8[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const u32 i = i0 + u * LZ_THREADS + tid; if (i < n4) v8[u] = __ldcg(src4 + i); }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const u32 i = i0 + u * LZ_THREADS + tid; if (i < n4) dst4[i] = v8[u]; }
+      }
+    }
     bm[tid] = 0;
     for (u32 i = tid; i < LZ_HCOPIES * LZ_NSYM; i += LZ_THREADS) hcopies[i] = 0;
     __syncthreads();

@@ -75,6 +75,10 @@ int zles_ctx_kernel_time(zles_ctx *ctx, const char *kernel, double *ms_total, ui
 int zles_dev_alloc(zles_ctx *ctx, size_t n, void **d_ptr);
 int zles_dev_free(zles_ctx *ctx, void *d_ptr);
 int zles_dev_copy(zles_ctx *ctx, void *dst, const void *src, size_t n);
+/* The same without waiting: the copy is ordered on the context's stream; a host-side source must be pinned and stay
+ * untouched until the stream has been synchronised (zles_ctx_sync or any synchronising call). */
+int zles_dev_copy_async(zles_ctx *ctx, void *dst, const void *src, size_t n);
+int zles_ctx_sync(zles_ctx *ctx);
 
 /* ---- the drop-in pair: host buffers in, host buffers out ----------------------
  * zles_deflate   replaces zlib.deflate  (/root/reference/src/zlib.ts:25-49)

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "zles_dev_alloc": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
     "zles_dev_free": (ctypes.c_int, [c_vp, c_vp]),
     "zles_dev_copy": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
+    "zles_dev_copy_async": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t]),
+    "zles_ctx_sync": (ctypes.c_int, [c_vp]),
     "zles_deflate_bound": (ctypes.c_size_t, [ctypes.c_size_t]),
     "zles_deflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
     "zles_inflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),

@@ -50,6 +50,7 @@ class Codec:
         self._check(self.L.zles_ctx_create(device, ctypes.byref(h)))
         self.h = h
         self.device = device
+        self.stream_ptr = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -80,6 +81,10 @@ class Codec:
 
     def set_stream(self, cuda_stream: int):
         self._check(self.L.zles_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
+        self.stream_ptr = cuda_stream  # the caller's stream the codec's kernels are ordered on (None: its own)
+
+    def sync(self):
+        self._check(self.L.zles_ctx_sync(self.h))
 
     @property
     def launches(self) -> int:
@@ -105,6 +110,10 @@ class Codec:
 
     def dev_copy(self, dst: int, src: int, n: int):
         self._check(self.L.zles_dev_copy(self.h, ctypes.c_void_p(dst), ctypes.c_void_p(src), n))
+
+    def dev_copy_async(self, dst: int, src: int, n: int):
+        """Ordered on the codec's stream, not waited for (a host source must be pinned and stay alive)."""
+        self._check(self.L.zles_dev_copy_async(self.h, ctypes.c_void_p(dst), ctypes.c_void_p(src), n))
 
     def ipc_export(self, ptr: int) -> bytes:
         buf = (ctypes.c_uint8 * 64)()

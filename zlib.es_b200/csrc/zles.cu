@@ -350,6 +350,19 @@ extern "C" int zles_dev_copy(zles_ctx *c, void *dst, const void *src, size_t n) 
   return 0;
 }
 
+extern "C" int zles_dev_copy_async(zles_ctx *c, void *dst, const void *src, size_t n) {
+  if ((!dst || !src) && n) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  if (n) CK(zrt_copy(dst, src, n, c->stream));
+  return 0;
+}
+
+extern "C" int zles_ctx_sync(zles_ctx *c) {
+  RET(resolve_ctx(c));
+  CK(zrt_sync(c->stream));
+  return 0;
+}
+
 static std::mutex g_default_mu;
 static zles_ctx *g_default_ctx = nullptr;
 

@@ -18,6 +18,7 @@ The transport that turns "a buffer on rank 0" into a pointer usable by every ran
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from dataclasses import dataclass
 
@@ -90,6 +91,31 @@ class ShardedCodec:
         self.comm_device = torch.device(comm_device)
         self.capacity = 0
         self.layout: ShardLayout | None = None
+        cuda = self.comm_device.type == "cuda"
+        # persistent exchange buffers: pinned on the host side, so that nothing but the one read-back waits
+        self._h_mine = torch.empty(5, dtype=torch.int64, pin_memory=cuda)
+        self._h_all = torch.empty(self.world * 5, dtype=torch.int64, pin_memory=cuda)
+        self._d_mine = torch.empty(5, dtype=torch.int64, device=self.comm_device)
+        self._d_all = torch.empty(self.world * 5, dtype=torch.int64, device=self.comm_device)
+        self._d_flag = torch.zeros(1, dtype=torch.int32, device=self.comm_device)
+        self._frame = torch.empty(8, dtype=torch.uint8, pin_memory=cuda)
+
+    def _ordered(self):
+        """Collectives issued inside this context are ordered on the codec's stream (when it runs on a caller's CUDA
+        stream): no host synchronisation is needed between the codec's kernels and the exchange."""
+        if self.comm_device.type == "cuda" and getattr(self.c, "stream_ptr", None):
+            return torch.cuda.stream(torch.cuda.ExternalStream(self.c.stream_ptr, device=self.comm_device))
+        return contextlib.nullcontext()
+
+    def _rendezvous(self):
+        """Every rank's work issued so far on the codec's stream is complete before anything issued after this, on any
+        rank (what the packer's peer stores need before the stream is read)."""
+        if self.comm_device.type == "cuda" and getattr(self.c, "stream_ptr", None):
+            with self._ordered():
+                dist.all_reduce(self._d_flag, group=self.group)  # stream-ordered: nobody's stream passes before everybody's arrives
+        else:
+            self.c.sync()
+            dist.barrier(group=self.group)
 
     # -- destination buffer -----------------------------------------------------------------
     def setup(self, capacity: int):
@@ -116,11 +142,15 @@ class ShardedCodec:
         """All ranks call this with their shard (device pointer).  Afterwards the zlib stream lies at
         ``self.t.base`` on rank 0 (``layout.total_comp`` bytes)."""
         info = self.c.dev_deflate_phase1(d_in, n_local, self.rank == self.world - 1)
-        mine = torch.tensor([info.comp_bytes, info.raw_bytes, info.adler_a, info.adler_b, info.n_blocks], dtype=torch.int64,
-                            device=self.comm_device)
-        allv = torch.empty(self.world * 5, dtype=torch.int64, device=self.comm_device)
-        dist.all_gather_into_tensor(allv, mine, group=self.group)  # the one exchange step of the path
-        rows = allv.cpu().view(self.world, 5).tolist()
+        self._h_mine[0], self._h_mine[1], self._h_mine[2], self._h_mine[3], self._h_mine[4] = (
+            info.comp_bytes, info.raw_bytes, info.adler_a, info.adler_b, info.n_blocks)
+        with self._ordered():
+            self._d_mine.copy_(self._h_mine, non_blocking=True)
+            dist.all_gather_into_tensor(self._d_all, self._d_mine, group=self.group)  # the one exchange step of the path
+            self._h_all.copy_(self._d_all, non_blocking=True)
+            if self.comm_device.type == "cuda":
+                torch.cuda.current_stream(self.comm_device).synchronize()
+        rows = self._h_all.view(self.world, 5).tolist()
         infos = []
         offsets, comp, raw = [], [], []
         off = 0
@@ -139,11 +169,11 @@ class ShardedCodec:
         # phase 2: the packer stores this shard's blocks at their global offset — local memory on rank 0,
         # peer-mapped memory (NVLink) elsewhere
         self.c.dev_deflate_phase2(self.t.base + 2 + offsets[self.rank])
-        dist.barrier(group=self.group)
         if self.rank == 0:  # framing stays on the host (/root/reference/src/zlib.ts:28-46)
-            frame = np.array([0x78, 0x9C, (adler >> 24) & 255, (adler >> 16) & 255, (adler >> 8) & 255, adler & 255], dtype=np.uint8)
-            self.c.dev_copy(self.t.base, frame.ctypes.data, 2)
-            self.c.dev_copy(self.t.base + total - 4, frame.ctypes.data + 2, 4)
+            self._frame[:6] = torch.tensor([0x78, 0x9C, (adler >> 24) & 255, (adler >> 16) & 255, (adler >> 8) & 255, adler & 255], dtype=torch.uint8)
+            self.c.dev_copy_async(self.t.base, self._frame.data_ptr(), 2)
+            self.c.dev_copy_async(self.t.base + total - 4, self._frame.data_ptr() + 2, 4)
+        self._rendezvous()
         self.layout = ShardLayout(offsets, comp, raw, total, adler)
         return self.layout
 
@@ -153,5 +183,5 @@ class ShardedCodec:
         least layout.comp[rank] bytes.  Returns the decoded length."""
         lay = layout or self.layout
         n = lay.comp[self.rank]
-        self.c.dev_copy(d_stage, self.t.base + 2 + lay.offsets[self.rank], n)  # peer read of this shard's bytes
+        self.c.dev_copy_async(d_stage, self.t.base + 2 + lay.offsets[self.rank], n)  # peer read of this shard's bytes
         return self.c.dev_inflate_segment(d_stage, n, d_out, cap, has_final=self.rank == self.world - 1)

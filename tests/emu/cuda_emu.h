@@ -134,6 +134,7 @@ static inline int __syncthreads_or(int pred) {
   emu::block_barrier();
   return r;
 }
+static inline int __syncthreads_and(int pred) { return !__syncthreads_or(!pred); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   uint64_t o[32];
   emu::warp_exchange(mask, 0, o);

@@ -76,6 +76,22 @@ def test_ragged_lengths(c, n):
     P.roundtrip(c, T.gen("G5", n))
 
 
+def test_batch_of_small_buffers_shares_sorts(c):
+    # groups of 16 consecutive buffers of at most 4 KiB each share one pass of the match finder (BASELINE configs[2]):
+    # every buffer must still compress to exactly the bytes it gets on its own, ragged and empty ones included
+    rng = np.random.default_rng(7)
+    lens = [4096] * 16 + [0, 1, 2, 3, 15, 16, 17, 100, 1000, 4095, 4096, 33, 2048, 7, 4000, 64] + [int(x) for x in rng.integers(0, 4097, size=85)]
+    src = T.fixture_raw() + T.gen("G5", 200000)
+    bufs, o = [], 0
+    for n in lens:
+        bufs.append(src[o:o + n]); o = (o + n + 37) % (len(src) - 5000)
+    zs = c.deflate_batch(bufs)
+    for b, z in zip(bufs, zs):
+        assert zlib.decompress(z) == b
+        assert z == c.deflate(b)
+    assert c.inflate_batch(zs) == bufs
+
+
 def test_window_modes(c):
     # zles_ctx_set_window_mode: 1 (default) sorts blocks {0,1} and {2,3} of a chunk together; 0 gives block 2 the block
     # before it as window (three sorts per chunk): smaller or equal output, same decoders, same size bound

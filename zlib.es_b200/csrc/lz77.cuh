@@ -55,6 +55,8 @@ constexpr u32 LZ_OFF_WH = LZ_OFF_X + 131072;                // u16[LZ_WARPS*256]
 constexpr u32 LZ_OFF_MISC = LZ_OFF_WH + 32768;              // scratch u32[40] | specexit u32[64] | mbarrier
 constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 232448 available)
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (at most)
+constexpr u32 LZ_BGROUP = 16;                               // batch mode: blocks per group (one sort when all are small)
+constexpr u32 LZ_BSLOT = (2 * SUB) / LZ_BGROUP;              // 4096: the most a block of a packed group holds
 constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
 // per-warp candidate ring: 64 entries of 4 bytes (lz_tag), stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
@@ -315,7 +317,13 @@ __device__ __forceinline__ void lz_clear_bits(u32 *bm, u32 a, u32 b) {  // clear
       : "r"(es), "r"(rp[-(int)(r)]), "r"(one), "r"(rrun), "n"(64 - (r)), "n"(r))
 #endif
 
-__global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
+// TABLE = false: one stream (P.in, P.n).  TABLE = true: a batch of independent buffers (P.table): groups of LZ_BGROUP
+// consecutive blocks; a group whose blocks are all small first blocks (<= LZ_BSLOT bytes, no window) shares ONE sort —
+// its buffers sit in 4 KiB slots of the staged 64 KiB and a position's candidates stop at its slot's start — which is
+// what makes 4 KiB buffers (BASELINE configs[2]) cost 1/16 of a sort each instead of a whole one; other groups are
+// processed a block at a time.
+template <bool TABLE>
+__device__ __forceinline__ void lz_body(const LzParams &P) {
   ZLES_SMEM_DECL(smem);
   u8 *data = smem + LZ_OFF_DATA;
   u16 *X = reinterpret_cast<u16 *>(smem + LZ_OFF_X);
@@ -328,6 +336,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   u64 *mbar = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK);     // 8-byte aligned: (40+128)*4 = 672
   u64 *red = reinterpret_cast<u64 *>(scratch + 40 + LZ_NWALK + 2);  // [2][LZ_WARPS] u64
   u32 *slice_ctr = scratch + 40 + LZ_NWALK + 2 + 4 * LZ_WARPS;       // S3 work counter
+  u32 *seg_len = slice_ctr + 2;                                      // [LZ_BGROUP] bytes of every block of a packed group
 
   const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
   u32 parity = 0;
@@ -342,9 +351,9 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
   // chunk share one sort (block 0 has no window, block 1's window is block 0: one sorted array serves both); blocks
   // 2 and 3 each take a sort with the block before as window (pair_mode 0), or share one without window for block 2
   // (pair_mode 1).  Batch mode: one block per unit, as its table entry says.
-  const u32 upc = P.table ? 1u : (P.pair_mode ? 2u : 3u);  // units per chunk
+  const u32 upc = P.pair_mode ? 2u : 3u;  // units per chunk (stream mode)
   const u32 c_begin = P.first_block / SUBS_PER_CHUNK, c_end = (P.nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
-  const u32 nunits = P.table ? P.nblocks - P.first_block : (c_end - c_begin) * upc;
+  const u32 nunits = TABLE ? (P.nblocks - P.first_block + LZ_BGROUP - 1) / LZ_BGROUP : (c_end - c_begin) * upc;
   for (;;) {
     // units come from a counter (their cost differs: two blocks or one); all two-block units are handed out first
     __syncthreads();
@@ -352,16 +361,38 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     __syncthreads();
     const u32 ui = *slice_ctr;
     if (ui >= nunits) break;
-    u32 v;  // table mode: the block; otherwise chunk * upc + unit within the chunk
-    if (P.table) v = P.first_block + ui;
-    else if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
-    else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
-    u64 own_off;
+    // batch mode: is the group one packed unit, or `gcnt` units of one block each?
+    u32 gfirst = 0, gcnt = 1;
+    bool packed = false;
+    if (TABLE) {
+      gfirst = P.first_block + ui * LZ_BGROUP;
+      gcnt = umin(LZ_BGROUP, P.nblocks - gfirst);
+      const u32 gi = tid & (LZ_BGROUP - 1);
+      int small = 1;
+      if (gi < gcnt) {
+        const BatchBlk t = P.table[gfirst + gi];
+        small = t.hist_len == 0 && t.own_len <= LZ_BSLOT;
+        if (tid < LZ_BGROUP) seg_len[tid] = t.own_len;
+      } else if (tid < LZ_BGROUP) {
+        seg_len[tid] = 0;
+      }
+      packed = __syncthreads_and(small) != 0 && gcnt > 1;
+    }
+    const u32 nrep = (TABLE && !packed) ? gcnt : 1u;
+    for (u32 rep = 0; rep < nrep; rep++) {
+    u64 own_off = 0;
     u32 own_len, hist_len, bfirst;
-    if (P.table) {
-      const BatchBlk t = P.table[v];
-      own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len; bfirst = v;
+    if (TABLE) {
+      if (packed) {
+        own_len = gcnt * LZ_BSLOT; hist_len = 0; bfirst = gfirst;
+      } else {
+        const BatchBlk t = P.table[gfirst + rep];
+        own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len; bfirst = gfirst + rep;
+      }
     } else {
+      u32 v;  // chunk * upc + unit within the chunk
+      if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
+      else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
       const u32 chunk = v / upc, k = v % upc;
       u32 sb0, nsb;
       if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
@@ -372,19 +403,43 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
       own_off = (u64)bfirst * SUB;
       own_len = (u32)umin64((u64)nsb * SUB, P.n - own_off);
     }
-    const u32 nsub = own_len > SUB ? 2u : 1u;  // deflate blocks in this unit
+    const u32 SEG = (TABLE && packed) ? LZ_BSLOT : SUB;  // bytes per deflate block slot of the unit
+    const u32 nsub = (TABLE && packed) ? gcnt : (own_len > SUB ? 2u : 1u);  // deflate blocks in this unit
     const u32 L = hist_len + own_len;
 
     LZ_CLK(scratch, -1);
     // S0: stage window + block, zero the pad so word reads past the end are defined
-    stage_g2s(data, P.in + own_off - hist_len, L, mbar, parity);
+    if (TABLE && packed) {
+      // every buffer into its slot, the rest of the slot zeroed; 16 bytes at a time where the source allows it
+      for (u32 i = tid; i < (L >> 4); i += LZ_THREADS) {
+        const u32 sl = i / (LZ_BSLOT >> 4), o = (i % (LZ_BSLOT >> 4)) << 4;
+        const u32 sl_len = seg_len[sl];
+        uint4 v4 = make_uint4(0, 0, 0, 0);
+        if (o < sl_len) {
+          const u8 *src = P.in + P.table[gfirst + sl].in_off + o;
+          if (o + 16 <= sl_len && ((uintptr_t)src & 15) == 0) {
+            v4 = *reinterpret_cast<const uint4 *>(src);
+          } else {
+            u32 wv[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (u32 q = 0; q < 16; q++)
+              if (o + q < sl_len) wv[q >> 2] |= (u32)src[q] << ((q & 3) * 8);
+            v4 = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+          }
+        }
+        *reinterpret_cast<uint4 *>(data + (i << 4)) = v4;
+      }
+      __syncthreads();
+    } else {
+      stage_g2s(data, P.in + own_off - hist_len, L, mbar, parity);
+    }
     for (u32 i = tid; i < LZ_PAD; i += LZ_THREADS) data[L + i] = 0;
     __syncthreads();
     LZ_CLK(scratch, 0);
 
     // S1: Adler-32 partial sums of every own block (K8 fused into the load)
     for (u32 sbi = 0; sbi < nsub; sbi++) {
-      const u32 sbase = sbi * SUB, slen = umin(SUB, own_len - sbase);
+      const u32 sbase = sbi * SEG, slen = (TABLE && packed) ? seg_len[sbi] : umin(SUB, own_len - sbase);
       u64 a = 0, bsum = 0;
       const u32 j0 = tid * 32;
       if (j0 < slen) {
@@ -479,15 +534,21 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
         __syncwarp();
         // rrun = how many entries before k belong to k's run (capped at the scan width): the only ones that
         // may be looked at — what precedes them in the ring is another run, an older slice, or stale
-        const bool own = valid && p >= hist_len;
+        // the block slot of p: where its candidates start (the window, or a packed buffer's own start) and where it ends
+        u32 lim = p > WINDOW ? p - WINDOW : 0, bend = (nsub == 2 && p < SUB) ? SUB : L;
+        bool own = valid && p >= hist_len;
+        if (TABLE && packed) {
+          lim = p & ~(LZ_BSLOT - 1);
+          bend = lim + seg_len[p / LZ_BSLOT];
+          own = valid && p < bend;
+        }
         u32 rrun = 0;
         if (own) {
           // bit 31 = entry k's run-start flag, bit 30 = entry k-1's, ...: the leading zeros count the run's earlier entries
           rrun = umin((u32)__clz((int)__funnelshift_rc(Bprev, B, lane + 1)), scan);
-          if (rrun && p > WINDOW && (u32)X[k - rrun] < p - WINDOW) {
-            // candidates older than the window (src/lz77.ts:49): positions ascend inside a run, so
-            // binary-search the largest r with X[k-r] >= p - WINDOW
-            const u32 lim = p - WINDOW;
+          if (rrun && (u32)X[k - rrun] < lim) {
+            // candidates older than the window (src/lz77.ts:49) or from another buffer of a packed group: positions
+            // ascend inside a run, so binary-search the largest r with X[k-r] >= lim
             u32 a = 0, b = rrun;  // X[k-a] in window (a = 0: k itself), X[k-b] not
             while (b - a > 1) {
               const u32 m = (a + b) >> 1;
@@ -518,15 +579,27 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
             }
           }
         }
+        // Within five bytes of its block's end a position's tag holds bytes from behind the end (the next block, another
+        // buffer of a packed group): they must not rank its candidates — whatever follows the block, the same nearest
+        // candidate wins (a buffer compresses to the same bytes alone, in a batch or in a packed group).  Rare: redone
+        // here with those bytes masked out.
+        if (rrun && bend - p < 6) {  // (rrun != 0 implies own; no warp collective inside: plain divergence)
+          const u32 m = bend - p;
+          const u32 vmask = 0xffu | (m > 3 ? 0xff00u : 0u) | (m > 4 ? 0xff0000u : 0u);
+          best = 0;
+          for (u32 r = 1; r <= rrun; r++) {
+            const u32 v = (es ^ rp[-(int)r]) & vmask;
+            best = umax(best, (~v & (v - 1) & 0x80808080u) | (64u - r));
+          }
+        }
         LZ_WCLK(13);
         // The winner: the nearest candidate of the longest class.  Classes 3..5 are exact lengths; the class "six or
         // more" is extended — its first 8 bytes in straight-line code for the whole warp, the rest (rare on text) in a loop.
         const bool hit = own && best >= 0x80u;
         if (__any_sync(ZLES_FULL, hit)) {
           const u32 c = hit ? (u32)X[k - (64 - (best & 0x7fu))] : p;
-          // a match ends with its deflate block: the unit's first block ends at hist_len + SUB
-          const u32 bend = (nsub == 2 && p < SUB) ? SUB : L;
-          const u32 maxlen = umin(MAX_MATCH, bend - p);
+          // a match ends with its deflate block (bend)
+          const u32 maxlen = own ? umin(MAX_MATCH, bend - p) : 0;
           u32 len = 2u + (u32)__popc(best & 0x80808080u);
           if (__any_sync(ZLES_FULL, hit && len == 6)) {
             const u64 x = lz_ld64(data, p + 6) ^ lz_ld64(data, c + 6);
@@ -553,11 +626,119 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     __syncthreads();
     LZ_CLK(scratch, 8);
 
+    // S4/S5 of a packed group: eight buffers (32 KiB of slots) at a time — their parses run side by side (the first
+    // walker of every buffer starts at its first byte, nothing crosses a slot), tokens, counts and histograms go to
+    // every buffer's own block.  Done one buffer after the other this stage cost more than sort and match together.
+    if (TABLE && packed) {
+      u32 *pref = reinterpret_cast<u32 *>(smem + LZ_OFF_WH + 16384);  // [1024] exclusive token counts per bitmap word
+      constexpr u32 WPS = LZ_BSLOT / LZ_RANGE;                         // walkers per slot
+      constexpr u32 SPH = SUB / LZ_BSLOT;                              // slots per half (8 = LZ_HCOPIES)
+      static_assert(SPH == LZ_HCOPIES, "one histogram copy per slot of a half");
+      for (u32 h = 0; h * SPH < gcnt; h++) {
+        const u32 nsl = umin(SPH, gcnt - h * SPH), hbase = h * SUB, hlen = nsl * LZ_BSLOT;
+        {
+          const uint4 *src4 = reinterpret_cast<const uint4 *>(R + hbase);
+          uint4 *dst4 = reinterpret_cast<uint4 *>(XR);
+          const u32 n4 = hlen >> 2;
+          for (u32 i0 = 0; i0 < n4; i0 += 8 * LZ_THREADS) {
+            uint4 v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const u32 i = i0 + u * LZ_THREADS + tid; if (i < n4) v8[u] = __ldcg(src4 + i); }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const u32 i = i0 + u * LZ_THREADS + tid; if (i < n4) dst4[i] = v8[u]; }
+          }
+        }
+        bm[tid] = 0;
+        for (u32 i = tid; i < LZ_HCOPIES * LZ_NSYM; i += LZ_THREADS) hcopies[i] = 0;
+        __syncthreads();
+        // the walkers: range [ws, we) of slot wsl; a slot's first walker has a fixed entry
+        const u32 wsl = tid / WPS;
+        const u32 sbeg = wsl * LZ_BSLOT, send = sbeg + (tid < LZ_NWALK && wsl < nsl ? seg_len[h * SPH + wsl] : 0u);
+        const u32 ws = tid * LZ_RANGE, we = umin(ws + LZ_RANGE, send);
+        const bool walker = tid < LZ_NWALK && ws < send;
+        u32 wentry = ws;
+        if (walker) {
+          u32 pos = ws;
+          while (pos < we) {
+            bm[pos >> 5] |= 1u << (pos & 31);
+            const u32 len = lz_parse_len(XR, pos, send, P.lazy);
+            pos += len ? len : 1;
+          }
+          specexit[tid] = pos;
+        }
+        for (;;) {
+          __syncthreads();
+          const u32 entry = (walker && (tid % WPS) != 0) ? specexit[tid - 1] : ws;
+          __syncthreads();
+          int changed = 0;
+          if (walker && entry != wentry) {
+            wentry = entry;
+            u32 exitpos = specexit[tid];
+            lz_clear_bits(bm, ws, umin(entry, we));
+            if (entry >= we) {
+              exitpos = entry;
+            } else {
+              u32 pos = entry;
+              for (;;) {
+                if (pos >= we) { exitpos = pos; break; }
+                if ((bm[pos >> 5] >> (pos & 31)) & 1) break;
+                bm[pos >> 5] |= 1u << (pos & 31);
+                const u32 len = lz_parse_len(XR, pos, send, P.lazy);
+                const u32 nxt = pos + (len ? len : 1);
+                lz_clear_bits(bm, pos + 1, umin(nxt, we));
+                pos = nxt;
+              }
+            }
+            if (exitpos != specexit[tid]) { specexit[tid] = exitpos; changed = 1; }
+          }
+          if (!__syncthreads_or(changed)) break;
+        }
+        // emit: bitmap word tid belongs to slot tid / 128
+        {
+          u32 word = bm[tid];
+          u32 total;
+          const u32 oex = block_exscan((u32)__popc(word), scratch, &total);
+          pref[tid] = oex;
+          __syncthreads();
+          const u32 sl = tid >> 7;  // 128 words of 32 positions per slot
+          const u32 bcur = bfirst + h * SPH + sl;
+          const u32 send2 = sl * LZ_BSLOT + (sl < nsl ? seg_len[h * SPH + sl] : 0u);
+          u32 o = oex - pref[tid & ~127u];
+          u32 *tok = P.tokens + (size_t)bcur * SUB;
+          u32 *hc = hcopies + sl * LZ_NSYM;
+          while (word) {
+            const u32 bit = (u32)(__ffs((int)word) - 1);
+            word &= word - 1;
+            const u32 pos = tid * 32 + bit;
+            const u32 len = lz_parse_len(XR, pos, send2, P.lazy);
+            if (len) {
+              const u32 dist = XR[pos] & 0xffff;
+              u32 ls, le, lv, ds, de, dv;
+              len_to_sym(len, ls, le, lv);
+              dist_to_sym(dist, ds, de, dv);
+              atomicAdd(hc + 257 + ls, 1u);
+              atomicAdd(hc + 288 + ds, 1u);
+              tok[o] = tok_match(len, dist);
+            } else {
+              const u32 d = data[hbase + pos];
+              atomicAdd(hc + d, 1u);
+              tok[o] = d;
+            }
+            o++;
+          }
+          __syncthreads();
+          for (u32 i = tid; i < nsl * LZ_NSYM; i += LZ_THREADS)
+            P.hist[(size_t)(bfirst + h * SPH + i / LZ_NSYM) * LZ_NSYM + i % LZ_NSYM] = hcopies[i];
+          if ((tid & 127) == 0 && sl < nsl) P.ntok[bcur] = (sl + 1 < SPH ? pref[tid + 128] : total) - oex;
+        }
+        __syncthreads();
+      }
+    }
     // S4/S5 once per deflate block of the unit (the match results stay in the scratch; XR takes one block's at a time)
     const u32 unit_own = own_len;
-    for (u32 sbi = 0; sbi < nsub; sbi++) {
-    const u32 sbase = sbi * SUB, bcur = bfirst + sbi, dbase = hist_len + sbase;
-    const u32 own_len = umin(SUB, unit_own - sbase);  // this block's bytes (shadows the unit's)
+    for (u32 sbi = 0; sbi < ((TABLE && packed) ? 0u : nsub); sbi++) {
+    const u32 sbase = sbi * SEG, bcur = bfirst + sbi, dbase = hist_len + sbase;
+    const u32 own_len = (TABLE && packed) ? seg_len[sbi] : umin(SUB, unit_own - sbase);  // this block's bytes (shadows the unit's)
     // S4: match results into shared memory (over the sorted array), then the parse
     {  // 16 bytes per load: the copy is bound by the round trips to L2, not by their width
       const uint4 *src4 = reinterpret_cast<const uint4 *>(R + sbase);
@@ -660,7 +841,11 @@ __global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) {
     }  // blocks of the unit
     __syncthreads();
     LZ_CLK(scratch, 11);
+    }  // blocks of an unpacked group
   }
 }
+
+__global__ void __launch_bounds__(LZ_THREADS, 1) k_lz(const LzParams P) { lz_body<false>(P); }
+__global__ void __launch_bounds__(LZ_THREADS, 1) k_lz_batch(const LzParams P) { lz_body<true>(P); }
 
 }  // namespace zles

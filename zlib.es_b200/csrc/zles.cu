@@ -218,6 +218,8 @@ static int set_kernel_attrs(int device) {
   // opt in to > 48 KiB dynamic shared memory where needed
   zrt_err_t e = zrt_set_smem(k_lz, (int)LZ_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_lz)");
+  e = zrt_set_smem(k_lz_batch, (int)LZ_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_lz_batch)");
   e = zrt_set_smem(k_huff, HUF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff)");
   e = zrt_set_smem(k_inflate, INF_SMEM);
@@ -1282,7 +1284,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   RET(c->unit_ctr.reserve(4));
   lp.unit_ctr = c->unit_ctr.as<u32>();
   CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
-  LAUNCH(c, k_lz, grid_lz, LZ_THREADS, LZ_SMEM, lp);
+  LAUNCH(c, k_lz_batch, grid_lz, LZ_THREADS, LZ_SMEM, lp);
   LAUNCH(c, k_huff, (nblocks + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), 0u, nblocks,
          c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)0, (const BatchBlk *)d_tab);
   BatchPackParams bp;

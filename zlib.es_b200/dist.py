@@ -99,6 +99,10 @@ class ShardedCodec:
         self._d_all = torch.empty(self.world * 5, dtype=torch.int64, device=self.comm_device)
         self._d_flag = torch.zeros(1, dtype=torch.int32, device=self.comm_device)
         self._frame = torch.empty(8, dtype=torch.uint8, pin_memory=cuda)
+        # numpy views of the pinned buffers: one assignment instead of a tensor operation per element
+        self._np_mine = self._h_mine.numpy()
+        self._np_all = self._h_all.numpy()
+        self._np_frame = self._frame.numpy()
 
     def _ordered(self):
         """Collectives issued inside this context are ordered on the codec's stream (when it runs on a caller's CUDA
@@ -142,15 +146,14 @@ class ShardedCodec:
         """All ranks call this with their shard (device pointer).  Afterwards the zlib stream lies at
         ``self.t.base`` on rank 0 (``layout.total_comp`` bytes)."""
         info = self.c.dev_deflate_phase1(d_in, n_local, self.rank == self.world - 1)
-        self._h_mine[0], self._h_mine[1], self._h_mine[2], self._h_mine[3], self._h_mine[4] = (
-            info.comp_bytes, info.raw_bytes, info.adler_a, info.adler_b, info.n_blocks)
+        self._np_mine[:] = (info.comp_bytes, info.raw_bytes, info.adler_a, info.adler_b, info.n_blocks)
         with self._ordered():
             self._d_mine.copy_(self._h_mine, non_blocking=True)
             dist.all_gather_into_tensor(self._d_all, self._d_mine, group=self.group)  # the one exchange step of the path
             self._h_all.copy_(self._d_all, non_blocking=True)
             if self.comm_device.type == "cuda":
                 torch.cuda.current_stream(self.comm_device).synchronize()
-        rows = self._h_all.view(self.world, 5).tolist()
+        rows = self._np_all.reshape(self.world, 5).tolist()
         infos = []
         offsets, comp, raw = [], [], []
         off = 0
@@ -170,7 +173,7 @@ class ShardedCodec:
         # peer-mapped memory (NVLink) elsewhere
         self.c.dev_deflate_phase2(self.t.base + 2 + offsets[self.rank])
         if self.rank == 0:  # framing stays on the host (/root/reference/src/zlib.ts:28-46)
-            self._frame[:6] = torch.tensor([0x78, 0x9C, (adler >> 24) & 255, (adler >> 16) & 255, (adler >> 8) & 255, adler & 255], dtype=torch.uint8)
+            self._np_frame[:6] = (0x78, 0x9C, (adler >> 24) & 255, (adler >> 16) & 255, (adler >> 8) & 255, adler & 255)
             self.c.dev_copy_async(self.t.base, self._frame.data_ptr(), 2)
             self.c.dev_copy_async(self.t.base + total - 4, self._frame.data_ptr() + 2, 4)
         self._rendezvous()

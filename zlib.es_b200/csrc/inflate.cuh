@@ -787,18 +787,18 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
         const u32 tokv = is_len ? (0x80000000u | ((len - 3) << 16) | (dist - 1)) : (len & 0xff);
         // The chain: lane 0 is a token start; a token of nb bits at lane c makes lane c + nb one.  A token that
         // ends the round (end of block, or a code the fast tables do not hold) leads nowhere.
-        const u32 nb = pack & 0xff;
-        const bool stop = nb == 0 || (pack & 0x100);
-        const u32 step = (!stop && lane + nb < 32) ? 1u << (lane + nb) : 0;
-        u32 R = 1;
+        // The chain: lane 0 is a token start; a token of nb bits at lane c makes lane c + nb one — one shuffle per
+        // token.  A token that ends the round (end of block, or a code the fast tables do not hold) leads nowhere.
+        u32 R = 1, last = 0, plast;
+        bool last_stops;
         for (;;) {
-          const u32 add = __reduce_or_sync(ZLES_FULL, ((R >> lane) & 1) ? step : 0u);
-          if ((add & ~R) == 0) break;
-          R |= add;
+          plast = __shfl_sync(ZLES_FULL, pack, (int)last);
+          const u32 nb = plast & 0xff;
+          last_stops = nb == 0 || (plast & 0x100);
+          if (last_stops || last + nb >= 32) break;
+          last += nb;
+          R |= 1u << last;
         }
-        const u32 last = 31u - (u32)__clz((int)R);                        // the chain's last member
-        const u32 plast = __shfl_sync(ZLES_FULL, pack, (int)last);
-        const bool last_stops = (plast & 0xff) == 0 || (plast & 0x100);
         const u32 plain = last_stops ? R & ~(1u << last) : R;              // the members that are ordinary tokens
         const bool mine = (plain >> lane) & 1;
         const u32 sum = __reduce_add_sync(ZLES_FULL, mine ? (is_len ? len : 1u) : 0u);

@@ -62,6 +62,19 @@ def test_batch_of_small_buffers_shares_sorts(c):
     assert c.inflate_batch(zs) == bufs
 
 
+def test_long_matches_between_text(c):
+    # runs of zeros (258-byte matches at distance 1) between stretches of text: a batch of 32 such tokens is wider than
+    # the small shared-memory mirror of the piece-parallel copy pass (regression: its slots aliased inside one batch)
+    rng = np.random.default_rng(11)
+    parts = []
+    for _ in range(14):
+        parts.append(T.gen("G5", int(rng.integers(1, 3000))))
+        parts.append(bytes(int(rng.integers(1, 40000))) if rng.integers(0, 3) else b"ab" * int(rng.integers(1, 9000)))
+    data = b"".join(parts)
+    P.roundtrip(c, data, check_size=False)
+    P.inflate_matches_oracle(c, zlib.compress(data, 6))
+
+
 def test_window_modes(c):
     data = T.fixture_raw()[:150000] + T.gen("G5", 120000)
     z1 = P.roundtrip(c, data, check_size=False, oracle_decode=False)

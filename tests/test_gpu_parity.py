@@ -92,6 +92,19 @@ def test_batch_of_small_buffers_shares_sorts(c):
     assert c.inflate_batch(zs) == bufs
 
 
+def test_long_matches_between_text(c):
+    # runs of zeros (258-byte matches at distance 1) between stretches of text: a batch of 32 such tokens is wider than
+    # the small shared-memory mirror of the piece-parallel copy pass (regression: its slots aliased inside one batch)
+    rng = np.random.default_rng(11)
+    parts = []
+    for _ in range(60):
+        parts.append(T.gen("G5", int(rng.integers(1, 3000))))
+        parts.append(bytes(int(rng.integers(1, 40000))) if rng.integers(0, 3) else b"ab" * int(rng.integers(1, 9000)))
+    data = b"".join(parts)
+    P.roundtrip(c, data, check_size=False)
+    P.inflate_matches_oracle(c, zlib.compress(data, 6))
+
+
 def test_window_modes(c):
     # zles_ctx_set_window_mode: 1 (default) sorts blocks {0,1} and {2,3} of a chunk together; 0 gives block 2 the block
     # before it as window (three sorts per chunk): smaller or equal output, same decoders, same size bound

@@ -1,0 +1,53 @@
+"""Randomised round trips through the C ABI on a GPU (not a benchmark): our deflate against system zlib's inflate and
+ours, system zlib's deflate (random level / strategy) against our inflate, single calls and batches.
+usage: python tools/gpu_stress.py [cases=200] [seed=1]"""
+import os, sys, zlib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import zles
+import vectors as T
+c = zles.Codec(0)
+cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+raw = T.fixture_raw()
+
+def make(n):
+    kind = int(rng.integers(0, 7))
+    if kind == 0: return rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+    if kind == 1: return rng.integers(97, 97 + int(rng.integers(2, 30)), size=n, dtype=np.uint8).tobytes()
+    if kind == 2:
+        unit = rng.integers(0, 256, size=int(rng.integers(1, 70000)), dtype=np.uint8).tobytes()
+        return (unit * (n // len(unit) + 1))[:n]
+    if kind == 3: o = int(rng.integers(0, max(1, len(raw) - n))); return (raw * (n // len(raw) + 2))[o:o + n]
+    if kind == 4: return bytes(n)
+    if kind == 5:
+        parts, left = [], n
+        while left > 0:
+            m = min(left, int(rng.integers(1, 50000))); parts.append(make(m) if rng.integers(0, 4) else bytes(m)); left -= m
+        return b"".join(parts)[:n]
+    return T.gen("G5", n)
+
+bad = 0
+for i in range(cases):
+    n = int(rng.choice([0, 1, 2, 3, 100, 4095, 4096, 4097, 32767, 32768, 32769, 65536, 131071, 131072, 131073])) if rng.integers(0, 3) == 0 else int(rng.integers(0, 1 << int(rng.integers(4, 22))))
+    d = make(n)
+    z = c.deflate(d)
+    ok = zlib.decompress(z) == d and c.inflate(z) == d
+    lvl = int(rng.integers(0, 10)); strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+    co = zlib.compressobj(lvl, zlib.DEFLATED, 15, 8, strat)
+    f = co.compress(d) + co.flush()
+    ok = ok and c.inflate(f) == d
+    if not ok:
+        bad += 1
+        print("FAIL case", i, "n", n, "level", lvl, "strategy", strat, flush=True)
+for r in range(max(1, cases // 40)):
+    bufs = [make(int(rng.integers(0, 9000 if rng.integers(0, 2) else 4097))) for _ in range(int(rng.integers(1, 200)))]
+    zs = c.deflate_batch(bufs)
+    ok = all(zlib.decompress(z) == b for b, z in zip(bufs, zs)) and c.inflate_batch(zs) == bufs and all(z == c.deflate(b) for b, z in zip(bufs[:30], zs[:30]))
+    if not ok:
+        bad += 1
+        print("FAIL batch", r, flush=True)
+print("stress: %d cases, %d failures" % (cases, bad))
+sys.exit(1 if bad else 0)

@@ -303,6 +303,7 @@ struct SymState {
   u16 *ring;
   u32 o;
   u32 refs;     // set once a source before the run was seen (a window reference was written)
+  u32 vfrom;    // the ring mirrors run positions >= vfrom only (a batch wider than the ring leaves it undefined)
 };
 
 // Same as res_tokens, on 16-bit symbols; a source position before the run (negative) yields a window reference.
@@ -358,7 +359,9 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
       const u32 pj = __shfl_sync(ZLES_FULL, pos, j), lj = __shfl_sync(ZLES_FULL, len, j), dj = __shfl_sync(ZLES_FULL, dist, j);
       const int sj = (int)pj - (int)dj;  // may be negative: before the run
       if (sj < 0) st.refs = 1;
-      const bool in_ring = sj >= 0 && o + total - (u32)sj <= RING;
+      // a batch wider than the ring aliases its own positions (their stores are not ordered): nothing of it is read
+      // from the ring, now or later (vfrom)
+      const bool in_ring = sj >= 0 && (u32)sj >= st.vfrom && total <= RING && o + total - (u32)sj <= RING;
       for (u32 q = lane; q < lj; q += 32) {
         const int s = sj + (int)(dj >= lj ? q : q % dj);
         u16 b;
@@ -370,6 +373,7 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
       __syncwarp();
     }
     o += total;
+    if (total > RING) st.vfrom = o;
   }
   st.o = o;
 }
@@ -398,6 +402,7 @@ k_run_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ cha
   st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SYM_RING;
   st.o = 0;
   st.refs = 0;
+  st.vfrom = 0;
   for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
     const FbChainEnt e = chain[i];
     if (e.stored) sym_bytes(st, in + e.a, e.b);
@@ -477,6 +482,7 @@ k_piece_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const 
   st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SEG_RING;
   st.o = 0;
   st.refs = 0;
+  st.vfrom = 0;
   if (r.flags & SEGF_STORED) {  // a stored block is concrete already: its payload goes straight to the output, four warps a block
     const u64 back = r.out_len + (r.status == SEG_SYNC ? 5 : 0);
     if (r.end_pos < back) { if (p == 0 && lane_id() == 0) atomicOr(problems, 1u); return; }

@@ -938,7 +938,8 @@ constexpr u32 SPEC_MAX_SEGS = 8192;  // phase A with four warps per block up to 
 static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8 *d_in, u8 *d_out, size_t cap) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   const u32 nchunks = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
-  if (nchunks <= SYM_PATH_MAX_CHUNKS && c->fsym.reserve((size_t)nseg * SUB * 2) == 0) {
+  static const bool no_sym = [] { const char *e = getenv("ZLES_NO_SYM"); return e && *e && *e != '0'; }();  // debugging aid
+  if (nchunks <= SYM_PATH_MAX_CHUNKS && !no_sym && c->fsym.reserve((size_t)nseg * SUB * 2) == 0) {
     const u32 *pinfo = c->pinfo_valid ? (const u32 *)c->pinfo.as<u32>() : nullptr;
     const u32 nwarps = nseg * SEG_PIECES;
     LAUNCH(c, k_piece_sym, (nwarps + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
@@ -967,7 +968,8 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     // 2. phase A on every candidate, acceptance check, and — optimistically — phase B with candidate j
     //    taken as block j of the stream (true unless a marker pattern occurs inside compressed data)
     // few blocks: four warps per block, the quarters decoded speculatively (inflate_spec.cuh); many: one warp per block
-    if (ncand <= SPEC_MAX_SEGS) {
+    static const bool no_spec = [] { const char *e = getenv("ZLES_NO_SPEC"); return e && *e && *e != '0'; }();  // debugging aid
+    if (ncand <= SPEC_MAX_SEGS && !no_spec) {
       const u32 grid = ncand < (u32)c->sm_count * 16 ? ncand : (u32)c->sm_count * 16;
       LAUNCH(c, k_inf_tokens4, grid, SPEC_THREADS, SPEC_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand, c->tokens.as<u32>(),
              c->ntok.as<u32>(), c->res.as<InfRes>(), c->pinfo.as<u32>(), &ctl->counter);

@@ -105,6 +105,18 @@ def test_long_matches_between_text(c):
     P.inflate_matches_oracle(c, zlib.compress(data, 6))
 
 
+def test_stored_block_followed_by_a_final_empty_one(c):
+    # what system zlib writes at level 0 for exactly 32 KiB: a NON-final stored block, then a final empty stored block
+    # (regression: the payload was looked for 5 bytes too late, as if the data block itself had been the final one)
+    import struct
+    for data in (T.fixture_raw()[5000:5000 + 32768], T.gen("G5", 1000), T.fixture_raw()[:32768], b"\x00\x00\xff\xff" * 300):
+        n = len(data)
+        z = b"\x78\x01" + b"\x00" + struct.pack("<HH", n, n ^ 0xffff) + data + b"\x01\x00\x00\xff\xff" + struct.pack(">I", zlib.adler32(data))
+        assert zlib.decompress(z) == data
+        P.inflate_matches_oracle(c, z)
+        assert c.inflate(z) == data
+
+
 def test_window_modes(c):
     # zles_ctx_set_window_mode: 1 (default) sorts blocks {0,1} and {2,3} of a chunk together; 0 gives block 2 the block
     # before it as window (three sorts per chunk): smaller or equal output, same decoders, same size bound

@@ -1,6 +1,6 @@
 """Randomised round trips through the C ABI on a GPU (not a benchmark): our deflate against system zlib's inflate and
 ours, system zlib's deflate (random level / strategy) against our inflate, single calls and batches.
-usage: python tools/gpu_stress.py [cases=200] [seed=1]"""
+usage: python tools/gpu_stress.py [cases=200] [seed=1] [log2 of the largest size=22]"""
 import os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
@@ -11,6 +11,7 @@ import vectors as T
 c = zles.Codec(0)
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+maxlog = int(sys.argv[3]) if len(sys.argv) > 3 else 22
 raw = T.fixture_raw()
 
 def make(n):
@@ -31,7 +32,7 @@ def make(n):
 
 bad = 0
 for i in range(cases):
-    n = int(rng.choice([0, 1, 2, 3, 100, 4095, 4096, 4097, 32767, 32768, 32769, 65536, 131071, 131072, 131073])) if rng.integers(0, 3) == 0 else int(rng.integers(0, 1 << int(rng.integers(4, 22))))
+    n = int(rng.choice([0, 1, 2, 3, 100, 4095, 4096, 4097, 32767, 32768, 32769, 65536, 131071, 131072, 131073])) if rng.integers(0, 3) == 0 else int(rng.integers(0, 1 << int(rng.integers(4, maxlog))))
     d = make(n)
     z = c.deflate(d)
     ok = zlib.decompress(z) == d and c.inflate(z) == d

@@ -503,6 +503,12 @@ k_mark_emit(const u8 *__restrict__ in, u64 n, u64 first, const u32 *tile_base, u
 // Tokens use the encoder's format (lz77.cuh): literal = byte value; match = bit31 | (len-3)<<16 | (dist-1).
 constexpr u32 SEGF_BADREF = 4;            // a distance reached before the start of the chunk
 constexpr u32 SEGF_STORED = 8;            // the segment's data block is a stored one: no tokens, phase B copies the bytes
+constexpr u32 SEGF_TAIL_SHIFT = 8;        // flags bits 8..15 of a stored segment: bytes between its payload's end and end_pos
+// where a stored segment's payload starts in the input, or ~0 when the result is inconsistent
+__host__ __device__ __forceinline__ u64 seg_stored_src(u64 end_pos, u64 out_len, u32 flags) {
+  const u64 back = out_len + ((flags >> SEGF_TAIL_SHIFT) & 0xffu);
+  return end_pos >= back ? end_pos - back : ~0ull;
+}
 
 // Phase A uses 32-bit LUT entries so that one shared-memory load yields everything about a symbol:
 //   bits 0-3 code length (0 = longer than the root: canonical slow path) | bits 4-7 extra-bit count |
@@ -708,7 +714,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
   r.init(in, n, in_pos);
   u32 o = 0, nt = 0;
   u32 status = 0, flags = 0;
-  u64 end_pos = 0;
+  u64 end_pos = 0, stored_end = 0;
   INF_CLK_DECL;
   // a single token, outside the parallel rounds of the symbol loop
 #define ZLES_EMIT(t)                 \
@@ -736,6 +742,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
         if (o != 0 || nt != 0 || (flags & SEGF_STORED) || LEN > SUB || q + LEN > n) { status = SEG_E_CORRUPT; break; }
         flags |= SEGF_STORED;
         o = LEN;
+        stored_end = q + LEN;
         if (bfinal) { status = SEG_FINAL; end_pos = q + LEN; break; }
         r.init(in, n, q + LEN);
         continue;
@@ -884,6 +891,9 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
 #undef ZLES_EMIT
   INF_CLK(0);
   INF_CNT(3, nt);
+  // a stored segment: how far before end_pos its payload ends (0: the data block was the final one; 5: an empty stored
+  // block — the marker, or a final one as system zlib writes after a full-size stored block — follows it)
+  if ((flags & SEGF_STORED) && end_pos >= stored_end) flags |= ((u32)umin64(end_pos - stored_end, 255) & 0xffu) << SEGF_TAIL_SHIFT;
   if (lane == 0) {
     res->end_pos = end_pos;
     res->out_len = o;
@@ -1040,9 +1050,9 @@ k_inf_resolve(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, cons
     if (r.status != SEG_SYNC && r.status != SEG_FINAL) { st.bad |= 1; break; }
     if (r.flags & SEGF_STORED) {  // stored block: the bytes sit in the input right before the marker / the end
       const u32 len = (u32)r.out_len;
-      const u64 back = (u64)len + (r.status == SEG_SYNC ? 5 : 0);
-      if (r.end_pos < back) { st.bad |= 1; break; }
-      if (!res_bytes(st, in + (r.end_pos - back), len)) break;
+      const u64 src = seg_stored_src(r.end_pos, r.out_len, r.flags);
+      if (src == ~0ull) { st.bad |= 1; break; }
+      if (!res_bytes(st, in + src, len)) break;
       continue;
     }
     if (!res_tokens(st, tokens + (size_t)sidx * SUB, umin(ntok[sidx], SUB))) break;

@@ -484,9 +484,9 @@ k_piece_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const 
   st.refs = 0;
   st.vfrom = 0;
   if (r.flags & SEGF_STORED) {  // a stored block is concrete already: its payload goes straight to the output, four warps a block
-    const u64 back = r.out_len + (r.status == SEG_SYNC ? 5 : 0);
-    if (r.end_pos < back) { if (p == 0 && lane_id() == 0) atomicOr(problems, 1u); return; }
-    const u8 *src = in + (r.end_pos - back);
+    const u64 so = seg_stored_src(r.end_pos, r.out_len, r.flags);
+    if (so == ~0ull) { if (p == 0 && lane_id() == 0) atomicOr(problems, 1u); return; }
+    const u8 *src = in + so;
     const u64 off = (u64)e * SUB;
     u32 len = (u32)r.out_len;
     if (off + len > cap) {

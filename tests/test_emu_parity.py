@@ -87,6 +87,25 @@ def test_stored_block_followed_by_a_final_empty_one(c):
         assert c.inflate(z) == data
 
 
+def test_random_round_trips_small(c):
+    # the randomised checks of tests/test_gpu_stress.py at sizes the emulator finishes in seconds
+    import stress_cases as S
+    rng = np.random.default_rng(3)
+    raw = T.fixture_raw()
+    for i in range(14):
+        d = S.make(rng, S.size(rng, 17) % 70000, raw)
+        z = c.deflate(d)
+        assert zlib.decompress(z) == d and c.inflate(z) == d, (i, len(d))
+        co = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, 15, 8, int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_RLE, zlib.Z_FIXED])))
+        f = co.compress(d) + co.flush()
+        assert c.inflate(f) == d, (i, len(d))
+        if rng.integers(0, 2):
+            s = bytearray(z if rng.integers(0, 2) else f)
+            if len(s) > 8:
+                s[int(rng.integers(2, len(s)))] ^= 1 << int(rng.integers(0, 8))
+            P.inflate_matches_oracle(c, bytes(s))
+
+
 def test_window_modes(c):
     data = T.fixture_raw()[:150000] + T.gen("G5", 120000)
     z1 = P.roundtrip(c, data, check_size=False, oracle_decode=False)

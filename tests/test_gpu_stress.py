@@ -1,0 +1,56 @@
+"""Randomised parity on the GPU (found two inflate bugs the hand-written cases missed): our deflate against system
+zlib's inflate, the oracle's and ours; system zlib's deflate at random levels / strategies against our inflate; damaged
+streams must give the reference's outcome (same bytes or same error text); batches must equal single calls."""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle as O
+import parity_cases as P
+import stress_cases as S
+import vectors as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c():
+    import zles
+    return zles.Codec(0)
+
+
+@pytest.mark.parametrize("seed", [1, 12, 77])
+def test_random_round_trips(c, seed):
+    rng = np.random.default_rng(seed)
+    raw = T.fixture_raw()
+    for i in range(120):
+        d = S.make(rng, S.size(rng, 21), raw)
+        z = c.deflate(d)
+        assert zlib.decompress(z) == d and c.inflate(z) == d, (seed, i, len(d))
+        lvl = int(rng.integers(0, 10))
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]))
+        co = zlib.compressobj(lvl, zlib.DEFLATED, 15, 8, strat)
+        f = co.compress(d) + co.flush()
+        assert c.inflate(f) == d, (seed, i, len(d), lvl, strat)
+        if len(d) <= 200000 and rng.integers(0, 3) == 0:  # damage: same outcome as the reference's inflate
+            s = bytearray(z if rng.integers(0, 2) else f)
+            if rng.integers(0, 2) and len(s) > 8:
+                del s[int(rng.integers(2, len(s))):]
+            else:
+                k = int(rng.integers(2, len(s)))
+                s[k] ^= 1 << int(rng.integers(0, 8))
+            P.inflate_matches_oracle(c, bytes(s))
+
+
+def test_random_batches(c):
+    rng = np.random.default_rng(5)
+    raw = T.fixture_raw()
+    for r in range(6):
+        small = bool(rng.integers(0, 2))
+        bufs = [S.make(rng, int(rng.integers(0, 4097 if small else 9000)), raw) for _ in range(int(rng.integers(1, 200)))]
+        zs = c.deflate_batch(bufs)
+        assert all(zlib.decompress(z) == b for b, z in zip(bufs, zs))
+        assert c.inflate_batch(zs) == bufs
+        assert all(z == c.deflate(b) for b, z in zip(bufs[:40], zs[:40]))
+        assert O.inflate(zs[0]) == bufs[0]

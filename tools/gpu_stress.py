@@ -14,25 +14,16 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 maxlog = int(sys.argv[3]) if len(sys.argv) > 3 else 22
 raw = T.fixture_raw()
 
+import stress_cases as S
+
+
 def make(n):
-    kind = int(rng.integers(0, 7))
-    if kind == 0: return rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
-    if kind == 1: return rng.integers(97, 97 + int(rng.integers(2, 30)), size=n, dtype=np.uint8).tobytes()
-    if kind == 2:
-        unit = rng.integers(0, 256, size=int(rng.integers(1, 70000)), dtype=np.uint8).tobytes()
-        return (unit * (n // len(unit) + 1))[:n]
-    if kind == 3: o = int(rng.integers(0, max(1, len(raw) - n))); return (raw * (n // len(raw) + 2))[o:o + n]
-    if kind == 4: return bytes(n)
-    if kind == 5:
-        parts, left = [], n
-        while left > 0:
-            m = min(left, int(rng.integers(1, 50000))); parts.append(make(m) if rng.integers(0, 4) else bytes(m)); left -= m
-        return b"".join(parts)[:n]
-    return T.gen("G5", n)
+    return S.make(rng, n, raw)
+
 
 bad = 0
 for i in range(cases):
-    n = int(rng.choice([0, 1, 2, 3, 100, 4095, 4096, 4097, 32767, 32768, 32769, 65536, 131071, 131072, 131073])) if rng.integers(0, 3) == 0 else int(rng.integers(0, 1 << int(rng.integers(4, maxlog))))
+    n = S.size(rng, maxlog)
     d = make(n)
     z = c.deflate(d)
     ok = zlib.decompress(z) == d and c.inflate(z) == d

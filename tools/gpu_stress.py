@@ -1,6 +1,6 @@
 """Randomised round trips through the C ABI on a GPU (not a benchmark): our deflate against system zlib's inflate and
 ours, system zlib's deflate (random level / strategy) against our inflate, single calls and batches.
-usage: python tools/gpu_stress.py [cases=200] [seed=1] [log2 of the largest size=22]"""
+usage: python tools/gpu_stress.py [cases=200] [seed=1] [log2 of the largest size=22] [window mode] [scan width]"""
 import os, sys, zlib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests")):
@@ -12,6 +12,10 @@ c = zles.Codec(0)
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 maxlog = int(sys.argv[3]) if len(sys.argv) > 3 else 22
+if len(sys.argv) > 4:  # window mode, then optionally the scan width
+    c.set_window_mode(int(sys.argv[4]))
+if len(sys.argv) > 5:
+    c.set_level(int(sys.argv[5]), 1, 8, True)
 raw = T.fixture_raw()
 
 import stress_cases as S

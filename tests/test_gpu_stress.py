@@ -54,3 +54,32 @@ def test_random_batches(c):
         assert c.inflate_batch(zs) == bufs
         assert all(z == c.deflate(b) for b, z in zip(bufs[:40], zs[:40]))
         assert O.inflate(zs[0]) == bufs[0]
+
+
+def test_random_batches_of_damaged_and_foreign_streams(c):
+    # k_inflate_batch: every stream of a batch — ours, system zlib's, truncated or with a flipped bit — must give what the
+    # reference's inflate gives on it alone: the same bytes or the same error text
+    rng = np.random.default_rng(9)
+    raw = T.fixture_raw()
+    for r in range(4):
+        streams = []
+        for _ in range(int(rng.integers(5, 60))):
+            d = S.make(rng, int(rng.integers(0, 20000)), raw)
+            z = c.deflate(d) if rng.integers(0, 2) else zlib.compress(d, int(rng.integers(0, 10)))
+            s = bytearray(z)
+            what = int(rng.integers(0, 4))
+            if what == 1 and len(s) > 8:
+                del s[int(rng.integers(2, len(s))):]
+            elif what == 2:
+                s[int(rng.integers(2, len(s)))] ^= 1 << int(rng.integers(0, 8))
+            streams.append(bytes(s))
+        got = c.inflate_batch(streams, raise_on_error=False)
+        for i, (st, g) in enumerate(zip(streams, got)):
+            try:
+                want = O.inflate(st)
+            except O.OracleError as e:
+                want = e
+            if isinstance(want, Exception):
+                assert isinstance(g, Exception) and str(g) == str(want), (r, i, str(want), g if isinstance(g, Exception) else len(g))
+            else:
+                assert not isinstance(g, Exception) and g == want, (r, i, len(want))

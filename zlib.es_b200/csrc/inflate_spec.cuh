@@ -201,7 +201,8 @@ __device__ __forceinline__ void spec_qinfo_whole(u32 *qinfo, u32 j, const InfRes
   }
 }
 
-__global__ void __launch_bounds__(SPEC_THREADS)
+// 9 CTAs per SM = 56 registers: what the kernel was tuned at (fewer registers spill, more CTAs per SM measured slower)
+__global__ void __launch_bounds__(SPEC_THREADS, 9)
 k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res, u32 *qinfo,
               u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);

@@ -80,6 +80,23 @@ def cpu_round_trip(data: bytes, cores: int) -> dict:
     return {"deflate_s": t1 - t0, "inflate_s": t2 - t1, "comp_bytes": sum(len(c) for c in comp), "pieces": len(pieces)}
 
 
+def cpu_single_thread(data: bytes) -> dict:
+    """The same oracle on ONE core, and system zlib -6 on one core for context, on the first 4 MiB of the stream (the
+    north_star asks for the CPU path both single-threaded and with one worker per core)."""
+    import zlib as syszlib
+    import oracle as O
+    O.lib()
+    sample = data[:4 << 20]
+    t0 = time.perf_counter(); z = O.deflate(sample); t1 = time.perf_counter(); back = O.inflate(z); t2 = time.perf_counter()
+    assert back == sample
+    t3 = time.perf_counter(); z6 = syszlib.compress(sample, 6); t4 = time.perf_counter(); syszlib.decompress(z6); t5 = time.perf_counter()
+    m = len(sample)
+    return {"value": round(m / (t2 - t0) / 1e9, 5), "unit": UNIT, "cores": 1, "sample": "the first 4 MiB of the stream, once",
+            "deflate_gbs": round(m / (t1 - t0) / 1e9, 5), "inflate_gbs": round(m / (t2 - t1) / 1e9, 5),
+            "system_zlib_level6": {"deflate_gbs": round(m / (t4 - t3) / 1e9, 5), "inflate_gbs": round(m / (t5 - t4) / 1e9, 5),
+                                   "ratio": round(m / len(z6), 4)}}
+
+
 def host_text(n: int) -> bytes:
     import ctypes
     import numpy as np
@@ -113,7 +130,8 @@ def run_reference(args):
         "deflate_gbs": round(SHARD / td / 1e9, 5), "inflate_gbs": round(SHARD / ti / 1e9, 5),
         "ratio": round(SHARD / times[-1]["comp_bytes"], 4),
         "cpu_baseline": {"value": round(value, 5), "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "the full 64 MiB stream per step, %d pieces" % times[-1]["pieces"]},
+                         "sample": "the full 64 MiB stream per step, %d pieces" % times[-1]["pieces"],
+                         "single_thread": cpu_single_thread(data)},
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -316,7 +334,7 @@ def run_ours(args):
         cpu = {"value": round(n / (r["deflate_s"] + r["inflate_s"]) / 1e9, 5), "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "the full 64 MiB stream once, %d independent pieces (one per core)" % r["pieces"],
                "deflate_gbs": round(n / r["deflate_s"] / 1e9, 5), "inflate_gbs": round(n / r["inflate_s"] / 1e9, 5),
-               "ratio": round(n / r["comp_bytes"], 4)}
+               "ratio": round(n / r["comp_bytes"], 4), "single_thread": cpu_single_thread(src[: 4 << 20].cpu().numpy().tobytes())}
 
     if rank == 0:
         total = n * world

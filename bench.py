@@ -107,6 +107,22 @@ def host_text(n: int) -> bytes:
     return out.tobytes()
 
 
+def node_reference(data: bytes):
+    """The unmodified zlib.es under Node (bench/node_ref.mjs), when this machine has `node` and ZLIBES_DIST names the
+    reference's dist/cjs/zlib.js.  Neither the build image nor the GPU boxes do: returns None there."""
+    import shutil, subprocess, tempfile
+    node, dist_js = shutil.which("node"), os.environ.get("ZLIBES_DIST")
+    if not node or not dist_js or not os.path.exists(dist_js):
+        return None
+    try:
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(data); f.flush()
+            out = subprocess.run([node, os.path.join(ROOT, "bench", "node_ref.mjs"), dist_js, f.name], capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # pragma: no cover
+        return {"error": str(e)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,6 +151,9 @@ def run_reference(args):
         "e2e": {"value": round(value, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    node = node_reference(data)
+    if node is not None:
+        line["node_zlib_es"] = node  # the reference itself, when a Node runtime exists on the box
     print(json.dumps(line), flush=True)
     return 0
 

@@ -38,7 +38,10 @@ enum {
   ZLES_E_OUTPUT_FULL = 16, /* output buffer too small; *out_len holds the size needed */
   ZLES_E_CUDA = 17,        /* CUDA runtime error (zles_last_cuda_error) */
   ZLES_E_ARG = 18,
-  ZLES_E_NOMEM = 19
+  ZLES_E_NOMEM = 19,
+  ZLES_E_RUNAWAY = 20      /* 'stream never ends': the reference does not return on this input — past the end of the
+                              buffer it reads zero bits for ever (/root/reference/src/utils/BitReadStream.ts:33-35 never
+                              sets isEnd) in a symbol loop that only stops on isEnd (/root/reference/src/inflate.ts:78,237) */
 };
 
 typedef struct zles_ctx zles_ctx;

@@ -36,6 +36,7 @@ const char *zo_strerror(int code) {
     case ZO_E_CORRUPTED: return "Data is corrupted";
     case ZO_E_LACK: return "Lack of data length";
     case ZO_E_NOMEM: return "out of memory";
+    case ZO_E_RUNAWAY: return "stream never ends";
   }
   return "unknown";
 }
@@ -648,6 +649,17 @@ static int decode_symbol(BitReadStream *s, const DecodeTable *t, int *err) {
     *err = ZO_E_LACK;
     return -1;
   }
+  /* NOT in the reference: a guard for inputs on which the reference never returns.  Past the end of the buffer every
+   * bit reads as zero (readRange, src/utils/BitReadStream.ts:33-35) and isEnd is only set by a read() that takes the
+   * last bit of a byte (:21-28).  A symbol loop whose all-zero token is a multiple of 8 bits long and whose read()s avoid
+   * that bit goes on for ever (writing output until the JS heap is exhausted, or nothing at all).  Its state is the bit
+   * offset inside a byte, so 8 tokens (<= 48 bits each) past the end without an exit prove the cycle: a coded symbol
+   * that STARTS 512 or more bits past the end is reported as ZO_E_RUNAWAY.  The GPU decoder applies the same rule
+   * (zlib.es_b200/csrc/inflate.cuh, inf_coded). */
+  if (!s->isEnd) {
+    const unsigned long long P = ((unsigned long long)s->bufferIndex + 1) * 8 - (unsigned long long)s->nowBitsLength;
+    if (P >= (unsigned long long)s->length * 8 + 512) { *err = ZO_E_RUNAWAY; return -1; }
+  }
   int codelen = t->lmin;
   uint32_t code = brs_readRangeCoded(s, t->lmin);
   if (s->err) { *err = s->err; return -1; }
@@ -662,10 +674,18 @@ static int decode_symbol(BitReadStream *s, const DecodeTable *t, int *err) {
   }
 }
 
+/* The match part of the symbol loop, src/inflate.ts:101-116 (fixed) / :260-290 (dynamic).  lenCode 29/30 (symbols
+ * 286/287) and distance codes 30/31 index past the ends of the const.ts tables: JS yields `undefined` there, and
+ *   - `0 < undefined` is false, so no extra bits are read for such a code;
+ *   - an undefined length makes `i < repeatLengthValue` false at once: the distance is still decoded (and its extra
+ *     bits consumed), nothing is written, no error;
+ *   - an undefined distance makes repeatStartIndex NaN, buffer.buffer[NaN + i] is undefined, and
+ *     Uint8WriteStream.write(undefined) stores 0: `len` zero bytes are written, no error. */
 static int copy_match(BitReadStream *s, Uint8WriteStream *b, int lenCode, const DecodeTable *distT, int fixedDist) {
   int err = 0;
-  int len = LENGTH_EXTRA_BIT_BASE[lenCode];
-  if (0 < LENGTH_EXTRA_BIT_LEN[lenCode]) len += (int)brs_readRange(s, LENGTH_EXTRA_BIT_LEN[lenCode]);
+  const int lenDefined = lenCode < 29;
+  int len = lenDefined ? LENGTH_EXTRA_BIT_BASE[lenCode] : 0;
+  if (lenDefined && 0 < LENGTH_EXTRA_BIT_LEN[lenCode]) len += (int)brs_readRange(s, LENGTH_EXTRA_BIT_LEN[lenCode]);
   int dc;
   if (fixedDist) {
     dc = (int)brs_readRangeCoded(s, 5); /* src/inflate.ts:107 */
@@ -674,12 +694,13 @@ static int copy_match(BitReadStream *s, Uint8WriteStream *b, int lenCode, const 
     dc = decode_symbol(s, distT, &err); /* :267-281 */
     if (err) return err;
   }
-  if (dc >= 30) return ZO_E_CORRUPTED; /* DISTANCE_EXTRA_BIT_BASE[30/31] is undefined -> NaN index */
-  int dist = DISTANCE_EXTRA_BIT_BASE[dc];
-  if (0 < DISTANCE_EXTRA_BIT_LEN[dc]) dist += (int)brs_readRange(s, DISTANCE_EXTRA_BIT_LEN[dc]);
+  const int distDefined = dc < 30;
+  int dist = distDefined ? DISTANCE_EXTRA_BIT_BASE[dc] : 0;
+  if (distDefined && 0 < DISTANCE_EXTRA_BIT_LEN[dc]) dist += (int)brs_readRange(s, DISTANCE_EXTRA_BIT_LEN[dc]);
+  if (!lenDefined) return 0;                      /* `i < undefined` never holds */
   long long startIdx = (long long)b->index - dist; /* :287 */
   for (int i = 0; i < len; i++) {                 /* :288-290 */
-    u8ws_write(b, u8ws_at(b, startIdx + i));
+    u8ws_write(b, distDefined ? u8ws_at(b, startIdx + i) : 0);
     if (b->err) return b->err;
   }
   return 0;
@@ -710,7 +731,6 @@ static int inflate_symbols(BitReadStream *s, Uint8WriteStream *b, const DecodeTa
       continue;
     }
     if (v == 256) break;
-    if (v - 257 >= 29) return ZO_E_CORRUPTED; /* LENGTH_EXTRA_BIT_BASE[29/30] undefined */
     err = copy_match(s, b, v - 257, distT, fixedDist);
     if (err) return err;
   }

@@ -35,7 +35,8 @@ enum {
   ZO_E_INSUFFICIENT = 3,  /* 'Data length is insufficient'    src/inflate.ts:35 */
   ZO_E_CORRUPTED = 4,     /* 'Data is corrupted'              src/inflate.ts:50,88,166,247,276; src/deflate.ts:172-224 */
   ZO_E_LACK = 5,          /* 'Lack of data length'            src/utils/BitReadStream.ts:15, BitWriteStream.ts:15 */
-  ZO_E_NOMEM = 6
+  ZO_E_NOMEM = 6,
+  ZO_E_RUNAWAY = 20       /* the reference never returns on this input (see decode_symbol in zlibes_oracle.c) */
 };
 
 const char *zo_strerror(int code);

@@ -84,6 +84,27 @@ def lenient_like_reference(c):
     inflate_matches_oracle(c, b"\x78\xff" + zlib.compress(b"abc" * 50)[2:])
 
 
+def undefined_codes(c):
+    """Literal/length symbols 286/287 copy nothing, distance codes 30.. write zeros — neither is an error in the reference
+    (/root/reference/src/inflate.ts:98-117, 260-290).  Hand-built vectors (tests/golden/make_undefined_vectors.py), then
+    every prefix and random bit flips of them against the oracle, and a stream on which the reference never returns."""
+    vecs = T.undefined_code_vectors()
+    for name, stream, expect in vecs:
+        assert c.inflate(stream) == expect, name
+        assert O.inflate(stream) == expect, name
+    truncation_sweep(c, [s for _, s, _ in vecs])
+    bitflip_sweep(c, [s for _, s, _ in vecs], trials=25, seed=9)
+    runaway = bytes.fromhex("789cfdde010900000080a0adfd3f5047c22592f50800000000")
+    inflate_matches_oracle(c, runaway)
+    try:
+        c.inflate(runaway)
+    except Exception as e:
+        assert str(e) == "stream never ends" and getattr(e, "code", None) == 20
+    else:
+        raise AssertionError("no error for the runaway stream")
+    assert c.inflate_batch([vecs[0][1], runaway, vecs[2][1]], raise_on_error=False)[::2] == [vecs[0][2], vecs[2][2]]
+
+
 def error_strings(c):
     for stream, msg in [(b"\x77\x9c\x03\x00", "Not compressed by deflate"),   # src/zlib.ts:15
                         (b"", "Not compressed by deflate"),

@@ -158,6 +158,10 @@ def test_lenient_and_errors(c):
     P.error_strings(c)
 
 
+def test_codes_the_reference_leaves_undefined(c):
+    P.undefined_codes(c)
+
+
 def test_truncated_and_corrupted_streams_match_the_reference(c):
     streams = P.damaged_streams(c)
     P.truncation_sweep(c, streams[:5], step=41)

@@ -182,6 +182,10 @@ def test_lenient_and_errors(c):
     P.error_strings(c)
 
 
+def test_codes_the_reference_leaves_undefined(c):
+    P.undefined_codes(c)
+
+
 def test_output_full_protocol(c):
     P.output_full_protocol(c)
 

@@ -84,3 +84,53 @@ def test_inflate_lenient_like_reference():
     body = co.compress(b"abcdefghabcdefgh") + co.flush()
     out = O.inflate(b"\x78\x9c" + body)
     assert out == (b"a" + bytes(7)) * 2  # literal 'a', then length-15 match at distance 8 into nothing
+
+
+# ---- codes the reference's tables do not define, and a second reading of the source ----------------------------
+# tests/golden/js_model.py is a line-by-line Python model of src/inflate.ts with JavaScript's `undefined` semantics;
+# tests/golden/undefined_codes.json holds hand-built streams whose expected output was derived from the source by hand
+# (make_undefined_vectors.py).  The C oracle must agree with both.
+
+@pytest.mark.parametrize("vec", T.undefined_code_vectors(), ids=lambda v: v[0])
+def test_undefined_length_and_distance_codes(vec):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import js_model as JS
+    _, stream, expect = vec
+    assert JS.inflate(stream) == expect
+    assert O.inflate(stream) == expect  # no 'Data is corrupted': src/inflate.ts:98-117, 260-290
+
+
+def test_oracle_agrees_with_the_js_model_on_damaged_streams():
+    import os, random, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import js_model as JS
+
+    def outcome(f, z):
+        try:
+            return ("ok", f(z))
+        except (O.OracleError, JS.JsError) as e:
+            return ("err", str(e))
+
+    rnd = random.Random(1)
+    d = T.gen("G5", 400)
+    co = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)
+    streams = [zlib.compress(d, 6), O.deflate(d), zlib.compress(T.gen("G3", 100), 0), T.FIXED, T.DYNAMIC, co.compress(d) + co.flush()]
+    streams += [s for _, s, _ in T.undefined_code_vectors()]
+    for z in streams:
+        for cut in range(0, len(z) + 1, 3):
+            assert outcome(O.inflate, z[:cut]) == outcome(JS.inflate, z[:cut]), ("cut", cut, z.hex())
+        for _ in range(60):
+            zz = bytearray(z)
+            for _k in range(rnd.choice([1, 1, 1, 2, 3])):
+                zz[rnd.randrange(len(zz))] ^= 1 << rnd.randrange(8)
+            assert outcome(O.inflate, bytes(zz)) == outcome(JS.inflate, bytes(zz)), bytes(zz).hex()
+
+
+def test_stream_on_which_the_reference_never_returns():
+    # past the end of the buffer the reference reads zero bits for ever unless a read() lands on the last bit of a byte
+    # (src/utils/BitReadStream.ts:21-28,33-35); this damaged stream makes its symbol loop cycle without writing anything.
+    # The oracle (and the GPU decoder) report it instead of hanging: 'stream never ends'.
+    z = bytes.fromhex("789cfdde010900000080a0adfd3f5047c22592f50800000000")
+    with pytest.raises(O.OracleError, match="stream never ends"):
+        O.inflate(z)

@@ -15,6 +15,13 @@ FIXED = bytes(V["FIXED"])
 DYNAMIC = bytes(V["DYNAMIC"])
 
 
+def undefined_code_vectors():
+    """Hand-built streams that use literal/length symbols 286/287 and distance codes 30.. (tests/golden/make_undefined_vectors.py):
+    [(name, stream, expected output)]."""
+    doc = json.load(open(os.path.join(GOLD, "undefined_codes.json")))
+    return [(v["name"], bytes.fromhex(v["stream"]), bytes.fromhex(v["expect"])) for v in doc["vectors"]]
+
+
 def repeat_input() -> bytes:
     rep = ""
     while len(rep) < 1000:

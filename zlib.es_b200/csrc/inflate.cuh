@@ -35,6 +35,7 @@ constexpr u32 SEG_E_BTYPE3 = 2;    // 'Not supported BTYPE : 3'        src/infla
 constexpr u32 SEG_E_INSUFF = 3;    // 'Data length is insufficient'    src/inflate.ts:35
 constexpr u32 SEG_E_CORRUPT = 4;   // 'Data is corrupted'              src/inflate.ts:50,88,166,247,276
 constexpr u32 SEG_E_LACK = 5;      // 'Lack of data length'            src/utils/BitReadStream.ts:15
+constexpr u32 SEG_E_RUNAWAY = 20;  // the reference never returns on this input (inf_coded); ZLES_E_RUNAWAY
 constexpr u32 SEGF_HISTORY = 1;    // a distance reached before the segment start
 constexpr u32 SEGF_OVERFLOW = 2;   // output did not fit (out_len is still the true length)
 
@@ -55,10 +56,11 @@ struct InfWarpSmem {
   u16 lut_ll[1 << LL_ROOT];
   u16 lut_d[1 << D_ROOT];  // doubles as the code-length-code LUT while a header is parsed
   u16 sorted_ll[288];
-  u16 sorted_d[32];
+  u16 sorted_d[64];
   InfTab tab_ll, tab_d;
   u16 cur[16];
-  u8 lens[320];  // [0,288) literal/length code lengths, [288,320) distance code lengths
+  u8 lens[352];  // [0,288) literal/length code lengths, [288,352) distance code lengths (a run of the code-length
+                 // code may spill up to 5 symbols past HDIST <= 32 — src/inflate.ts:187-200 keeps them, so do we)
   u8 cl_lens[32];
 };
 constexpr int INF_SMEM = (int)(sizeof(InfWarpSmem) + sizeof(InfRes)) * INF_WARPS;  // per-warp tables | per-warp result (batch kernel)
@@ -210,15 +212,23 @@ __device__ __forceinline__ u32 inf_coded(InfReader &r, const u16 *lut, int root,
   bool found = true;
   if (l == 0) found = inf_slow(r.bb, t, sorted, sym, l);
   const u64 P = r.bitpos();
+  u32 L = l;
+  if (!found) {  // the reference reads up to the longest code of the table before giving up
+    L = 0;
+    for (int k = 15; k >= 1; k--)
+      if (t->cnt[k]) { L = (u32)k; break; }
+    // empty table: codelenMin stays Number.MAX_SAFE_INTEGER (src/inflate.ts:139-147, 206-224) and readRangeCoded reads
+    // bit after bit until read() throws at the end of the buffer, wherever in the stream this happens
+    if (L == 0) return SEG_E_LACK;
+  }
   if (P + 64 >= nbits) {  // only near the end of the buffer can the bookkeeping matter
     if (is_end) return SEG_E_LACK;
-    u32 L = l;
-    if (!found) {  // the reference reads up to the longest code of the table before giving up
-      L = 0;
-      for (int k = 15; k >= 1; k--)
-        if (t->cnt[k]) { L = (u32)k; break; }
-      if (L == 0) return SEG_E_LACK;  // empty table: it reads until the buffer ends
-    }
+    // Past the end every bit reads as zero and isEnd is only set by a read() that takes the last bit of a byte: a symbol
+    // loop whose all-zero token is a multiple of 8 bits long and avoids that bit never ends in the reference (it writes
+    // until the JS heap is gone, or nothing at all).  The decoder's state is then its bit offset inside a byte, so a
+    // coded symbol that STARTS >= 512 bits past the end (8 tokens of <= 48 bits without an exit) proves the cycle.
+    // The oracle reports it at exactly the same point (oracle/zlibes_oracle.c, decode_symbol).
+    if (P >= nbits + 512) return SEG_E_RUNAWAY;
     const u64 x0 = P > nbits - 1 ? P : nbits - 1;
     const u64 E = x0 + ((7 - (x0 & 7)) & 7);  // first bit position >= x0 that is the last bit of a byte
     if (E < P + L - 1) return SEG_E_LACK;     // a read() after the one that reached the end
@@ -249,7 +259,7 @@ __device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSme
   const u32 HDIST = r.take(5) + 1;
   const u32 HCLEN = r.take(4) + 4;
   S->cl_lens[lane] = 0;
-  for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
+  for (u32 i = lane; i < 352; i += 32) S->lens[i] = 0;
   __syncwarp();
   for (u32 i = 0; i < HCLEN; i++) {
     r.refill();
@@ -274,7 +284,7 @@ __device__ __forceinline__ bool inf_read_dynamic_header(InfReader &r, InfWarpSme
       for (u32 k = lane; k < rep; k += 32) {
         u32 j = i + k;
         if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
-        else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
+        else if (j - HLIT < 64) S->lens[288 + j - HLIT] = (u8)val;
       }
     }
     i += rep;
@@ -322,13 +332,14 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
       continue;
     }
     if (btype == 1) {  // fixed, src/huffman.ts:41-53, src/inflate.ts:57-118
-      for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+      // (the distance is readRangeCoded(5), src/inflate.ts:107: 32 codes of 5 bits)
+      for (u32 i = lane; i < 352; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : i < 320 ? 5 : 0);
       __syncwarp();
     } else {  // dynamic header, src/inflate.ts:121-202
       if (!inf_read_dynamic_header(r, S, nbits, is_end, stale, status)) break;
     }
     inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
-    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+    inf_build(S->lens + 288, 64, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
 
     // symbol loop, src/inflate.ts:76-117 / 237-291: `while (!stream.isEnd)`
     while (!is_end) {
@@ -342,16 +353,29 @@ __device__ __forceinline__ void inf_segment(InfWarpSmem *S, const u8 *in, u64 n,
         continue;
       }
       if (sym == 256) break;
+      // Length codes 29/30 (symbols 286/287) and distance codes >= 30 index past the ends of the reference's tables
+      // (src/const.ts:9-31): base and extra-bit count are `undefined` there, `0 < undefined` is false (no extra bits
+      // are read), an undefined length makes the copy loop `i < undefined` do nothing — the distance is still decoded —
+      // and an undefined distance makes the source index NaN, so `len` zeros are written (src/inflate.ts:101-116,
+      // 260-290).  Neither is an error.
       const u32 ls = sym - 257;
-      if (ls >= 29) { status = SEG_E_CORRUPT; break; }
-      const u32 len = c_len_base[ls] + inf_extra(r, c_len_extra[ls], stale);
+      const bool len_def = ls < 29;
+      const u32 len = len_def ? c_len_base[ls] + inf_extra(r, c_len_extra[ls], stale) : 0;
       r.refill();
       u32 ds;
       rc = inf_coded(r, S->lut_d, D_ROOT, &S->tab_d, S->sorted_d, nbits, is_end, stale, ds);
       if (rc) { status = rc; break; }
-      if (ds >= 30) { status = SEG_E_CORRUPT; break; }
       r.refill();
-      const u32 dist = c_dist_base[ds] + inf_extra(r, c_dist_extra[ds], stale);
+      const bool dist_def = ds < 30;
+      const u32 dist = dist_def ? c_dist_base[ds] + inf_extra(r, c_dist_extra[ds], stale) : 0;
+      if (!len_def) continue;
+      if (!dist_def) {
+        for (u32 i = lane; i < len; i += 32)
+          if (opos + i < cap) out[opos + i] = 0;
+        opos += len;
+        __syncwarp();
+        continue;
+      }
       // back-reference copy, src/inflate.ts:287-290; bytes before the start read as 0
       const long long src = (long long)opos - (long long)dist;
       if (src < (long long)obase) flags |= SEGF_HISTORY;
@@ -652,7 +676,7 @@ __device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem
   const u32 HDIST = r.take(5) + 1;
   const u32 HCLEN = r.take(4) + 4;
   S->cl_lens[lane] = 0;
-  for (u32 i = lane; i < 320; i += 32) S->lens[i] = 0;
+  for (u32 i = lane; i < 352; i += 32) S->lens[i] = 0;
   __syncwarp();
   for (u32 i = 0; i < HCLEN; i++) {
     r.refill();
@@ -680,6 +704,9 @@ __device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem
         if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
         else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
       }
+      // a run that gives distance symbols 32.. a length (it spills past HDIST = 32): the reference keeps those codes
+      // (src/inflate.ts:187-200); the parallel tiers do not model them — such a block is left to the sequential decoder
+      if (i + rep > HLIT + 32) { status = SEG_E_CORRUPT; return false; }
     }
     i += rep;
   }

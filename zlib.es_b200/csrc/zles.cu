@@ -207,6 +207,7 @@ extern "C" const char *zles_strerror(int code) {
     case ZLES_E_CUDA: return "CUDA error";
     case ZLES_E_ARG: return "invalid argument";
     case ZLES_E_NOMEM: return "out of memory";
+    case ZLES_E_RUNAWAY: return "stream never ends";
   }
   return "unknown error";
 }
@@ -722,6 +723,7 @@ static int seg_status_to_code(u32 st) {
     case SEG_E_INSUFF: return ZLES_E_INSUFFICIENT;
     case SEG_E_CORRUPT: return ZLES_E_CORRUPTED;
     case SEG_E_LACK: return ZLES_E_LACK;
+    case SEG_E_RUNAWAY: return ZLES_E_RUNAWAY;
   }
   return ZLES_E_CORRUPTED;
 }

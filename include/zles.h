@@ -66,6 +66,9 @@ int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, 
  * pass.  0: the block before it, like blocks 1 and 3 — three passes per chunk, ~25 % slower, output ~1.4 % smaller on text.
  * Either way the stream stays within 3 % of the reference's size on the benchmark corpora ("Size"). */
 int zles_ctx_set_window_mode(zles_ctx *ctx, uint32_t mode);
+/* Host-buffer inflate of our own streams runs slab by slab (finished slabs are copied to the host while the next one is
+ * decoded): blocks of 32 KiB per slab, a multiple of 4; 0 (default) = automatic (a quarter of the stream, 16..256 MiB). */
+int zles_ctx_set_slab_blocks(zles_ctx *ctx, uint32_t blocks);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the context's
@@ -142,6 +145,38 @@ uint32_t zles_adler32_combine_shards(const zles_shard_info *infos, uint32_t coun
  * shard that ends on a block boundary before the stream's last block. */
 int zles_dev_inflate_segment(zles_ctx *ctx, const uint8_t *d_in, size_t n, int has_final, uint8_t *d_out, size_t cap,
                              size_t *out_len);
+
+/* ---- one process, several GPUs (sharding behind the drop-in boundary) --------------
+ * The reference is a synchronous library inside ONE process (/root/reference/src/zlib.ts:11-49); a Node process that
+ * loads the addon can only use more than one GPU if the library shards below this ABI.  A zles_mgpu owns a context and
+ * a worker thread per device.  Host buffers in, host buffers out, same results byte for byte as the single-device calls
+ * (chunks are independent; shards are contiguous runs of whole 128 KiB chunks):
+ *   deflate  every device compresses its shard; one host-side exchange of the shards' compressed sizes (what the
+ *            multi-process form all-gathers over NCCL) places every shard in the caller's buffer;
+ *   inflate  the shards are found from the stream itself (marker scan of equal byte slices on every device), decoded
+ *            slab by slab with the copies back overlapped.  Streams that are not ours go to device 0's general path.
+ * zles_init(device_mask) installs a process-wide zles_mgpu over the devices whose bit is set (bit d = CUDA device d) as
+ * the default that zles_deflate / zles_inflate / zles_inflate_alloc use when ctx is NULL — what the N-API addon calls at
+ * load time with ZLES_DEVICES; mask 0 or 1 keeps the single-device default.  zles_shutdown releases the defaults. */
+typedef struct zles_mgpu zles_mgpu;
+int zles_init(uint32_t device_mask);
+void zles_shutdown(void);
+int zles_mgpu_create(const int *devices, int count, zles_mgpu **out);
+void zles_mgpu_destroy(zles_mgpu *m);
+int zles_mgpu_device_count(const zles_mgpu *m);
+/* Inputs with fewer than `bytes` per device use fewer devices (default 4 MiB). */
+int zles_mgpu_set_min_shard(zles_mgpu *m, size_t bytes);
+zles_ctx *zles_mgpu_ctx(zles_mgpu *m, int index);   /* the context of device `index` (encoder settings, timing) */
+uint64_t zles_mgpu_launches(const zles_mgpu *m);
+int zles_mgpu_deflate(zles_mgpu *m, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_mgpu_inflate(zles_mgpu *m, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_mgpu_inflate_alloc(zles_mgpu *m, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len);
+
+/* Block starts of one of our streams, found from the bytes themselves: `first` and every position in d_in[0 .. n) that
+ * follows a 00 00 FF FF marker (ascending, relative to d_in, starts[0] = first).  The sharded inflate runs it on every
+ * rank's slice of the compressed bytes and all-gathers the results (zlib.es_b200/dist.py, inflate_from_stream).
+ * ZLES_E_OUTPUT_FULL: *count holds the number found; ZLES_E_CORRUPTED: more candidates than a stream of ours can have. */
+int zles_dev_scan_blocks(zles_ctx *ctx, const uint8_t *d_in, size_t n, uint64_t first, uint64_t *starts, size_t cap, size_t *count);
 
 /* CUDA IPC helpers so that another process can map a device buffer (64-byte handles). */
 int zles_ipc_export(const void *d_ptr, uint8_t handle[64]);

@@ -207,3 +207,52 @@ def foreign_tier(c, n):
         c.set_timing(False)
         assert out == O.inflate(z), name
         assert used >= 1 and seq == 0, (name, used, seq)
+
+
+def multi_device(c, mc, n):
+    """One process, several devices (zles_mgpu_*): the stream is bit for bit the single-device one, inflate finds its
+    shards from the stream itself, other encoders' streams and damaged ones give the reference's outcome through the
+    fallback, and the output-size protocol holds.  `mc` may name the same device several times (one-GPU boxes)."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    data = (T.fixture_raw() + T.gen("G5", n // 2) + bytes(n // 8) + rng.integers(0, 256, n // 8, dtype=np.uint8).tobytes() + T.gen("G5", n))[:n]
+    mc.set_min_shard(65536)
+    z = mc.deflate(data)
+    assert z == c.deflate(data)
+    assert zlib.decompress(z) == data
+    for slab in (0, 8, 64):
+        mc.set_slab_blocks(slab)
+        assert mc.inflate(z) == data, slab
+    mc.set_slab_blocks(0)
+    for cut in (n // 3, 131072 * 3, 131072 * 3 + 1, 100, 0):  # ragged sizes, fewer chunks than devices, empty
+        d = data[:cut]
+        zz = mc.deflate(d)
+        assert zz == c.deflate(d) and mc.inflate(zz) == d, cut
+    assert mc.inflate(zlib.compress(data, 6)) == data
+    assert mc.inflate(O.deflate(data[:300000])) == data[:300000]
+    small = np.zeros(n - 1, dtype=np.uint8)
+    try:
+        mc.inflate_into(z, small)
+    except Exception as e:
+        assert getattr(e, "code", None) == 16, e
+    else:
+        raise AssertionError("inflate into n - 1 bytes succeeded")
+    out = np.zeros(n, dtype=np.uint8)
+    assert mc.inflate_into(z, out) == n and out.tobytes() == data
+    for cut in (len(z) // 2, len(z) - 3, 100):
+        assert _outcome(O.inflate, z[:cut]) == _outcome(mc.inflate, z[:cut]), cut
+    zz = bytearray(z)
+    zz[len(z) // 3] ^= 4
+    assert _outcome(O.inflate, bytes(zz)) == _outcome(mc.inflate, bytes(zz))
+
+
+def slabbed_host_inflate(c, n):
+    """zles_inflate of one of our streams decodes slab by slab (copies back overlapped): same bytes for every slab size."""
+    data = (T.gen("G5", n // 2) + T.fixture_raw() * 3 + bytes(n))[:n]
+    z = c.deflate(data)
+    for slab in (4, 8, 12, 0):
+        c.set_slab_blocks(slab)
+        try:
+            assert c.inflate(z) == data, slab
+        finally:
+            c.set_slab_blocks(0)

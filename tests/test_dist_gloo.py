@@ -54,6 +54,25 @@ def _worker(rank, world, port, total, q):
         n = sc.inflate(stage.ctypes.data, out.ctypes.data, b - a)
         assert n == b - a and out[:n].tobytes() == data[a:b]
         dist.barrier()
+        # the same stream decoded WITHOUT the encoder's layout: shards found from the bytes (marker scan + all-gather).
+        # The stream in the shared buffer is replaced by the single-call one first (made by "a different world size").
+        if rank == 0:
+            whole = np.frombuffer(c.deflate(data), dtype=np.uint8)
+            assert whole.size == lay.total_comp
+            __import__("ctypes").memmove(sc.t.base, whole.ctypes.data, whole.size)
+        dist.barrier()
+        cap = c.deflate_bound(total) + 64
+        sl = np.zeros(cap, dtype=np.uint8)
+        rg = np.zeros(cap, dtype=np.uint8)
+        out2 = np.zeros(b - a + 16, dtype=np.uint8)
+        n2 = sc.inflate_from_stream(lay.total_comp, sl.ctypes.data, rg.ctypes.data, cap, out2.ctypes.data, b - a)
+        if total >= 131072 * world:
+            assert n2 == b - a and out2[:n2].tobytes() == data[a:b], (rank, n2, b - a)
+        else:  # fewer chunks than ranks: the chunks go where shard_bounds over the BLOCK count puts them
+            got = __import__("torch").tensor([n2])
+            dist.all_reduce(got)
+            assert int(got) == total
+        dist.barrier()
         sc.teardown()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover

@@ -212,3 +212,16 @@ def test_sharded_phases_match_single_call(c):
     stream = b"\x78\x9c" + b"".join(parts) + adler.to_bytes(4, "big")
     assert stream == whole
     assert zlib.decompress(stream) == data
+
+
+def test_multi_device_context(c):
+    import zles
+    mc = zles.MultiCodec([0, 0, 0], lib=c.L)
+    try:
+        P.multi_device(c, mc, 1200000)
+    finally:
+        mc.close()
+
+
+def test_host_inflate_in_slabs(c):
+    P.slabbed_host_inflate(c, 1500000)

@@ -256,3 +256,20 @@ def test_sharded_phases_match_single_call(c):
         n = c.dev_inflate_segment(d_in.data_ptr(), len(part), d_out.data_ptr(), d_out.numel(), has_final=k == len(parts) - 1)
         assert n == cuts[k + 1] - cuts[k]
         assert d_out.cpu().numpy().tobytes() == data[cuts[k]:cuts[k + 1]]
+
+
+def test_multi_device_context(c):
+    # zles_mgpu_*: one process driving several devices; on a one-GPU box the same device is named three times, which
+    # exercises the same sharding, exchange and stream-discovered inflate
+    import torch
+    import zles
+    ndev = torch.cuda.device_count()
+    mc = zles.MultiCodec(list(range(ndev)) if ndev > 1 else [0, 0, 0])
+    try:
+        P.multi_device(c, mc, 24 << 20)
+    finally:
+        mc.close()
+
+
+def test_host_inflate_in_slabs(c):
+    P.slabbed_host_inflate(c, 40 << 20)

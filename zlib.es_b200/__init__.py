@@ -14,7 +14,7 @@ shim at the repository root (``import zles``).
 """
 from __future__ import annotations
 
-from .codec import (Codec, ZlesError, adler32, default_codec, deflate, deflate_batch, inflate, inflate_batch)  # noqa: F401
+from .codec import (Codec, MultiCodec, ZlesError, adler32, default_codec, deflate, deflate_batch, inflate, inflate_batch)  # noqa: F401
 from . import _capi  # noqa: F401
 
-__all__ = ["deflate", "inflate", "adler32", "deflate_batch", "inflate_batch", "Codec", "ZlesError", "default_codec"]
+__all__ = ["deflate", "inflate", "adler32", "deflate_batch", "inflate_batch", "Codec", "MultiCodec", "ZlesError", "default_codec"]

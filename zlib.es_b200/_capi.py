@@ -36,7 +36,19 @@ PROTOTYPES = {
     "zles_ctx_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "zles_ctx_set_level": (ctypes.c_int, [c_vp, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]),
     "zles_ctx_set_window_mode": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
+    "zles_ctx_set_slab_blocks": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
     "zles_ctx_launches": (ctypes.c_uint64, [c_vp]),
+    "zles_init": (ctypes.c_int, [ctypes.c_uint32]),
+    "zles_shutdown": (None, []),
+    "zles_mgpu_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "zles_mgpu_destroy": (None, [c_vp]),
+    "zles_mgpu_device_count": (ctypes.c_int, [c_vp]),
+    "zles_mgpu_set_min_shard": (ctypes.c_int, [c_vp, ctypes.c_size_t]),
+    "zles_mgpu_ctx": (c_vp, [c_vp, ctypes.c_int]),
+    "zles_mgpu_launches": (ctypes.c_uint64, [c_vp]),
+    "zles_mgpu_deflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_mgpu_inflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_mgpu_inflate_alloc": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp), c_szp]),
     "zles_ctx_set_timing": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "zles_ctx_kernel_time": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "zles_dev_alloc": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
@@ -62,6 +74,7 @@ PROTOTYPES = {
     "zles_dev_deflate_phase2": (ctypes.c_int, [c_vp, c_vp]),
     "zles_adler32_combine_shards": (ctypes.c_uint32, [ctypes.POINTER(ShardInfo), ctypes.c_uint32]),
     "zles_dev_inflate_segment": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_dev_scan_blocks": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_uint64, c_vp, ctypes.c_size_t, c_szp]),
     "zles_ipc_export": (ctypes.c_int, [c_vp, c_vp]),
     "zles_ipc_open": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "zles_ipc_close": (ctypes.c_int, [c_vp]),
@@ -71,7 +84,7 @@ PROTOTYPES = {
 
 # status codes of include/zles.h
 OK, E_NOT_DEFLATE, E_BTYPE3, E_INSUFFICIENT, E_CORRUPTED, E_LACK = 0, 1, 2, 3, 4, 5
-E_OUTPUT_FULL, E_CUDA, E_ARG, E_NOMEM = 16, 17, 18, 19
+E_OUTPUT_FULL, E_CUDA, E_ARG, E_NOMEM, E_RUNAWAY = 16, 17, 18, 19, 20
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:

@@ -79,6 +79,10 @@ class Codec:
     def set_level(self, max_checks: int, min_checks: int, good_len: int, lazy: bool = True):
         self._check(self.L.zles_ctx_set_level(self.h, max_checks, min_checks, good_len, 1 if lazy else 0))
 
+    def set_slab_blocks(self, blocks: int):
+        """Blocks of 32 KiB per slab of the host-buffer inflate of our own streams (0 = automatic)."""
+        self._check(self.L.zles_ctx_set_slab_blocks(self.h, blocks))
+
     def set_stream(self, cuda_stream: int):
         self._check(self.L.zles_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
         self.stream_ptr = cuda_stream  # the caller's stream the codec's kernels are ordered on (None: its own)
@@ -276,6 +280,14 @@ class Codec:
         self._check(self.L.zles_dev_inflate_segment(self.h, d_in, n, 1 if has_final else 0, d_out, cap, ctypes.byref(olen)))
         return olen.value
 
+    def dev_scan_blocks(self, d_in: int, n: int, first: int) -> np.ndarray:
+        """Block starts of one of our streams in d_in[0 .. n) (uint64, relative to d_in; [0] = first)."""
+        cap = n // 32 + 64
+        out = np.empty(cap, dtype=np.uint64)
+        cnt = ctypes.c_size_t()
+        self._check(self.L.zles_dev_scan_blocks(self.h, d_in, n, first, out.ctypes.data, cap, ctypes.byref(cnt)))
+        return out[:cnt.value]
+
     def dev_corpus(self, kind: int, offset: int, d_out: int, n: int):
         self._check(self.L.zles_dev_corpus(self.h, kind, offset, d_out, n))
 
@@ -283,6 +295,80 @@ class Codec:
         out = np.empty(n, dtype=np.uint8)
         self._check(self.L.zles_host_corpus(kind, offset, out.ctypes.data, n))
         return out
+
+
+class MultiCodec:
+    """One process, several GPUs (zles_mgpu_*, include/zles.h): the same ``deflate`` / ``inflate`` on host buffers, the input's
+    128 KiB chunks sharded over the devices inside the library.  Results are byte for byte those of ``Codec``."""
+
+    def __init__(self, devices: Sequence[int], lib: ctypes.CDLL | None = None):
+        self.L = lib if lib is not None else _capi.lib()
+        arr = (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        self._check(self.L.zles_mgpu_create(arr, len(devices), ctypes.byref(h)))
+        self.h = h
+        self.devices = list(devices)
+
+    _check = Codec._check
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.zles_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.zles_mgpu_launches(self.h))
+
+    def set_min_shard(self, nbytes: int):
+        self._check(self.L.zles_mgpu_set_min_shard(self.h, nbytes))
+
+    def set_slab_blocks(self, blocks: int):
+        for i in range(len(self.devices)):
+            self._check(self.L.zles_ctx_set_slab_blocks(ctypes.c_void_p(self.L.zles_mgpu_ctx(self.h, i)), blocks))
+
+    def deflate_bound(self, n: int) -> int:
+        return int(self.L.zles_deflate_bound(n))
+
+    def deflate(self, data) -> bytes:
+        p, n, keep = _addr(data)
+        cap = self.deflate_bound(n)
+        out = np.empty(cap, dtype=np.uint8)
+        olen = ctypes.c_size_t()
+        self._check(self.L.zles_mgpu_deflate(self.h, p, n, out.ctypes.data, cap, ctypes.byref(olen)))
+        del keep
+        return out[:olen.value].tobytes()
+
+    def inflate(self, data) -> bytes:
+        p, n, keep = _addr(data)
+        optr = ctypes.c_void_p()
+        olen = ctypes.c_size_t()
+        self._check(self.L.zles_mgpu_inflate_alloc(self.h, p, n, ctypes.byref(optr), ctypes.byref(olen)))
+        del keep
+        try:
+            return ctypes.string_at(optr.value, olen.value)
+        finally:
+            self.L.zles_free(optr)
+
+    def deflate_into(self, data, out: np.ndarray) -> int:
+        p, n, keep = _addr(data)
+        olen = ctypes.c_size_t()
+        self._check(self.L.zles_mgpu_deflate(self.h, p, n, out.ctypes.data, out.size, ctypes.byref(olen)))
+        del keep
+        return olen.value
+
+    def inflate_into(self, data, out: np.ndarray) -> int:
+        p, n, keep = _addr(data)
+        olen = ctypes.c_size_t()
+        self._check(self.L.zles_mgpu_inflate(self.h, p, n, out.ctypes.data, out.size, ctypes.byref(olen)))
+        del keep
+        return olen.value
 
 
 def combine_adler(infos: Sequence[_capi.ShardInfo], lib: ctypes.CDLL | None = None) -> int:

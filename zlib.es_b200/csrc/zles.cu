@@ -105,6 +105,7 @@ struct zles_ctx {
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
   u32 pair_mode = 1;  // zles_ctx_set_window_mode
+  u32 inf_slab_blocks = 0;  // host-buffer inflate of our own streams: blocks per slab (inflate_slabs_to_host); 0 = automatic
   DevBuf unit_ctr;    // k_lz hands its units out from this counter
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
@@ -158,6 +159,8 @@ static bool debug_sync() {
 static void debug_check(zles_ctx *c, const char *kern);
 
 static int resolve_ctx(zles_ctx *&c);
+struct zles_mgpu;
+static zles_mgpu *default_mgpu();  // mgpu.inl: the multi-GPU default installed by zles_init(device_mask), or null
 
 static zrt_event_t timing_event(zles_ctx *c) {
   if (!c->event_pool.empty()) { zrt_event_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
@@ -312,6 +315,12 @@ extern "C" int zles_ctx_set_window_mode(zles_ctx *c, uint32_t mode) {
   return 0;
 }
 
+extern "C" int zles_ctx_set_slab_blocks(zles_ctx *c, uint32_t blocks) {
+  if (!c || (blocks && blocks < SUBS_PER_CHUNK) || blocks > (1u << 20)) return ZLES_E_ARG;
+  c->inf_slab_blocks = (blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+  return 0;
+}
+
 extern "C" uint64_t zles_ctx_launches(const zles_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int zles_ctx_set_timing(zles_ctx *c, int on) {
@@ -437,6 +446,8 @@ struct DeflatePipe {
   u8 *d_out;      // device staging for the raw deflate bytes (room for zles_deflate_bound)
   u8 *h_out;      // caller's buffer for them
   size_t h_cap;   // its capacity in bytes
+  bool defer = false;  // pack slab by slab into d_out but leave the copy to the host to the caller (multi-GPU: a shard's
+                       // place in the stream is only known once every shard before it has been laid out)
   bool done = false, overflow = false;
 };
 
@@ -508,7 +519,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   const u32 nslabs = (u32)slab_begin.size() - 1;
   const bool piped = pipe && h_src && nslabs > 1;
   std::vector<zrt_event_t> slab_ev;
-  if (piped) {
+  if (piped && !pipe->defer) {
     if (c->slab_mail_cap < nslabs) {
       if (c->slab_mail) zrt_host_free(c->slab_mail);
       c->slab_mail = nullptr;
@@ -516,8 +527,8 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
       CK(zrt_host_alloc(reinterpret_cast<void **>(&c->slab_mail), (size_t)nslabs * 8));
       c->slab_mail_cap = nslabs;
     }
-    CK(zrt_memset(c->summary.p, 0, 64, c->stream));  // summary[4] carries the running offset between slabs
   }
+  if (piped) CK(zrt_memset(c->summary.p, 0, 64, c->stream));  // summary[4] carries the running offset between slabs
   for (u32 si = 0; si < nslabs; si++) {
     const u32 b0 = slab_begin[si], b1 = slab_begin[si + 1];
     if (h_src) {
@@ -550,13 +561,16 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
       pp.in = d_in;
       pp.n = n;
       LAUNCH(c, k_pack, b1 - b0, PACK_THREADS, PACK_SMEM, pp);
-      CK(zrt_d2h(c->slab_mail + si, c->summary.as<u64>() + 5, 8, c->stream));
-      zrt_event_t ev = timing_event(c);
-      CK(zrt_event_record(ev, c->stream));
-      slab_ev.push_back(ev);
+      if (!pipe->defer) {
+        CK(zrt_d2h(c->slab_mail + si, c->summary.as<u64>() + 5, 8, c->stream));
+        zrt_event_t ev = timing_event(c);
+        CK(zrt_event_record(ev, c->stream));
+        slab_ev.push_back(ev);
+      }
     }
   }
-  if (piped) {
+  if (piped && pipe->defer) pipe->done = true;
+  if (piped && !pipe->defer) {
     // the GPU works through the slabs in order; as each one's end offset arrives, its bytes go to the caller's buffer
     u64 prev = 0;
     for (u32 si = 0; si < nslabs; si++) {
@@ -688,6 +702,8 @@ extern "C" int zles_dev_deflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint
 
 extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
   if ((!in && n) || !out_len) return ZLES_E_ARG;
+  if (!c)
+    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_deflate(m, in, n, out, cap, out_len);
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
   zles_shard_info info;
@@ -956,8 +972,9 @@ static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8
 }
 
 // Steps 2.. of inflate.  On success *out_len = decoded size.  ZLES_E_OUTPUT_FULL: *out_len = size needed.
+// ours_only: give up (ZLES_E_CORRUPTED) instead of trying the other tiers when the bytes are not a run of our own blocks.
 static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 ncand_all, u32 cand_cap, u8 *d_out, size_t cap,
-                          size_t *out_len, bool has_final = true) {
+                          size_t *out_len, bool has_final = true, bool ours_only = false) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   bool fast = ncand_all >= 1 && ncand_all <= cand_cap;
   const u32 ncand = ncand_all;
@@ -1037,7 +1054,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     }
   }
 
-  if (!has_final) return ZLES_E_CORRUPTED;  // a shard of one of our streams must have decoded above
+  if (!has_final || ours_only) return ZLES_E_CORRUPTED;  // a shard / slab of one of our streams must have decoded above
 
   // 3b. a stream from another encoder (zlib.es itself, system zlib): find the dynamic blocks, decode them in
   //     parallel, chain them up.  Only a complete, consistent chain that ends in a BFINAL block is accepted;
@@ -1073,10 +1090,90 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
   }
 }
 
-static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len, bool has_final = true) {
+static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len, bool has_final = true,
+                        bool ours_only = false) {
   u32 ncand = 0, cand_cap = 0;
   RET(inflate_scan(c, d_in, n, first, &ncand, &cand_cap));
-  return inflate_decode(c, d_in, n, first, ncand, cand_cap, d_out, cap, out_len, has_final);
+  return inflate_decode(c, d_in, n, first, ncand, cand_cap, d_out, cap, out_len, has_final, ours_only);
+}
+
+
+// ---- host-buffer inflate of OUR streams, slab by slab ----------------------------------------------
+// The blocks of our own streams are byte aligned (every one ends with the 00 00 FF FF marker), 32 KiB of output each,
+// and chunks of four never refer to one another.  So a long run of them can be decoded a slab of whole chunks at a
+// time: while slab k is decoded on the context's stream, slab k - 1 (final once decoded) travels to the host on the
+// copy stream — the device-to-host copy of the output no longer waits for the whole decode.
+// d_in[0 .. n): marker-delimited blocks whose starts (relative to d_in, ascending, starts[0] = first block) are given;
+// the run stands for whole chunks except for its last block when has_final.  Output goes to h_out (capacity h_cap).
+// Returns 0, ZLES_E_OUTPUT_FULL (*out_len = size needed), ZLES_E_CUDA, or -1: not decodable this way (the caller then
+// runs the general path on the same device bytes).
+constexpr size_t INF_SLAB_MIN_STREAM = 1u << 16;  // shorter streams are not worth the extra scan
+constexpr u32 INF_SLAB_BLOCKS = 8192;  // 256 MiB of output per slab (the four-warp phase A takes up to 8,192 blocks)
+static int inflate_slabs_to_host(zles_ctx *c, const u8 *d_in, size_t n, const std::vector<u64> &starts, bool has_final, u8 *h_out, size_t h_cap,
+                                 size_t *out_len, u32 slab_blocks = INF_SLAB_BLOCKS) {
+  const size_t B = starts.size();
+  if (B == 0) return -1;
+  // every block but the last stands for exactly 32 KiB: when those cannot fit, the general path reports the exact size
+  if (B > 1 && (u64)(B - 1) * SUB > (u64)h_cap) return -1;
+  slab_blocks = (slab_blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+  if (slab_blocks == 0) slab_blocks = SUBS_PER_CHUNK;
+  const size_t slab_out = (size_t)slab_blocks * SUB;
+  RET(c->d_out.reserve(2 * slab_out + 32));
+  zrt_event_t done[2] = {timing_event(c), timing_event(c)}, copied[2] = {timing_event(c), timing_event(c)};
+  bool copied_valid[2] = {false, false};
+  int rc = 0;
+  size_t total = 0;
+  u32 k = 0;
+  for (size_t b0 = 0; b0 < B && rc == 0; b0 += slab_blocks, k++) {
+    const size_t b1 = b0 + slab_blocks < B ? b0 + slab_blocks : B;
+    const bool last = b1 == B;
+    const u64 in1 = last ? (u64)n : starts[b1];
+    const u64 al = (starts[b0] + (u64)((uintptr_t)d_in & 15)) & 15;  // the slab's bytes from a 16-byte aligned address on
+    const u64 in0 = starts[b0] - al;                                  // (al <= starts[b0]: device buffers are 256-byte aligned)
+    u8 *d_slab = c->d_out.as<u8>() + (size_t)(k & 1) * (slab_out + 16);
+    const size_t off = b0 * (size_t)SUB;
+    const size_t cap = off >= h_cap ? 0 : (h_cap - off < slab_out ? h_cap - off : slab_out);
+    if (copied_valid[k & 1]) CK(zrt_stream_wait_event(c->stream, copied[k & 1]));  // the copy out of this buffer (slab k - 2) is done
+    size_t olen = 0;
+    rc = inflate_body(c, d_in + in0, (size_t)(in1 - in0), al, d_slab, cap, &olen, has_final && last, /*ours_only=*/true);
+    if (rc == ZLES_E_OUTPUT_FULL) { total = off + olen; break; }
+    if (rc) break;
+    if (!(last && has_final) && olen != (b1 - b0) * (size_t)SUB) { rc = -1; break; }
+    CK(zrt_event_record(done[k & 1], c->stream));
+    CK(zrt_stream_wait_event(c->copy_stream, done[k & 1]));
+    if (olen) CK(zrt_d2h(h_out + off, d_slab, olen, c->copy_stream));
+    CK(zrt_event_record(copied[k & 1], c->copy_stream));
+    copied_valid[k & 1] = true;
+    total = off + olen;
+  }
+  zrt_err_t e = zrt_sync(c->copy_stream);
+  for (int i = 0; i < 2; i++) { c->event_pool.push_back(done[i]); c->event_pool.push_back(copied[i]); }
+  if (e != ZRT_OK) return cuda_fail(e, "copy to host");
+  *out_len = total;
+  if (rc == ZLES_E_OUTPUT_FULL || rc == ZLES_E_CUDA) return rc;
+  return rc ? -1 : 0;
+}
+
+// blocks per slab for a run of B blocks: the context's setting, or (0 = automatic) a quarter of the run, between 16 MiB
+// and 256 MiB of output — enough work per slab to fill the GPU, enough slabs for the copies to overlap
+static u32 inflate_slab_size(const zles_ctx *c, size_t B) {
+  if (c->inf_slab_blocks) return c->inf_slab_blocks;
+  size_t q = (B / 4 / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+  if (q < 512) q = 512;
+  if (q > INF_SLAB_BLOCKS) q = INF_SLAB_BLOCKS;
+  return (u32)q;
+}
+
+// The block starts of one of our streams, on the host: candidates found by the marker scan of d_in[0 .. n) (first = where
+// the first block starts).  Returns 0 and fills `starts`, or -1 when the scan says "not ours" (too many candidates).
+static int scan_block_starts(zles_ctx *c, const u8 *d_in, size_t n, u64 first, std::vector<u64> &starts) {
+  u32 ncand = 0, cand_cap = 0;
+  RET(inflate_scan(c, d_in, n, first, &ncand, &cand_cap));
+  if (ncand == 0 || ncand > cand_cap) return -1;
+  starts.resize(ncand);
+  CK(zrt_d2h(starts.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+  CK(zrt_sync(c->stream));
+  return 0;
 }
 
 // header check of zlib.inflate (src/zlib.ts:12-16): only CM is looked at.
@@ -1106,12 +1203,38 @@ extern "C" int zles_dev_inflate_segment(zles_ctx *c, const uint8_t *d_in, size_t
   return inflate_body(c, d_in, n, 0, d_out, cap, out_len, has_final != 0);
 }
 
+extern "C" int zles_dev_scan_blocks(zles_ctx *c, const uint8_t *d_in, size_t n, uint64_t first, uint64_t *starts, size_t cap, size_t *count) {
+  if ((!d_in && n) || !count || (!starts && cap)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  std::vector<u64> v;
+  const int rs = scan_block_starts(c, d_in, n, first, v);
+  if (rs > 0) return rs;
+  if (rs < 0) { *count = 0; return ZLES_E_CORRUPTED; }  // more candidates than one of our streams can hold
+  *count = v.size();
+  if (v.size() > cap) return ZLES_E_OUTPUT_FULL;
+  memcpy(starts, v.data(), v.size() * 8);
+  return 0;
+}
+
 extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
   if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
+  if (!c)
+    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_inflate(m, in, n, out, cap, out_len);
   RET(check_zlib_header(in, n));
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
   if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  {
+    // one of our own streams, long enough to be worth it: decode slab by slab, copying finished slabs out meanwhile
+    std::vector<u64> starts;
+    int rs = n >= INF_SLAB_MIN_STREAM ? scan_block_starts(c, c->d_in.as<u8>(), n, 2, starts) : -1;
+    if (rs > 0) return rs;
+    const u32 slab = inflate_slab_size(c, starts.size());
+    if (rs == 0 && starts.size() >= 2 * (size_t)slab) {
+      int rc = inflate_slabs_to_host(c, c->d_in.as<u8>(), n, starts, true, out, cap, out_len, slab);
+      if (rc >= 0) return rc;
+    }
+  }
   RET(c->d_out.reserve(cap + 16));
   int rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, out_len);
   if (rc) return rc;
@@ -1122,6 +1245,8 @@ extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *o
 
 extern "C" int zles_inflate_alloc(zles_ctx *c, const uint8_t *in, size_t n, uint8_t **out, size_t *out_len) {
   if ((!in && n) || !out || !out_len) return ZLES_E_ARG;
+  if (!c)
+    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_inflate_alloc(m, in, n, out, out_len);
   *out = nullptr;
   *out_len = 0;
   RET(check_zlib_header(in, n));
@@ -1442,6 +1567,8 @@ extern "C" int zles_dev_corpus(zles_ctx *c, int kind, uint64_t offset, uint8_t *
   CK(zrt_sync(c->stream));
   return 0;
 }
+
+#include "mgpu.inl"
 
 #ifdef ZLES_STAGE_CLOCKS
 // profiling build only (tools/lz_stages.py): per-stage cycle totals of k_lz, summed over CTAs

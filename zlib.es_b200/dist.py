@@ -188,3 +188,56 @@ class ShardedCodec:
         n = lay.comp[self.rank]
         self.c.dev_copy_async(d_stage, self.t.base + 2 + lay.offsets[self.rank], n)  # peer read of this shard's bytes
         return self.c.dev_inflate_segment(d_stage, n, d_out, cap, has_final=self.rank == self.world - 1)
+
+    def inflate_from_stream(self, total_comp: int, d_slice: int, d_range: int, stage_cap: int, d_out: int, cap: int) -> int:
+        """The same without any knowledge of how the stream was made (a consumer that only holds the zlib bytes,
+        /root/reference/src/zlib.ts:11-23): the stream of ``total_comp`` bytes lies at ``self.t.base`` on rank 0.  Every rank
+        pulls an equal slice of its bytes and scans it for block markers; ONE all-gather of the block starts; block j stands
+        for output bytes [32 KiB j, 32 KiB (j + 1)) and chunks of four blocks are independent, so rank r takes the chunks
+        ``shard_bounds`` gives it, completes the bytes of its range it does not hold yet (peer read) and decodes them into
+        d_out.  d_slice / d_range: local scratch of stage_cap bytes each.  Returns the decoded length of this rank's shard.
+        Works for a stream made by any number of ranks (or by the single-device call)."""
+        n, R, r = total_comp, self.world, self.rank
+        sb = [0] + [((2 + (n - 2) * k // R) & ~15) for k in range(1, R)] + [n]
+        lo, hi = (0 if r == 0 else sb[r] - 16), sb[r + 1]
+        if hi - lo > stage_cap:
+            raise RuntimeError("scratch too small for the slice: need %d, have %d" % (hi - lo, stage_cap))
+        self.c.dev_copy_async(d_slice, self.t.base + lo, hi - lo)
+        mine = self.c.dev_scan_blocks(d_slice, hi - lo, 2 if r == 0 else 15)
+        mine = (mine[1:] if r else mine) + np.uint64(lo)  # cand[0] is the scan's `first`: a block only for the stream's first slice
+        # the one exchange: counts, then the (padded) lists
+        dev = self.comm_device
+        with self._ordered():
+            cnt = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
+            cnts = torch.empty(R, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(cnts, cnt, group=self.group)
+            counts = cnts.cpu().tolist()
+            width = max(1, max(counts))
+            pad = np.zeros(width, dtype=np.int64)
+            pad[:len(mine)] = mine.astype(np.int64)
+            allpos = torch.empty(R * width, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allpos, torch.from_numpy(pad).to(dev), group=self.group)
+            allpos = allpos.cpu().numpy().reshape(R, width)
+        starts = np.concatenate([allpos[k, :counts[k]] for k in range(R)]).astype(np.uint64)
+        B = len(starts)
+        if B == 0 or (B > 1 and not bool((starts[1:] > starts[:-1]).all())):
+            raise RuntimeError("not one of our streams")
+        nchunks = (B + 3) // 4
+        bb = [min(B, (nchunks * k // R) * 4) for k in range(R)] + [B]
+        if bb[r] == bb[r + 1]:
+            return 0
+        a = int(starts[bb[r]]) & ~15
+        b = n if r == R - 1 else int(starts[bb[r + 1]])
+        if b - a > stage_cap:
+            raise RuntimeError("scratch too small for the range: need %d, have %d" % (b - a, stage_cap))
+        ia, ib = max(a, lo), min(b, hi)
+        if ia < ib:  # what the slice already holds moves locally; the rest is read from the owner
+            self.c.dev_copy_async(d_range + (ia - a), d_slice + (ia - lo), ib - ia)
+            if a < ia:
+                self.c.dev_copy_async(d_range, self.t.base + a, ia - a)
+            if ib < b:
+                self.c.dev_copy_async(d_range + (ib - a), self.t.base + ib, b - ib)
+        else:
+            self.c.dev_copy_async(d_range, self.t.base + a, b - a)
+        first = int(starts[bb[r]]) - a
+        return self.c.dev_inflate_segment(d_range + first, b - a - first, d_out, cap, has_final=r == R - 1)

@@ -308,8 +308,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the codec has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     multi = world > 1
+    host_group = None
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        host_group = dist.new_group(backend="gloo")  # waits that must not keep a GPU busy (an NCCL barrier spins on the device)
     c = zles.Codec(local)
     stream = torch.cuda.Stream()
     c.set_stream(stream.cuda_stream)
@@ -414,7 +416,8 @@ def run_ours(args):
         sc = None
     torch.cuda.empty_cache()
     if multi:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
     e2e = None
     pageable = None
     if rank == 0:
@@ -467,7 +470,7 @@ def run_ours(args):
         if multi:
             codec.close()
     if multi:
-        dist.barrier()
+        dist.barrier(group=host_group)  # the other ranks wait on the host: their GPUs belong to rank 0's multi-GPU context meanwhile
 
     # ---- max over ranks --------------------------------------------------------------------------
     vals = torch.tensor([td / args.steps, ti / args.steps, float(launches), lz_ms / max(1, lz_n), tok_ms / max(1, args.steps), res_ms / max(1, args.steps)],

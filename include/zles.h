@@ -39,6 +39,7 @@ enum {
   ZLES_E_CUDA = 17,        /* CUDA runtime error (zles_last_cuda_error) */
   ZLES_E_ARG = 18,
   ZLES_E_NOMEM = 19,
+  ZLES_E_CHECKSUM = 21,    /* zles_gzip_inflate only: CRC-32 or ISIZE of the trailer do not match the data */
   ZLES_E_RUNAWAY = 20      /* 'stream never ends': the reference does not return on this input — past the end of the
                               buffer it reads zero bits for ever (/root/reference/src/utils/BitReadStream.ts:33-35 never
                               sets isEnd) in a symbol loop that only stops on isEnd (/root/reference/src/inflate.ts:78,237) */
@@ -57,9 +58,10 @@ void zles_ctx_destroy(zles_ctx *ctx);
 /* Use an existing CUDA stream (cudaStream_t passed as void*) instead of the context's own. */
 int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
 /* Encoder search depth (the reference's FAST_INDEX_CHECK_MAX, /root/reference/src/lz77.ts:7, scaled for an
- * all-positions search): max_checks = candidates compared per position (1..32, default 32); lazy = defer a match by
- * one literal when the next position has a longer one (default 1).  min_checks and good_len are reserved (ignored):
- * the nearest candidate of the longest class is the one that is extended. */
+ * all-positions search): max_checks = candidates compared per position (1..32, default 32; larger values are clamped
+ * to 32); lazy = defer a match by one literal when the next position has a longer one (default 1).  min_checks and
+ * good_len are accepted for signature compatibility with the reference's constants and have NO effect: the nearest
+ * candidate of the longest class is the one that is extended. */
 int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
 /* Which window the third 32 KiB block of a 128 KiB chunk sees (/root/reference/src/lz77.ts:49 gives every position the
  * 32 KiB before it inside its chunk).  1 (default): none, like block 0 — blocks {0,1} and {2,3} each share one match-finder
@@ -99,10 +101,29 @@ void zles_free(void *p);
 /* calcAdler32 >>> 0 (/root/reference/src/adler32.ts:1-10). */
 int zles_adler32(zles_ctx *ctx, const uint8_t *in, size_t n, uint32_t *adler);
 
+/* ---- wire-format siblings behind the same kernels --------------------------------
+ * raw:  the deflate data alone (RFC 1951) — what the reference's deflate core returns (/root/reference/src/deflate.ts:14)
+ *       and what its inflate(input, offset = 0) reads from byte `offset` on (/root/reference/src/inflate.ts:16).
+ * gzip: RFC 1952 — 10-byte header (no name, no time), the same deflate data, CRC-32 and ISIZE (little endian).
+ *       zles_gzip_inflate reads one member (any header flags), takes the trailer from the last eight bytes of the buffer and
+ *       verifies both fields (ZLES_E_CHECKSUM); other errors are those of zles_inflate.  Use zles_deflate_bound for `cap`.
+ * zles_crc32 is the container's checksum (IEEE 802.3), computed on the GPU in shard-combinable form:
+ * crc32(A || B) = zles_crc32_combine(crc32(A), crc32(B), len(B)). */
+int zles_deflate_raw(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_inflate_raw(zles_ctx *ctx, const uint8_t *in, size_t n, size_t offset, uint8_t *out, size_t cap, size_t *out_len);
+int zles_gzip_deflate(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_gzip_inflate(zles_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len);
+int zles_crc32(zles_ctx *ctx, const uint8_t *in, size_t n, uint32_t *crc);
+int zles_dev_crc32(zles_ctx *ctx, const uint8_t *d_in, size_t n, uint32_t *crc);
+uint32_t zles_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+
 /* ---- batches of independent buffers (BASELINE config 3: 262,144 x 4 KiB) --------
  * Buffer i is in[in_off[i] .. in_off[i+1]); its result is written at out + out_off[i]
  * (capacity out_off[i+1] - out_off[i]) and its length to out_len[i]; status[i] gets
- * the per-buffer code.  Host pointers. Returns the first non-zero status. */
+ * the per-buffer code.  Host pointers.  Returns 0 when every buffer succeeded, ZLES_E_CUDA / ZLES_E_ARG / ZLES_E_NOMEM when
+ * the call as a whole failed (status[] is then untouched), otherwise the LARGEST per-buffer status — e.g. OUTPUT_FULL (16)
+ * hides CORRUPTED (4): inspect status[], do not branch on the return value alone.  For inflate, out_len[i] of a buffer
+ * with status OUTPUT_FULL holds the size it needs; only the bytes actually produced are copied back to the host. */
 int zles_deflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
                        const uint64_t *out_off, uint64_t *out_len, int32_t *status);
 int zles_inflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,

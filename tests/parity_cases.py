@@ -256,3 +256,44 @@ def slabbed_host_inflate(c, n):
             assert c.inflate(z) == data, slab
         finally:
             c.set_slab_blocks(0)
+
+
+def wire_format_siblings(c, n):
+    """raw deflate data (the reference's cores, /root/reference/src/deflate.ts:14 and src/inflate.ts:16 with its
+    `offset` parameter) and gzip (RFC 1952, CRC-32) behind the same kernels — against system zlib / Python gzip / the oracle."""
+    import gzip
+    import io
+    import os
+    rnd = os.urandom
+    for m in (0, 1, 5, 15, 16, 17, 127, 128, 129, 32767, 32768, 32769, 100000, n):
+        d = rnd(m)
+        assert c.crc32(d) == zlib.crc32(d), m
+        assert c.crc32(memoryview(b"xyz" + d)[3:]) == zlib.crc32(d), m  # a source that is not 16-byte aligned
+    a, b = rnd(1000), rnd(77777)
+    assert c.L.zles_crc32_combine(zlib.crc32(a), zlib.crc32(b), len(b)) == zlib.crc32(a + b)
+    data = (T.fixture_raw() + T.gen("G5", n))[:n]
+    r = c.deflate_raw(data)
+    assert r == c.deflate(data)[2:-4]                     # the same deflate data as inside the zlib container
+    assert zlib.decompress(r, -15) == data and O.inflate_raw(r) == data
+    assert c.inflate_raw(r) == data and c.inflate_raw(b"junk!" + r, 5) == data   # inflate(input, offset), src/inflate.ts:16
+    assert c.inflate_raw(zlib.compress(data, 6)[2:-4]) == data
+    zo = O.deflate(data[:200000])
+    assert c.inflate_raw(zo, 2) == data[:200000]
+    g = c.gzip_deflate(data)
+    assert gzip.decompress(g) == data and zlib.decompress(g, 31) == data
+    assert g[10:-8] == r
+    assert c.gzip_inflate(g) == data
+    assert c.gzip_inflate(gzip.compress(data, 6)) == data
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="name.txt", mode="wb", fileobj=buf, mtime=12345) as f:
+        f.write(data)
+    assert c.gzip_inflate(buf.getvalue()) == data         # FNAME set
+    assert c.gzip_inflate(c.gzip_deflate(b"")) == b""
+    for damage, code in ((lambda z: z[:-6] + bytes([z[-6] ^ 1]) + z[-5:], 21), (lambda z: z[:-1] + bytes([z[-1] ^ 1]), 21),
+                         (lambda z: b"\x1f\x8b\x07" + z[3:], 1), (lambda z: z[:5], 5)):
+        try:
+            c.gzip_inflate(damage(g))
+        except Exception as e:
+            assert getattr(e, "code", None) == code, (code, e)
+        else:
+            raise AssertionError("no error")

@@ -273,3 +273,7 @@ def test_multi_device_context(c):
 
 def test_host_inflate_in_slabs(c):
     P.slabbed_host_inflate(c, 40 << 20)
+
+
+def test_raw_deflate_and_gzip(c):
+    P.wire_format_siblings(c, 20971527)

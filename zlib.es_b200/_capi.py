@@ -62,6 +62,13 @@ PROTOTYPES = {
     "zles_inflate_alloc": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp), c_szp]),
     "zles_free": (None, [c_vp]),
     "zles_adler32": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
+    "zles_deflate_raw": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_inflate_raw": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_gzip_deflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_gzip_inflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
+    "zles_crc32": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
+    "zles_dev_crc32": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]),
+    "zles_crc32_combine": (ctypes.c_uint32, [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]),
     "zles_deflate_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "zles_inflate_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_uint32, c_vp, c_vp, c_vp, c_vp]),
     "zles_dev_deflate": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_szp]),
@@ -84,7 +91,7 @@ PROTOTYPES = {
 
 # status codes of include/zles.h
 OK, E_NOT_DEFLATE, E_BTYPE3, E_INSUFFICIENT, E_CORRUPTED, E_LACK = 0, 1, 2, 3, 4, 5
-E_OUTPUT_FULL, E_CUDA, E_ARG, E_NOMEM, E_RUNAWAY = 16, 17, 18, 19, 20
+E_OUTPUT_FULL, E_CUDA, E_ARG, E_NOMEM, E_RUNAWAY, E_CHECKSUM = 16, 17, 18, 19, 20, 21
 
 
 def bind(lib: ctypes.CDLL) -> ctypes.CDLL:

@@ -181,6 +181,52 @@ class Codec:
         del keep
         return int(v.value)
 
+    # -- wire-format siblings: raw deflate data and gzip ---------------------------------------
+    def _deflate_fmt(self, fn, data) -> bytes:
+        p, n, keep = _addr(data)
+        cap = self.deflate_bound(n) + 16
+        out = np.empty(cap, dtype=np.uint8)
+        olen = ctypes.c_size_t()
+        self._check(fn(self.h, p, n, out.ctypes.data, cap, ctypes.byref(olen)))
+        del keep
+        return out[:olen.value].tobytes()
+
+    def _inflate_fmt(self, call, n: int) -> bytes:
+        cap = n * 10 + 131072  # the reference's initial guess (src/inflate.ts:17); retried once with the exact size
+        for _ in range(2):
+            out = np.empty(cap, dtype=np.uint8)
+            olen = ctypes.c_size_t()
+            rc = call(out.ctypes.data, cap, ctypes.byref(olen))
+            if rc == _capi.E_OUTPUT_FULL:
+                cap = olen.value
+                continue
+            self._check(rc)
+            return out[:olen.value].tobytes()
+        self._check(rc)
+
+    def deflate_raw(self, data) -> bytes:
+        """The reference's deflate core (/root/reference/src/deflate.ts:14): raw RFC 1951 data, no container."""
+        return self._deflate_fmt(self.L.zles_deflate_raw, data)
+
+    def inflate_raw(self, data, offset: int = 0) -> bytes:
+        """The reference's inflate core, ``inflate(input, offset = 0)`` (/root/reference/src/inflate.ts:16)."""
+        p, n, keep = _addr(data)
+        return self._inflate_fmt(lambda o, cap, olen: self.L.zles_inflate_raw(self.h, p, n, offset, o, cap, olen), n)
+
+    def gzip_deflate(self, data) -> bytes:
+        return self._deflate_fmt(self.L.zles_gzip_deflate, data)
+
+    def gzip_inflate(self, data) -> bytes:
+        p, n, keep = _addr(data)
+        return self._inflate_fmt(lambda o, cap, olen: self.L.zles_gzip_inflate(self.h, p, n, o, cap, olen), n)
+
+    def crc32(self, data) -> int:
+        p, n, keep = _addr(data)
+        v = ctypes.c_uint32()
+        self._check(self.L.zles_crc32(self.h, p, n, ctypes.byref(v)))
+        del keep
+        return int(v.value)
+
     # -- batches of independent buffers ----------------------------------------------------
     def deflate_batch(self, bufs: Sequence) -> list[bytes]:
         """``[deflate(b) for b in bufs]`` in one launch sequence."""

@@ -24,6 +24,7 @@
 #include "adler32.cuh"
 #include "corpus.cuh"
 #include "corpus_text.h"
+#include "crc32.cuh"
 #include "huffman.cuh"
 #include "inflate.cuh"
 #include "inflate_foreign.cuh"
@@ -120,6 +121,8 @@ struct zles_ctx {
   u64 *slab_mail = nullptr;  // pinned: where each slab of a pipelined host-buffer deflate ends (bytes)
   size_t slab_mail_cap = 0;
   CorpusTable *d_corpus = nullptr;
+  CrcTables *d_crc = nullptr;  // CRC-32 tables (gzip), uploaded on first use
+  DevBuf crc_part;
   // per-kernel timing
   bool timing = false;
   struct TimedLaunch { const char *name; zrt_event_t e0, e1; };
@@ -157,6 +160,15 @@ static bool debug_sync() {
   return on;
 }
 static void debug_check(zles_ctx *c, const char *kern);
+
+// ZLES_TRACE=1 in the environment: host-side timestamps of the host-buffer calls on stderr (where does the wall time go)
+#include <chrono>
+static bool trace_on() {
+  static const bool on = [] { const char *e = getenv("ZLES_TRACE"); return e && *e && *e != '0'; }();
+  return on;
+}
+static double trace_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TRACE(...) do { if (trace_on()) { fprintf(stderr, "[zles %.3f] ", trace_now()); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } } while (0)
 
 static int resolve_ctx(zles_ctx *&c);
 struct zles_mgpu;
@@ -211,6 +223,7 @@ extern "C" const char *zles_strerror(int code) {
     case ZLES_E_ARG: return "invalid argument";
     case ZLES_E_NOMEM: return "out of memory";
     case ZLES_E_RUNAWAY: return "stream never ends";
+    case ZLES_E_CHECKSUM: return "gzip checksum mismatch";
   }
   return "unknown error";
 }
@@ -263,7 +276,7 @@ extern "C" int zles_ctx_create(int device, zles_ctx **out) {
   c->sm_count = zrt_sm_count(device);
   void *m = nullptr;
   e = zrt_host_alloc(&m, sizeof(HostMail));
-  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
+  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
   c->mail = reinterpret_cast<HostMail *>(m);
   memset(c->mail, 0, sizeof(HostMail));
   int rc = set_kernel_attrs(device);
@@ -285,6 +298,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   timing_collect(c);
   for (zrt_event_t e : c->event_pool) zrt_event_destroy(e);
   if (c->d_corpus) zrt_free(c->d_corpus);
+  if (c->d_crc) zrt_free(c->d_crc);
+  c->crc_part.release();
   if (c->mail) zrt_host_free(c->mail);
   if (c->own_stream) zrt_stream_destroy(c->stream);
   zrt_stream_destroy(c->copy_stream);
@@ -302,6 +317,7 @@ extern "C" int zles_ctx_set_stream(zles_ctx *c, void *cuda_stream) {
 
 extern "C" int zles_ctx_set_level(zles_ctx *c, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy) {
   if (!c || max_checks == 0) return ZLES_E_ARG;
+  if (max_checks > LZ_SCAN) max_checks = LZ_SCAN;  // the matcher compares at most LZ_SCAN candidates per position (and relies on it)
   c->max_checks = max_checks;
   c->min_checks = min_checks ? min_checks : 1;
   c->good_len = good_len;
@@ -407,7 +423,7 @@ static int dev_adler32(zles_ctx *c, const u8 *d_in, size_t n, uint32_t *adler) {
   }
   LAUNCH(c, k_adler_final, 1, 32, 0, acc, (u64)n, reinterpret_cast<u32 *>(acc + 2));
   CK(zrt_last_error());
-  CK(zrt_d2h(&c->mail->adler, acc + 2, 4, c->stream));
+  CK(zrt_mail(&c->mail->adler, acc + 2, 4, c->stream));
   CK(zrt_sync(c->stream));
   *adler = c->mail->adler;
   return 0;
@@ -506,11 +522,16 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     if (!h_src || wave == 0 || nblocks < 4 * wave) {
       slab_begin = {0, nblocks};
     } else {
+      // slabs double from one wave up to an eighth of the input (at least 4, at most 64 waves): a long input gets slabs
+      // with dozens of units per CTA — every launch ends with a tail in which the last CTAs finish alone
+      u32 cap_sz = (nblocks / 8 / wave) * wave;
+      if (cap_sz < 4 * wave) cap_sz = 4 * wave;
+      if (cap_sz > 64 * wave) cap_sz = 64 * wave;
       u32 b = 0, sz = wave;
       while (b < nblocks) {
         slab_begin.push_back(b);
         b += sz;
-        if (sz < 4 * wave) sz *= 2;
+        if (sz < cap_sz) sz = sz * 2 < cap_sz ? sz * 2 : cap_sz;
       }
       if (nblocks - slab_begin.back() < wave && slab_begin.size() > 1) slab_begin.pop_back();  // no sliver at the end
       slab_begin.push_back(nblocks);
@@ -562,7 +583,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
       pp.n = n;
       LAUNCH(c, k_pack, b1 - b0, PACK_THREADS, PACK_SMEM, pp);
       if (!pipe->defer) {
-        CK(zrt_d2h(c->slab_mail + si, c->summary.as<u64>() + 5, 8, c->stream));
+        CK(zrt_mail(c->slab_mail + si, c->summary.as<u64>() + 5, 8, c->stream));
         zrt_event_t ev = timing_event(c);
         CK(zrt_event_record(ev, c->stream));
         slab_ev.push_back(ev);
@@ -599,7 +620,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   LAUNCH(c, k_layout, 1, 1024, LAYOUT_SMEM, yp);
   CK(zrt_last_error());
 
-  CK(zrt_d2h(c->mail->summary, c->summary.p, 24, c->stream));
+  CK(zrt_mail(c->mail->summary, c->summary.p, 24, c->stream));
   CK(zrt_sync(c->stream));
   c->p1_valid = true;
   c->p1_in = d_in;
@@ -700,35 +721,119 @@ extern "C" int zles_dev_deflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint
   return 0;
 }
 
-extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
-  if ((!in && n) || !out_len) return ZLES_E_ARG;
-  if (!c)
-    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_deflate(m, in, n, out, cap, out_len);
+// ---- CRC-32 (gzip's checksum; crc32.cuh) --------------------------------------------------------
+static int dev_crc32(zles_ctx *c, const u8 *d_in, size_t n, uint32_t *crc) {
+  if (!c->d_crc) {
+    CrcTables *T = new (std::nothrow) CrcTables();
+    if (!T) return ZLES_E_NOMEM;
+    crc_tables_build(T);
+    void *p = nullptr;
+    zrt_err_t e = zrt_malloc(&p, sizeof(CrcTables));
+    if (e == ZRT_OK) e = zrt_h2d(p, T, sizeof(CrcTables), c->stream);
+    if (e == ZRT_OK) e = zrt_sync(c->stream);
+    delete T;
+    if (e != ZRT_OK) { if (p) zrt_free(p); return cuda_fail(e, "CRC tables"); }
+    c->d_crc = reinterpret_cast<CrcTables *>(p);
+  }
+  const u32 skew = (u32)((uintptr_t)d_in & 15);
+  const u8 *base = d_in - skew;
+  const u64 nfull = ((u64)skew + n) / CRC_PER_BLOCK;
+  RET(c->crc_part.reserve((size_t)(nfull + 1) * 4 + 16));
+  u32 *part = c->crc_part.as<u32>();
+  if (nfull) {
+    const u32 grid = (u32)umin64(nfull, (u64)c->sm_count * 8);
+    LAUNCH(c, k_crc_partial, grid, CRC_THREADS, CRC_SMEM, base, skew, nfull, (const CrcTables *)c->d_crc, part);
+  }
+  LAUNCH(c, k_crc_final, 1, 1024, CRC_FINAL_SMEM, base, skew, (u64)n, nfull, (const u32 *)part, (const CrcTables *)c->d_crc, part + nfull);
+  CK(zrt_last_error());
+  CK(zrt_mail(&c->mail->adler, part + nfull, 4, c->stream));
+  CK(zrt_sync(c->stream));
+  *crc = c->mail->adler;
+  return 0;
+}
+
+extern "C" int zles_dev_crc32(zles_ctx *c, const uint8_t *d_in, size_t n, uint32_t *crc) {
+  if (!crc || (!d_in && n)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  return dev_crc32(c, d_in, n, crc);
+}
+
+extern "C" int zles_crc32(zles_ctx *c, const uint8_t *in, size_t n, uint32_t *crc) {
+  if (!crc || (!in && n)) return ZLES_E_ARG;
+  RET(resolve_ctx(c));
+  RET(c->d_in.reserve(n + 16));
+  if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
+  return dev_crc32(c, c->d_in.as<u8>(), n, crc);
+}
+
+extern "C" uint32_t zles_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) { return crc_combine(crc_a, crc_b, len_b); }
+
+// ---- containers around the raw deflate data ---------------------------------------------------------
+// zlib (RFC 1950): 78 9C | data | Adler-32 big endian — what the reference writes (/root/reference/src/zlib.ts:25-49).
+// raw  (RFC 1951): data only — the reference's deflate core (/root/reference/src/deflate.ts:14) and its
+//                  inflate(input, offset) (/root/reference/src/inflate.ts:16).
+// gzip (RFC 1952): 10-byte header | data | CRC-32 | ISIZE, both little endian — the sibling format.
+enum { FMT_ZLIB = 0, FMT_RAW = 1, FMT_GZIP = 2 };
+static size_t fmt_head(int fmt) { return fmt == FMT_ZLIB ? 2 : fmt == FMT_GZIP ? 10 : 0; }
+static size_t fmt_tail(int fmt) { return fmt == FMT_ZLIB ? 4 : fmt == FMT_GZIP ? 8 : 0; }
+static void put_le32(u8 *p, u32 v) { p[0] = (u8)v; p[1] = (u8)(v >> 8); p[2] = (u8)(v >> 16); p[3] = (u8)(v >> 24); }
+static u32 get_le32(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
+static void put_gzip_header(u8 *p) {
+  // ID1 ID2 CM=8 FLG=0 MTIME=0 XFL=0 OS=255 (unknown)
+  static const u8 h[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 255};
+  memcpy(p, h, 10);
+}
+
+static int deflate_host(zles_ctx *c, int fmt, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  const size_t H = fmt_head(fmt), T = fmt_tail(fmt);
   RET(resolve_ctx(c));
   RET(c->d_in.reserve(n + 16));
   zles_shard_info info;
   DeflatePipe pipe;
   DeflatePipe *pp = nullptr;
-  if (out && cap >= 6 && c->d_out.reserve(zles_deflate_bound(n) + 16) == 0) {  // raw deflate bytes go to out + 2 .. cap - 4
+  if (out && cap >= H + T && c->d_out.reserve(zles_deflate_bound(n) + 16) == 0) {  // raw deflate bytes go to out + H .. cap - T
     pipe.d_out = c->d_out.as<u8>() + 2;
-    pipe.h_out = out + 2;
-    pipe.h_cap = cap - 6;
+    pipe.h_out = out + H;
+    pipe.h_cap = cap - H - T;
     pp = &pipe;
   }
   // the host-to-device copy is pipelined with the matcher, and (long inputs) packing and the copy back with it too
   RET(deflate_phase1(c, c->d_in.as<u8>(), n, 1, &info, in, pp));
-  const size_t need = (size_t)info.comp_bytes + 6;
+  const size_t need = (size_t)info.comp_bytes + H + T;
   *out_len = need;
   if (!out || cap < need) return ZLES_E_OUTPUT_FULL;
   if (!pipe.done || pipe.overflow) {
     RET(c->d_out.reserve(need + 16));
     RET(deflate_phase2(c, c->d_out.as<u8>() + 2));
-    CK(zrt_d2h(out + 2, c->d_out.as<u8>() + 2, info.comp_bytes, c->stream));
+    CK(zrt_d2h(out + H, c->d_out.as<u8>() + 2, info.comp_bytes, c->stream));
   }
-  put_zlib_header(out);
-  put_be32(out + need - 4, zles_adler32_combine_shards(&info, 1));
+  if (fmt == FMT_ZLIB) {
+    put_zlib_header(out);
+    put_be32(out + need - 4, zles_adler32_combine_shards(&info, 1));
+  } else if (fmt == FMT_GZIP) {
+    u32 crc = 0;
+    RET(dev_crc32(c, c->d_in.as<u8>(), n, &crc));  // the input is in device memory: its CRC-32 costs no extra copy
+    put_gzip_header(out);
+    put_le32(out + need - 8, crc);
+    put_le32(out + need - 4, (u32)n);  // ISIZE = length mod 2^32
+  }
   CK(zrt_sync(c->stream));
   return 0;
+}
+
+extern "C" int zles_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len) return ZLES_E_ARG;
+  if (!c)
+    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_deflate(m, in, n, out, cap, out_len);
+  return deflate_host(c, FMT_ZLIB, in, n, out, cap, out_len);
+}
+extern "C" int zles_deflate_raw(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len) return ZLES_E_ARG;
+  return deflate_host(c, FMT_RAW, in, n, out, cap, out_len);
+}
+extern "C" int zles_gzip_deflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len) return ZLES_E_ARG;
+  return deflate_host(c, FMT_GZIP, in, n, out, cap, out_len);
 }
 
 // ---- inflate (K6/K7) ---------------------------------------------------------------------
@@ -785,7 +890,7 @@ static int inflate_scan(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 *n
     LAUNCH(c, k_mark_none, 1, 32, 0, first, c->cand.as<u64>(), &ctl->ncand);
   }
   CK(zrt_last_error());
-  CK(zrt_d2h(&c->mail->ncand, &ctl->ncand, 4, c->stream));
+  CK(zrt_mail(&c->mail->ncand, &ctl->ncand, 4, c->stream));
   CK(zrt_sync(c->stream));
   *ncand_all = c->mail->ncand;
   *cand_cap_out = cand_cap;
@@ -793,7 +898,7 @@ static int inflate_scan(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 *n
 }
 
 static int read_ctl(zles_ctx *c, InfCtl *h) {
-  CK(zrt_d2h(&c->mail->summary[0], c->ctl.p, sizeof(InfCtl), c->stream));
+  CK(zrt_mail(&c->mail->summary[0], c->ctl.p, sizeof(InfCtl), c->stream));
   CK(zrt_sync(c->stream));
   memcpy(h, &c->mail->summary[0], sizeof(InfCtl));
   return 0;
@@ -1080,7 +1185,7 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
     LAUNCH(c, k_inflate, 1, INF_THREADS, INF_SMEM, d_in, (u64)n, (const u64 *)c->seg_pos.as<u64>(), (const u64 *)c->seg_off.as<u64>(),
            (const u32 *)&ctl->ncand, 1u, d_out, (u64)cap, 0, c->res.as<InfRes>(), &ctl->counter);
     CK(zrt_last_error());
-    CK(zrt_d2h(&c->mail->res0, c->res.p, sizeof(InfRes), c->stream));
+    CK(zrt_mail(&c->mail->res0, c->res.p, sizeof(InfRes), c->stream));
     CK(zrt_sync(c->stream));
     const InfRes r = c->mail->res0;
     if (r.status != SEG_FINAL) return seg_status_to_code(r.status);
@@ -1135,7 +1240,9 @@ static int inflate_slabs_to_host(zles_ctx *c, const u8 *d_in, size_t n, const st
     const size_t cap = off >= h_cap ? 0 : (h_cap - off < slab_out ? h_cap - off : slab_out);
     if (copied_valid[k & 1]) CK(zrt_stream_wait_event(c->stream, copied[k & 1]));  // the copy out of this buffer (slab k - 2) is done
     size_t olen = 0;
+    TRACE("slab %u: blocks [%zu, %zu) begin", k, b0, b1);
     rc = inflate_body(c, d_in + in0, (size_t)(in1 - in0), al, d_slab, cap, &olen, has_final && last, /*ours_only=*/true);
+    TRACE("slab %u: decoded rc=%d olen=%zu", k, rc, olen);
     if (rc == ZLES_E_OUTPUT_FULL) { total = off + olen; break; }
     if (rc) break;
     if (!(last && has_final) && olen != (b1 - b0) * (size_t)SUB) { rc = -1; break; }
@@ -1147,6 +1254,7 @@ static int inflate_slabs_to_host(zles_ctx *c, const u8 *d_in, size_t n, const st
     total = off + olen;
   }
   zrt_err_t e = zrt_sync(c->copy_stream);
+  TRACE("slabs: copies done");
   for (int i = 0; i < 2; i++) { c->event_pool.push_back(done[i]); c->event_pool.push_back(copied[i]); }
   if (e != ZRT_OK) return cuda_fail(e, "copy to host");
   *out_len = total;
@@ -1216,30 +1324,80 @@ extern "C" int zles_dev_scan_blocks(zles_ctx *c, const uint8_t *d_in, size_t n, 
   return 0;
 }
 
-extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
-  if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
-  if (!c)
-    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_inflate(m, in, n, out, cap, out_len);
-  RET(check_zlib_header(in, n));
+// Host-buffer inflate of the raw deflate data that starts at byte `first` of in[0 .. n).  crc: when not null, the
+// CRC-32 of the output is computed on the device (gzip) — the whole output then stays in device memory until it is checked.
+static int inflate_host(zles_ctx *c, const uint8_t *in, size_t n, u64 first, uint8_t *out, size_t cap, size_t *out_len, uint32_t *crc = nullptr) {
   RET(resolve_ctx(c));
+  TRACE("inflate: n=%zu cap=%zu", n, cap);
   RET(c->d_in.reserve(n + 16));
   if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
-  {
+  TRACE("inflate: h2d enqueued");
+  if (!crc) {
     // one of our own streams, long enough to be worth it: decode slab by slab, copying finished slabs out meanwhile
     std::vector<u64> starts;
-    int rs = n >= INF_SLAB_MIN_STREAM ? scan_block_starts(c, c->d_in.as<u8>(), n, 2, starts) : -1;
+    int rs = n >= INF_SLAB_MIN_STREAM ? scan_block_starts(c, c->d_in.as<u8>(), n, first, starts) : -1;
     if (rs > 0) return rs;
     const u32 slab = inflate_slab_size(c, starts.size());
+    TRACE("inflate: scan done rs=%d blocks=%zu slab=%u", rs, starts.size(), slab);
     if (rs == 0 && starts.size() >= 2 * (size_t)slab) {
       int rc = inflate_slabs_to_host(c, c->d_in.as<u8>(), n, starts, true, out, cap, out_len, slab);
       if (rc >= 0) return rc;
     }
   }
   RET(c->d_out.reserve(cap + 16));
-  int rc = inflate_body(c, c->d_in.as<u8>(), n, 2, c->d_out.as<u8>(), cap, out_len);
+  int rc = inflate_body(c, c->d_in.as<u8>(), n, first, c->d_out.as<u8>(), cap, out_len);
   if (rc) return rc;
+  if (crc) RET(dev_crc32(c, c->d_out.as<u8>(), *out_len, crc));
   if (*out_len) CK(zrt_d2h(out, c->d_out.p, *out_len, c->stream));
   CK(zrt_sync(c->stream));
+  return 0;
+}
+
+extern "C" int zles_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
+  if (!c)
+    if (zles_mgpu *m = default_mgpu()) return zles_mgpu_inflate(m, in, n, out, cap, out_len);
+  RET(check_zlib_header(in, n));
+  return inflate_host(c, in, n, 2, out, cap, out_len);
+}
+
+// inflate(input, offset = 0) of the reference's core (/root/reference/src/inflate.ts:16): raw deflate data from byte `offset` on
+extern "C" int zles_inflate_raw(zles_ctx *c, const uint8_t *in, size_t n, size_t offset, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
+  return inflate_host(c, in, n, offset, out, cap, out_len);
+}
+
+// gzip member header (RFC 1952 2.3): returns its length, or 0 with *err set
+static size_t gzip_header_len(const u8 *in, size_t n, int *err) {
+  *err = 0;
+  if (n < 10) { *err = ZLES_E_LACK; return 0; }
+  if (in[0] != 0x1f || in[1] != 0x8b || in[2] != 8) { *err = ZLES_E_NOT_DEFLATE; return 0; }
+  const u32 flg = in[3];
+  size_t p = 10;
+  if (flg & 4) {  // FEXTRA
+    if (p + 2 > n) { *err = ZLES_E_LACK; return 0; }
+    p += 2 + ((size_t)in[p] | ((size_t)in[p + 1] << 8));
+  }
+  for (u32 bit = 8; bit <= 16; bit <<= 1)  // FNAME, FCOMMENT: zero-terminated
+    if (flg & bit) {
+      while (p < n && in[p]) p++;
+      p++;
+    }
+  if (flg & 2) p += 2;  // FHCRC
+  if (p > n) { *err = ZLES_E_LACK; return 0; }
+  return p;
+}
+
+// One gzip member: header, deflate data, CRC-32 and ISIZE in the last eight bytes of the buffer; both are verified.
+extern "C" int zles_gzip_inflate(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+  if ((!in && n) || !out_len || (!out && cap)) return ZLES_E_ARG;
+  int err = 0;
+  const size_t first = gzip_header_len(in, n, &err);
+  if (err) return err;
+  uint32_t crc = 0;
+  RET(inflate_host(c, in, n, first, out, cap, out_len, &crc));
+  if (n < first + 8) return ZLES_E_LACK;
+  if (get_le32(in + n - 8) != crc || get_le32(in + n - 4) != (u32)*out_len) return ZLES_E_CHECKSUM;
   return 0;
 }
 
@@ -1296,9 +1454,9 @@ extern "C" int zles_dev_inflate_batch(zles_ctx *c, const uint8_t *d_in, const ui
   LAUNCH(c, k_inflate_batch, inflate_grid(c, count), INF_THREADS, INF_SMEM, d_in, d_in_off, count, d_out, d_out_off, d_out_len, d_status,
          &ctl->counter, &ctl->ok);
   CK(zrt_last_error());
-  CK(zrt_d2h(&c->mail->ok, &ctl->ok, 4, c->stream));
+  CK(zrt_mail(&c->mail->ok, &ctl->ok, 4, c->stream));
   CK(zrt_sync(c->stream));
-  return (int)c->mail->ok;  // first (lowest) non-zero status, 0 if none
+  return (int)c->mail->ok;  // the LARGEST per-stream status (atomicMax), 0 if none: callers inspect status[]
 }
 
 extern "C" int zles_inflate_batch(zles_ctx *c, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
@@ -1378,7 +1536,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   u64 *d_blk_first = c->seg_pos.as<u64>();  // [count + 1] first block index of each buffer
   LAUNCH(c, k_batch_count, 1, 1024, 64 * 4, d_in_off, count, d_blk_first);
   CK(zrt_last_error());
-  CK(zrt_d2h(&c->mail->total, d_blk_first + count, 8, c->stream));
+  CK(zrt_mail(&c->mail->total, d_blk_first + count, 8, c->stream));
   CK(zrt_sync(c->stream));
   const u64 nb64 = c->mail->total;
   if (nb64 > 0x7fffffffull / LZ_NSYM) return ZLES_E_ARG;
@@ -1434,7 +1592,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   bp.first_err = &ctl->ok;
   LAUNCH(c, k_pack_batch, count, PACK_THREADS, PACK_SMEM, bp);
   CK(zrt_last_error());
-  CK(zrt_d2h(&c->mail->ok, &ctl->ok, 4, c->stream));
+  CK(zrt_mail(&c->mail->ok, &ctl->ok, 4, c->stream));
   CK(zrt_sync(c->stream));
   return (int)c->mail->ok;
 }

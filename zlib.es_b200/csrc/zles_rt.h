@@ -26,6 +26,7 @@ static inline zrt_err_t zrt_host_free(void *p) { free(p); return 0; }
 static inline zrt_err_t zrt_h2d(void *d, const void *s, size_t n, zrt_stream_t) { memcpy(d, s, n); return 0; }
 static inline zrt_err_t zrt_d2h(void *d, const void *s, size_t n, zrt_stream_t) { memcpy(d, s, n); return 0; }
 static inline zrt_err_t zrt_memset(void *d, int v, size_t n, zrt_stream_t) { memset(d, v, n); return 0; }
+static inline zrt_err_t zrt_mail(void *h, const void *d, size_t n, zrt_stream_t) { memcpy(h, d, n); return 0; }
 static inline zrt_err_t zrt_sync(zrt_stream_t) { return 0; }
 static inline zrt_err_t zrt_last_error() { return 0; }
 static inline const char *zrt_err_str(zrt_err_t) { return "emulator"; }
@@ -57,6 +58,18 @@ static inline zrt_err_t zrt_host_free(void *p) { return cudaFreeHost(p); }
 static inline zrt_err_t zrt_h2d(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st); }
 static inline zrt_err_t zrt_d2h(void *d, const void *s, size_t n, zrt_stream_t st) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st); }
 static inline zrt_err_t zrt_memset(void *d, int v, size_t n, zrt_stream_t st) { return cudaMemsetAsync(d, v, n, st); }
+// A few words from device memory to PINNED host memory, written by a kernel over PCIe (pinned allocations are device
+// accessible under unified addressing) instead of a copy: a cudaMemcpyAsync would queue on the device-to-host copy
+// engine behind whatever bulk copy another stream has in flight — the small read-backs between the steps of a pipelined
+// call (candidate counts, status words) then wait for hundreds of megabytes.  n is a multiple of 4.
+static __global__ void zrt_k_mail(unsigned *dst, const unsigned *src, unsigned nwords) {
+  for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+static inline zrt_err_t zrt_mail(void *h, const void *d, size_t n, zrt_stream_t st) {
+  zrt_k_mail<<<1, 32, 0, st>>>(reinterpret_cast<unsigned *>(h), reinterpret_cast<const unsigned *>(d), (unsigned)(n / 4));
+  return cudaGetLastError();
+}
 static inline zrt_err_t zrt_sync(zrt_stream_t st) { return cudaStreamSynchronize(st); }
 static inline zrt_err_t zrt_last_error() { return cudaGetLastError(); }
 static inline const char *zrt_err_str(zrt_err_t e) { return cudaGetErrorString(e); }

@@ -93,23 +93,60 @@ static napi_value make_u8(napi_env env, const uint8_t *src, size_t n) {
 }
 
 /* ---- deflate(input: Uint8Array): Uint8Array — replaces zlib.deflate, src/zlib.ts:25-49 ---- */
-static napi_value js_deflate(napi_env env, napi_callback_info info) {
+typedef int (*deflate_fn)(zles_ctx *, const uint8_t *, size_t, uint8_t *, size_t, size_t *);
+static napi_value deflate_with(napi_env env, napi_callback_info info, deflate_fn fn) {
   size_t argc = 1;
   napi_value argv[1];
   napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
   const uint8_t *in;
   size_t n;
   if (argc < 1 || !get_bytes(env, argv[0], &in, &n)) { napi_throw_type_error(env, NULL, "deflate: expected a Uint8Array"); return NULL; }
-  size_t cap = zles_deflate_bound(n), out_len = 0;
+  size_t cap = zles_deflate_bound(n) + 16, out_len = 0;
   void *dst = NULL;
   napi_value ab, out;
   if (napi_create_arraybuffer(env, cap, &dst, &ab) != napi_ok) return NULL;
-  int rc = zles_deflate(NULL, in, n, (uint8_t *)dst, cap, &out_len);
+  int rc = fn(NULL, in, n, (uint8_t *)dst, cap, &out_len);
   if (rc) return throw_status(env, rc);
   /* a view of exact length over the (slightly larger) buffer; the reference returns a fresh array of exact length */
   if (napi_create_typedarray(env, napi_uint8_array, out_len, ab, 0, &out) != napi_ok) return NULL;
   return out;
 }
+static napi_value js_deflate(napi_env env, napi_callback_info info) { return deflate_with(env, info, zles_deflate); }
+/* the reference's deflate core (src/deflate.ts:14) and the gzip container (RFC 1952) */
+static napi_value js_deflate_raw(napi_env env, napi_callback_info info) { return deflate_with(env, info, zles_deflate_raw); }
+static napi_value js_gzip(napi_env env, napi_callback_info info) { return deflate_with(env, info, zles_gzip_deflate); }
+
+/* inflateRaw / gunzip: the output size is not known in advance — the reference's first guess (10 x input, src/inflate.ts:17),
+ * then once more with the size the library reports */
+typedef int (*inflate_fn)(zles_ctx *, const uint8_t *, size_t, uint8_t *, size_t, size_t *);
+static int inflate_raw0(zles_ctx *c, const uint8_t *in, size_t n, uint8_t *out, size_t cap, size_t *len) {
+  return zles_inflate_raw(c, in, n, 0, out, cap, len);
+}
+static napi_value inflate_with(napi_env env, napi_callback_info info, inflate_fn fn) {
+  size_t argc = 1;
+  napi_value argv[1];
+  napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+  const uint8_t *in;
+  size_t n;
+  if (argc < 1 || !get_bytes(env, argv[0], &in, &n)) { napi_throw_type_error(env, NULL, "inflate: expected a Uint8Array"); return NULL; }
+  size_t cap = 10 * n + 131072, out_len = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    uint8_t *buf = (uint8_t *)malloc(cap ? cap : 1);
+    if (!buf) return throw_status(env, ZLES_E_NOMEM);
+    int rc = fn(NULL, in, n, buf, cap, &out_len);
+    if (rc == 0) {
+      napi_value out = make_u8(env, buf, out_len);
+      free(buf);
+      return out;
+    }
+    free(buf);
+    if (rc != ZLES_E_OUTPUT_FULL || attempt) return throw_status(env, rc);
+    cap = out_len;
+  }
+  return NULL;
+}
+static napi_value js_inflate_raw(napi_env env, napi_callback_info info) { return inflate_with(env, info, inflate_raw0); }
+static napi_value js_gunzip(napi_env env, napi_callback_info info) { return inflate_with(env, info, zles_gzip_inflate); }
 
 /* ---- inflate(input: Uint8Array): Uint8Array — replaces zlib.inflate, src/zlib.ts:11-23 ---- */
 static void free_cb(napi_env env, void *data, void *hint) { (void)env; (void)hint; zles_free(data); }
@@ -158,7 +195,9 @@ static napi_value batch(napi_env env, napi_callback_info info, int inflate) {
     napi_get_element(env, argv[0], i, &e);
     if (!get_bytes(env, e, &ptr[i], &n)) { napi_throw_type_error(env, NULL, "expected an array of Uint8Array"); goto done; }
     in_off[i + 1] = in_off[i] + n;
-    out_off[i + 1] = out_off[i] + (inflate ? 10 * n + 131072 : zles_deflate_bound(n)); /* src/inflate.ts:17 initial capacity */
+    /* inflate: the reference's initial capacity is 10 x the input (src/inflate.ts:17); a stream that needs more is retried
+     * on its own below, so no large constant per message is added (ten thousand 60-byte messages stay at ~6 MB) */
+    out_off[i + 1] = out_off[i] + (inflate ? 10 * n + 64 : zles_deflate_bound(n));
   }
   in = (uint8_t *)malloc(in_off[count] ? in_off[count] : 1);
   out = (uint8_t *)malloc(out_off[count] ? out_off[count] : 1);
@@ -168,16 +207,19 @@ static napi_value batch(napi_env env, napi_callback_info info, int inflate) {
   {
     int rc = inflate ? zles_inflate_batch(NULL, in, in_off, count, out, out_off, out_len, status)
                      : zles_deflate_batch(NULL, in, in_off, count, out, out_off, out_len, status);
+    /* a failure of the call as a whole (no device, out of memory, a kernel fault) leaves status[] untouched: throw now */
+    if (rc == ZLES_E_CUDA || rc == ZLES_E_ARG || rc == ZLES_E_NOMEM) { throw_status(env, rc); goto done; }
     if (rc) {
-      /* streams that need more room than the first guess fall back to the single-buffer call */
-      for (uint32_t i = 0; i < count && rc; i++)
-        if (status[i] && status[i] != ZLES_E_OUTPUT_FULL) { throw_status(env, status[i]); goto done; }
+      /* per-buffer errors: the first one is thrown, like `inputs.map(inflate)` would; streams that only need more room
+       * than the first guess fall back to the single-buffer call below */
+      for (uint32_t i = 0; i < count; i++)
+        if (status[i] && !(inflate && status[i] == ZLES_E_OUTPUT_FULL)) { throw_status(env, status[i]); goto done; }
     }
   }
   if (napi_create_array_with_length(env, count, &result) != napi_ok) { result = NULL; goto done; }
   for (uint32_t i = 0; i < count; i++) {
     napi_value v;
-    if (status[i] == ZLES_E_OUTPUT_FULL) {
+    if (inflate && status[i] == ZLES_E_OUTPUT_FULL) {
       uint8_t *buf = NULL;
       size_t len = 0;
       int rc = zles_inflate_alloc(NULL, ptr[i], (size_t)(in_off[i + 1] - in_off[i]), &buf, &len);
@@ -197,13 +239,36 @@ done:
 static napi_value js_deflate_batch(napi_env env, napi_callback_info info) { return batch(env, info, 0); }
 static napi_value js_inflate_batch(napi_env env, napi_callback_info info) { return batch(env, info, 1); }
 
+/* ZLES_DEVICES in the environment picks the GPUs the drop-in calls shard over: "all", or a comma-separated list of CUDA
+ * device indices ("0,1,2,3").  Unset: device 0.  Large inputs are then sharded inside the library (zles_init, zles.h). */
+static void init_devices(void) {
+  const char *e = getenv("ZLES_DEVICES");
+  uint32_t mask = 0;
+  if (!e || !*e) return;
+  if (e[0] == 'a') mask = 0xffffffffu;
+  else
+    for (const char *p = e; *p;) {
+      char *end;
+      long d = strtol(p, &end, 10);
+      if (end == p) break;
+      if (d >= 0 && d < 32) mask |= 1u << d;
+      p = *end ? end + 1 : end;
+    }
+  if (mask) zles_init(mask);
+}
+
 /* module entry point looked up by Node (NAPI_MODULE_INIT expands to this symbol) */
 napi_value napi_register_module_v1(napi_env env, napi_value exports) {
+  init_devices();
   napi_property_descriptor props[] = {
       {"deflate", NULL, js_deflate, NULL, NULL, NULL, napi_default, NULL},
       {"inflate", NULL, js_inflate, NULL, NULL, NULL, napi_default, NULL},
       {"deflateBatch", NULL, js_deflate_batch, NULL, NULL, NULL, napi_default, NULL},
       {"inflateBatch", NULL, js_inflate_batch, NULL, NULL, NULL, napi_default, NULL},
+      {"deflateRaw", NULL, js_deflate_raw, NULL, NULL, NULL, napi_default, NULL},
+      {"inflateRaw", NULL, js_inflate_raw, NULL, NULL, NULL, napi_default, NULL},
+      {"gzip", NULL, js_gzip, NULL, NULL, NULL, napi_default, NULL},
+      {"gunzip", NULL, js_gunzip, NULL, NULL, NULL, napi_default, NULL},
   };
   napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
   return exports;

@@ -11,6 +11,10 @@ const native = require('./zles.node') as {
   inflate(input: Uint8Array): Uint8Array;
   deflateBatch(inputs: Uint8Array[]): Uint8Array[];
   inflateBatch(inputs: Uint8Array[]): Uint8Array[];
+  deflateRaw(input: Uint8Array): Uint8Array;
+  inflateRaw(input: Uint8Array): Uint8Array;
+  gzip(input: Uint8Array): Uint8Array;
+  gunzip(input: Uint8Array): Uint8Array;
 };
 
 /** zlib-wrapped DEFLATE of `input` (CMF/FLG 78 9C, Adler-32 trailer), computed on the GPU. */
@@ -31,4 +35,24 @@ export function deflateBatch(inputs: Uint8Array[]): Uint8Array[] {
 /** `inputs.map(inflate)` in one launch sequence. */
 export function inflateBatch(inputs: Uint8Array[]): Uint8Array[] {
   return native.inflateBatch(inputs);
+}
+
+/** Raw DEFLATE data (RFC 1951), no container: what the reference's deflate core returns (src/deflate.ts:14). */
+export function deflateRaw(input: Uint8Array): Uint8Array {
+  return native.deflateRaw(input);
+}
+
+/** Inverse of deflateRaw: the reference's inflate core with offset 0 (src/inflate.ts:16). */
+export function inflateRaw(input: Uint8Array): Uint8Array {
+  return native.inflateRaw(input);
+}
+
+/** gzip container (RFC 1952: CRC-32 and length trailer) around the same DEFLATE data. */
+export function gzip(input: Uint8Array): Uint8Array {
+  return native.gzip(input);
+}
+
+/** Inverse of gzip; verifies CRC-32 and length. */
+export function gunzip(input: Uint8Array): Uint8Array {
+  return native.gunzip(input);
 }

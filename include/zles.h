@@ -71,6 +71,10 @@ int zles_ctx_set_window_mode(zles_ctx *ctx, uint32_t mode);
 /* Host-buffer inflate of our own streams runs slab by slab (finished slabs are copied to the host while the next one is
  * decoded): blocks of 32 KiB per slab, a multiple of 4; 0 (default) = automatic (a quarter of the stream, 16..256 MiB). */
 int zles_ctx_set_slab_blocks(zles_ctx *ctx, uint32_t blocks);
+/* Host-buffer inflate: a stream of at least `bytes` compressed bytes (default 96 MiB) is copied to the device in pieces
+ * (a sixth of the threshold, doubling up to eight times that) that are scanned and decoded as they land, so that the copy
+ * in, the decode and the copy out all overlap.  Streams that turn out not to be ours take the general path afterwards. */
+int zles_ctx_set_stream_min(zles_ctx *ctx, size_t bytes);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the context's

@@ -256,6 +256,25 @@ def slabbed_host_inflate(c, n):
             assert c.inflate(z) == data, slab
         finally:
             c.set_slab_blocks(0)
+    # the same with the stream copied in pieces that are scanned and decoded as they land
+    import numpy as np
+    zf = zlib.compress(data, 1)
+    for smin, slab in ((262144, 8), (400000, 16), (len(z) // 2, 4)):
+        c.set_stream_min(smin)
+        c.set_slab_blocks(slab)
+        try:
+            assert c.inflate(z) == data, (smin, slab)
+            assert c.inflate(zf) == data                     # not ours: falls through to the general path
+            assert _outcome(O.inflate, z[:len(z) * 2 // 3]) == _outcome(c.inflate, z[:len(z) * 2 // 3])
+            try:
+                c.inflate_into(z, np.zeros(n - 1, dtype=np.uint8))
+            except Exception as e:
+                assert getattr(e, "code", None) == 16, e
+            else:
+                raise AssertionError("inflate into n - 1 bytes succeeded")
+        finally:
+            c.set_stream_min(96 << 20)
+            c.set_slab_blocks(0)
 
 
 def wire_format_siblings(c, n):

@@ -83,6 +83,10 @@ class Codec:
         """Blocks of 32 KiB per slab of the host-buffer inflate of our own streams (0 = automatic)."""
         self._check(self.L.zles_ctx_set_slab_blocks(self.h, blocks))
 
+    def set_stream_min(self, nbytes: int):
+        """Host-buffer inflate copies streams of at least ``nbytes`` in pieces that are decoded as they land."""
+        self._check(self.L.zles_ctx_set_stream_min(self.h, nbytes))
+
     def set_stream(self, cuda_stream: int):
         self._check(self.L.zles_ctx_set_stream(self.h, ctypes.c_void_p(cuda_stream)))
         self.stream_ptr = cuda_stream  # the caller's stream the codec's kernels are ordered on (None: its own)

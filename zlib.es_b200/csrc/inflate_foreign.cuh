@@ -466,10 +466,12 @@ __device__ __forceinline__ bool seg_piece(const u32 *__restrict__ pinfo, u32 sid
 
 __global__ void __launch_bounds__(RES_THREADS)
 k_piece_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const u32 *__restrict__ pinfo, const u32 *__restrict__ seg_list, u32 nseg,
-            const u8 *__restrict__ in, const InfRes *__restrict__ res, u16 *sym, u8 *out, u64 cap, u32 *problems) {
+            u32 seg0, const u8 *__restrict__ in, const InfRes *__restrict__ res, u16 *sym, u8 *out, u64 cap, u32 *problems) {
+  // this launch covers entries seg0 .. of the list (a multiple of four: whole chunks); `sym` holds the launch's symbols only
   ZLES_SMEM_DECL(smem_raw);
   const u32 g = blockIdx.x * RES_WARPS + warp_id();
-  const u32 e = g / SEG_PIECES, p = g % SEG_PIECES;
+  const u32 el = g / SEG_PIECES, p = g % SEG_PIECES;
+  const u32 e = seg0 + el;
   if (e >= nseg) return;
   const u32 sidx = seg_list ? seg_list[e] : e;
   const InfRes r = res[sidx];
@@ -502,15 +504,15 @@ k_piece_sym(const u32 *__restrict__ tokens, const u32 *__restrict__ ntok, const 
     return;
   }
   if (cnt == 0) return;
-  st.base = sym + (size_t)e * SUB + out_off;
+  st.base = sym + (size_t)el * SUB + out_off;
   sym_tokens<SEG_RING>(st, tokens + (size_t)sidx * SUB + tok_off, cnt);  // phase A made sure they stand for `bytes` bytes
 }
 
 constexpr int FIN_THREADS = 512;
 __global__ void __launch_bounds__(FIN_THREADS)
 k_chunk_final(const u16 *__restrict__ sym, const u32 *__restrict__ ntok, const u32 *__restrict__ pinfo, const u32 *__restrict__ seg_list, u32 nseg,
-              const InfRes *__restrict__ res, u8 *out, u64 cap, u32 *problems) {
-  const u32 c = blockIdx.x;
+              u32 seg0, const InfRes *__restrict__ res, u8 *out, u64 cap, u32 *problems) {
+  const u32 c = seg0 / SUBS_PER_CHUNK + blockIdx.x;
   u8 *cbase = out + (u64)c * CHUNK;
   for (u32 k = 0; k < SUBS_PER_CHUNK; k++) {
     const u32 e = c * SUBS_PER_CHUNK + k;
@@ -530,7 +532,7 @@ k_chunk_final(const u16 *__restrict__ sym, const u32 *__restrict__ ntok, const u
         if (threadIdx.x == 0) atomicOr(problems, 2u);
         len = off >= cap ? 0 : (u32)(cap - off);
       }
-      const u16 *s = sym + (size_t)e * SUB + out_off;
+      const u16 *s = sym + (size_t)(e - seg0) * SUB + out_off;
       u32 bad = 0;
       // four independent elements per thread and round: the loads of a round are all in flight together
       for (u32 i0 = threadIdx.x; i0 < len; i0 += 4 * FIN_THREADS) {

@@ -100,12 +100,15 @@ struct zles_ctx {
   int device = 0;
   zrt_stream_t stream{};
   zrt_stream_t copy_stream{};  // host<->device copies that overlap kernels on `stream`
+  zrt_stream_t out_stream{};   // device-to-host copies of finished output slabs (inflate), so that they do not queue behind
+                               // host-to-device copies on copy_stream
   bool own_stream = false;
   int sm_count = 148;
   uint64_t launches = 0;
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
   u32 pair_mode = 1;  // zles_ctx_set_window_mode
+  size_t inf_stream_min = (size_t)96 << 20;  // host-buffer inflate: streams at least this long are copied in pieces, scanned and decoded as they land
   u32 inf_slab_blocks = 0;  // host-buffer inflate of our own streams: blocks per slab (inflate_slabs_to_host); 0 = automatic
   DevBuf unit_ctr;    // k_lz hands its units out from this counter
   // deflate workspace
@@ -273,10 +276,12 @@ extern "C" int zles_ctx_create(int device, zles_ctx **out) {
   c->own_stream = true;
   e = zrt_stream_create(&c->copy_stream);
   if (e != ZRT_OK) { zrt_stream_destroy(c->stream); delete c; return cuda_fail(e, "cudaStreamCreate"); }
+  e = zrt_stream_create(&c->out_stream);
+  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); delete c; return cuda_fail(e, "cudaStreamCreate"); }
   c->sm_count = zrt_sm_count(device);
   void *m = nullptr;
   e = zrt_host_alloc(&m, sizeof(HostMail));
-  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
+  if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); zrt_stream_destroy(c->out_stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
   c->mail = reinterpret_cast<HostMail *>(m);
   memset(c->mail, 0, sizeof(HostMail));
   int rc = set_kernel_attrs(device);
@@ -303,6 +308,7 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   if (c->mail) zrt_host_free(c->mail);
   if (c->own_stream) zrt_stream_destroy(c->stream);
   zrt_stream_destroy(c->copy_stream);
+  zrt_stream_destroy(c->out_stream);
   delete c;
 }
 
@@ -334,6 +340,12 @@ extern "C" int zles_ctx_set_window_mode(zles_ctx *c, uint32_t mode) {
 extern "C" int zles_ctx_set_slab_blocks(zles_ctx *c, uint32_t blocks) {
   if (!c || (blocks && blocks < SUBS_PER_CHUNK) || blocks > (1u << 20)) return ZLES_E_ARG;
   c->inf_slab_blocks = (blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+  return 0;
+}
+
+extern "C" int zles_ctx_set_stream_min(zles_ctx *c, size_t bytes) {
+  if (!c) return ZLES_E_ARG;
+  c->inf_stream_min = bytes;
   return 0;
 }
 
@@ -1052,23 +1064,30 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
 }
 
 // Phase B of our own streams: the copies of nseg segments (seg_list, or candidates 0..nseg-1 when null) into d_out;
-// problem bits go to ctl->ok_res.  Many chunks: one warp per 128 KiB chunk (k_inf_resolve).  Few chunks (< 256 MiB of
-// output): one warp per piece of a block (phase A leaves up to four) into 16-bit symbols, then the pieces of each
-// chunk made concrete in order (k_piece_sym + k_chunk_final) — sixteen times as many warps, for 2 bytes of scratch
-// per output byte.
-constexpr u32 SYM_PATH_MAX_CHUNKS = 2048;
-constexpr u32 SPEC_MAX_SEGS = 8192;  // phase A with four warps per block up to 256 MiB of output
+// problem bits go to ctl->ok_res.  One warp per piece of a block (phase A leaves up to four; one when it ran one warp per
+// block) into 16-bit symbols, then the pieces of each chunk made concrete in order (k_piece_sym + k_chunk_final) —
+// sixteen times as many warps as one warp per 128 KiB chunk (k_inf_resolve, kept as the fallback when the symbol buffer
+// cannot be allocated), for 2 bytes of scratch per output byte of a group.
+constexpr u32 SYM_GROUP_SEGS = 8192;  // blocks per launch pair of the piece-parallel phase B (512 MiB of 16-bit symbols)
+constexpr u32 SPEC_MAX_SEGS = 4096;   // phase A with four warps per block up to 128 MiB of output; beyond, one warp per block fills the GPU
 static int launch_phase_b(zles_ctx *c, const u32 *d_seg_list, u32 nseg, const u8 *d_in, u8 *d_out, size_t cap) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   const u32 nchunks = (nseg + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
   static const bool no_sym = [] { const char *e = getenv("ZLES_NO_SYM"); return e && *e && *e != '0'; }();  // debugging aid
-  if (nchunks <= SYM_PATH_MAX_CHUNKS && !no_sym && c->fsym.reserve((size_t)nseg * SUB * 2) == 0) {
+  const u32 group = nseg < SYM_GROUP_SEGS ? nseg : SYM_GROUP_SEGS;
+  if (!no_sym && c->fsym.reserve((size_t)group * SUB * 2) == 0) {
+    // one warp per piece into 16-bit symbols, then every chunk's pieces made concrete in order; long runs go through the
+    // symbol buffer a group of whole chunks at a time (measured: 59 ms for 8 GiB, against 82 ms with one warp per chunk)
     const u32 *pinfo = c->pinfo_valid ? (const u32 *)c->pinfo.as<u32>() : nullptr;
-    const u32 nwarps = nseg * SEG_PIECES;
-    LAUNCH(c, k_piece_sym, (nwarps + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
-           (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, nseg, d_in, (const InfRes *)c->res.as<InfRes>(), c->fsym.as<u16>(), d_out, (u64)cap, &ctl->ok_res);
-    LAUNCH(c, k_chunk_final, nchunks, FIN_THREADS, 0, (const u16 *)c->fsym.as<u16>(), (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, nseg,
-           (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap, &ctl->ok_res);
+    for (u32 seg0 = 0; seg0 < nseg; seg0 += group) {
+      const u32 cnt = nseg - seg0 < group ? nseg - seg0 : group;
+      const u32 nwarps = cnt * SEG_PIECES;
+      LAUNCH(c, k_piece_sym, (nwarps + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SEG_SMEM, (const u32 *)c->tokens.as<u32>(),
+             (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, seg0 + cnt, seg0, d_in, (const InfRes *)c->res.as<InfRes>(), c->fsym.as<u16>(), d_out,
+             (u64)cap, &ctl->ok_res);
+      LAUNCH(c, k_chunk_final, (cnt + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK, FIN_THREADS, 0, (const u16 *)c->fsym.as<u16>(),
+             (const u32 *)c->ntok.as<u32>(), pinfo, d_seg_list, seg0 + cnt, seg0, (const InfRes *)c->res.as<InfRes>(), d_out, (u64)cap, &ctl->ok_res);
+    }
     return 0;
   }
   LAUNCH(c, k_inf_resolve, (nchunks + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
@@ -1213,53 +1232,137 @@ static int inflate_body(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_
 // Returns 0, ZLES_E_OUTPUT_FULL (*out_len = size needed), ZLES_E_CUDA, or -1: not decodable this way (the caller then
 // runs the general path on the same device bytes).
 constexpr size_t INF_SLAB_MIN_STREAM = 1u << 16;  // shorter streams are not worth the extra scan
-constexpr u32 INF_SLAB_BLOCKS = 8192;  // 256 MiB of output per slab (the four-warp phase A takes up to 8,192 blocks)
+constexpr u32 INF_SLAB_BLOCKS = 16384;  // 512 MiB of output per slab: enough blocks for one warp per block to fill the GPU
+static int scan_block_starts(zles_ctx *c, const u8 *d_in, size_t n, u64 first, std::vector<u64> &starts);
+
+// One slab after the other: decode(b0, b1) decodes blocks [b0, b1) of the run into one of two device buffers and queues
+// its copy to the host on the output stream; finish() waits for the copies.
+struct SlabDecoder {
+  zles_ctx *c;
+  const u8 *d_in;
+  bool has_final;
+  u8 *h_out;
+  size_t h_cap;
+  u32 slab_blocks;
+  size_t slab_out = 0;
+  zrt_event_t done[2], copied[2];
+  bool copied_valid[2] = {false, false};
+  bool have_events = false;
+  u32 k = 0;
+  size_t total = 0;
+
+  int begin() {
+    slab_blocks = (slab_blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+    if (slab_blocks == 0) slab_blocks = SUBS_PER_CHUNK;
+    slab_out = (size_t)slab_blocks * SUB;
+    RET(c->d_out.reserve(2 * slab_out + 64));
+    for (int i = 0; i < 2; i++) { done[i] = timing_event(c); copied[i] = timing_event(c); }
+    have_events = true;
+    return 0;
+  }
+  // blocks [b0, b1) start at starts[b0 ..]; `end` = where the slab's bytes end (the next block's start, or the run's end);
+  // last: the run's final slab.  Returns 0, ZLES_E_OUTPUT_FULL (total = size needed so far), ZLES_E_CUDA or -1.
+  int decode(const std::vector<u64> &starts, size_t b0, size_t b1, u64 end, bool last) {
+    const u64 al = (starts[b0] + (u64)((uintptr_t)d_in & 15)) & 15;  // the slab's bytes from a 16-byte aligned address on
+    const u64 in0 = starts[b0] - al;                                  // (al <= starts[b0]: device buffers are 256-byte aligned)
+    u8 *d_slab = c->d_out.as<u8>() + (size_t)(k & 1) * (slab_out + 32);
+    const size_t off = b0 * (size_t)SUB;
+    const size_t cap = off >= h_cap ? 0 : (h_cap - off < slab_out ? h_cap - off : slab_out);
+    if (copied_valid[k & 1]) CK(zrt_stream_wait_event(c->stream, copied[k & 1]));  // the copy out of this buffer (slab k - 2) is done
+    size_t olen = 0;
+    TRACE("slab %u: blocks [%zu, %zu) begin", k, b0, b1);
+    int rc = inflate_body(c, d_in + in0, (size_t)(end - in0), al, d_slab, cap, &olen, has_final && last, /*ours_only=*/true);
+    TRACE("slab %u: decoded rc=%d olen=%zu", k, rc, olen);
+    if (rc == ZLES_E_OUTPUT_FULL) { total = off + olen; return rc; }
+    if (rc == ZLES_E_CUDA) return rc;
+    if (rc) return -1;
+    if (!(last && has_final) && olen != (b1 - b0) * (size_t)SUB) return -1;
+    CK(zrt_event_record(done[k & 1], c->stream));
+    CK(zrt_stream_wait_event(c->out_stream, done[k & 1]));
+    if (olen) CK(zrt_d2h(h_out + off, d_slab, olen, c->out_stream));
+    CK(zrt_event_record(copied[k & 1], c->out_stream));
+    copied_valid[k & 1] = true;
+    total = off + olen;
+    k++;
+    return 0;
+  }
+  int finish() {
+    zrt_err_t e = zrt_sync(c->out_stream);
+    TRACE("slabs: copies done");
+    if (have_events)
+      for (int i = 0; i < 2; i++) { c->event_pool.push_back(done[i]); c->event_pool.push_back(copied[i]); }
+    have_events = false;
+    if (e != ZRT_OK) return cuda_fail(e, "copy to host");
+    return 0;
+  }
+};
+
 static int inflate_slabs_to_host(zles_ctx *c, const u8 *d_in, size_t n, const std::vector<u64> &starts, bool has_final, u8 *h_out, size_t h_cap,
                                  size_t *out_len, u32 slab_blocks = INF_SLAB_BLOCKS) {
   const size_t B = starts.size();
   if (B == 0) return -1;
   // every block but the last stands for exactly 32 KiB: when those cannot fit, the general path reports the exact size
   if (B > 1 && (u64)(B - 1) * SUB > (u64)h_cap) return -1;
-  slab_blocks = (slab_blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
-  if (slab_blocks == 0) slab_blocks = SUBS_PER_CHUNK;
-  const size_t slab_out = (size_t)slab_blocks * SUB;
-  RET(c->d_out.reserve(2 * slab_out + 32));
-  zrt_event_t done[2] = {timing_event(c), timing_event(c)}, copied[2] = {timing_event(c), timing_event(c)};
-  bool copied_valid[2] = {false, false};
+  SlabDecoder sd{c, d_in, has_final, h_out, h_cap, slab_blocks};
+  RET(sd.begin());
   int rc = 0;
-  size_t total = 0;
-  u32 k = 0;
-  for (size_t b0 = 0; b0 < B && rc == 0; b0 += slab_blocks, k++) {
-    const size_t b1 = b0 + slab_blocks < B ? b0 + slab_blocks : B;
-    const bool last = b1 == B;
-    const u64 in1 = last ? (u64)n : starts[b1];
-    const u64 al = (starts[b0] + (u64)((uintptr_t)d_in & 15)) & 15;  // the slab's bytes from a 16-byte aligned address on
-    const u64 in0 = starts[b0] - al;                                  // (al <= starts[b0]: device buffers are 256-byte aligned)
-    u8 *d_slab = c->d_out.as<u8>() + (size_t)(k & 1) * (slab_out + 16);
-    const size_t off = b0 * (size_t)SUB;
-    const size_t cap = off >= h_cap ? 0 : (h_cap - off < slab_out ? h_cap - off : slab_out);
-    if (copied_valid[k & 1]) CK(zrt_stream_wait_event(c->stream, copied[k & 1]));  // the copy out of this buffer (slab k - 2) is done
-    size_t olen = 0;
-    TRACE("slab %u: blocks [%zu, %zu) begin", k, b0, b1);
-    rc = inflate_body(c, d_in + in0, (size_t)(in1 - in0), al, d_slab, cap, &olen, has_final && last, /*ours_only=*/true);
-    TRACE("slab %u: decoded rc=%d olen=%zu", k, rc, olen);
-    if (rc == ZLES_E_OUTPUT_FULL) { total = off + olen; break; }
-    if (rc) break;
-    if (!(last && has_final) && olen != (b1 - b0) * (size_t)SUB) { rc = -1; break; }
-    CK(zrt_event_record(done[k & 1], c->stream));
-    CK(zrt_stream_wait_event(c->copy_stream, done[k & 1]));
-    if (olen) CK(zrt_d2h(h_out + off, d_slab, olen, c->copy_stream));
-    CK(zrt_event_record(copied[k & 1], c->copy_stream));
-    copied_valid[k & 1] = true;
-    total = off + olen;
+  for (size_t b0 = 0; b0 < B && rc == 0; b0 += sd.slab_blocks) {
+    const size_t b1 = b0 + sd.slab_blocks < B ? b0 + sd.slab_blocks : B;
+    rc = sd.decode(starts, b0, b1, b1 == B ? (u64)n : starts[b1], b1 == B);
   }
-  zrt_err_t e = zrt_sync(c->copy_stream);
-  TRACE("slabs: copies done");
-  for (int i = 0; i < 2; i++) { c->event_pool.push_back(done[i]); c->event_pool.push_back(copied[i]); }
-  if (e != ZRT_OK) return cuda_fail(e, "copy to host");
-  *out_len = total;
-  if (rc == ZLES_E_OUTPUT_FULL || rc == ZLES_E_CUDA) return rc;
-  return rc ? -1 : 0;
+  const int rf = sd.finish();
+  *out_len = sd.total;
+  if (rc == 0 && rf) return rf;
+  return rc;
+}
+
+// The same for a stream that is still on its way to the device: the compressed bytes are copied in pieces (16 MiB, then
+// doubling up to 128 MiB) on the copy stream; as each piece lands it is scanned for block starts and every slab whose
+// bytes are complete is decoded, its output leaving on the output stream — host-to-device copy, decode and device-to-host
+// copy all overlap.  h_in[0 .. n) is the whole stream, `first` its first block.  Returns like inflate_slabs_to_host; on -1
+// the whole stream is in device memory (the caller runs the general path on it).
+static int inflate_streaming_to_host(zles_ctx *c, const u8 *h_in, size_t n, u64 first, u8 *h_out, size_t h_cap, size_t *out_len) {
+  u8 *d_in = c->d_in.as<u8>();
+  std::vector<size_t> pb{0};
+  size_t piece0 = (c->inf_stream_min / 6) & ~(size_t)4095;  // 16 MiB with the default threshold
+  if (piece0 < 65536) piece0 = 65536;
+  if (piece0 > ((size_t)16 << 20)) piece0 = (size_t)16 << 20;
+  for (size_t sz = piece0; pb.back() < n; sz = sz < 8 * piece0 ? sz * 2 : sz) pb.push_back(pb.back() + sz < n ? pb.back() + sz : n);
+  const size_t np = pb.size() - 1;
+  std::vector<zrt_event_t> ev(np);
+  for (size_t i = 0; i < np; i++) {
+    CK(zrt_h2d(d_in + pb[i], h_in + pb[i], pb[i + 1] - pb[i], c->copy_stream));
+    ev[i] = timing_event(c);
+    CK(zrt_event_record(ev[i], c->copy_stream));
+  }
+  SlabDecoder sd{c, d_in, true, h_out, h_cap, c->inf_slab_blocks ? c->inf_slab_blocks : INF_SLAB_BLOCKS};
+  int rc = sd.begin();
+  std::vector<u64> starts, found;
+  size_t next = 0;  // first block not decoded yet
+  for (size_t i = 0; i < np && rc == 0; i++) {
+    CK(zrt_stream_wait_event(c->stream, ev[i]));
+    const size_t lo = i == 0 ? 0 : pb[i] - 16, hi = pb[i + 1];
+    const int rs = scan_block_starts(c, d_in + lo, hi - lo, i == 0 ? first : 15, found);
+    if (rs) { rc = rs > 0 ? rs : -1; break; }
+    for (size_t j = i == 0 ? 0 : 1; j < found.size(); j++) starts.push_back(found[j] + lo);
+    TRACE("piece %zu: %zu blocks so far", i, starts.size());
+    const bool all = i + 1 == np;
+    // every block but the last stands for exactly 32 KiB: when those cannot fit, the general path reports the exact size
+    if (starts.size() > 1 && (u64)(starts.size() - 1) * SUB > (u64)h_cap) { rc = -1; break; }
+    while (rc == 0 && (all ? next < starts.size() : next + sd.slab_blocks < starts.size())) {
+      const size_t b1 = next + sd.slab_blocks < starts.size() ? next + sd.slab_blocks : starts.size();
+      const bool last = all && b1 == starts.size();
+      rc = sd.decode(starts, next, b1, last ? (u64)n : starts[b1], last);
+      next = b1;
+    }
+  }
+  for (size_t i = 0; i < np; i++) c->event_pool.push_back(ev[i]);
+  zrt_err_t e = zrt_sync(c->copy_stream);  // whatever happens next needs the whole stream on the device
+  const int rf = sd.finish();
+  if (e != ZRT_OK) return cuda_fail(e, "copy to device");
+  *out_len = sd.total;
+  if (rc == 0 && rf) return rf;
+  return rc;
 }
 
 // blocks per slab for a run of B blocks: the context's setting, or (0 = automatic) a quarter of the run, between 16 MiB
@@ -1330,6 +1433,18 @@ static int inflate_host(zles_ctx *c, const uint8_t *in, size_t n, u64 first, uin
   RET(resolve_ctx(c));
   TRACE("inflate: n=%zu cap=%zu", n, cap);
   RET(c->d_in.reserve(n + 16));
+  if (!crc && n >= c->inf_stream_min && n >= 262144) {
+    // long stream: pieces of it are scanned and decoded while the rest is still being copied in
+    const int rc = inflate_streaming_to_host(c, in, n, first, out, cap, out_len);
+    TRACE("inflate: streaming rc=%d", rc);
+    if (rc >= 0) return rc;
+    RET(c->d_out.reserve(cap + 16));  // not a long run of our blocks: the general path, on the bytes already in device memory
+    const int rg = inflate_body(c, c->d_in.as<u8>(), n, first, c->d_out.as<u8>(), cap, out_len);
+    if (rg) return rg;
+    if (*out_len) CK(zrt_d2h(out, c->d_out.p, *out_len, c->stream));
+    CK(zrt_sync(c->stream));
+    return 0;
+  }
   if (n) CK(zrt_h2d(c->d_in.p, in, n, c->stream));
   TRACE("inflate: h2d enqueued");
   if (!crc) {

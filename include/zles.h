@@ -75,6 +75,10 @@ int zles_ctx_set_slab_blocks(zles_ctx *ctx, uint32_t blocks);
  * (a sixth of the threshold, doubling up to eight times that) that are scanned and decoded as they land, so that the copy
  * in, the decode and the copy out all overlap.  Streams that turn out not to be ours take the general path afterwards. */
 int zles_ctx_set_stream_min(zles_ctx *ctx, size_t bytes);
+/* Host batch calls go through the device a slab of buffers at a time (the workspace is sized by the slab; the results of
+ * slab k travel to the host and into the caller's buffers while slab k + 1 is computed): at most `buffers` per slab
+ * (default and maximum 16,384; also bounded by 64 MiB of input and 256 MiB of output room). */
+int zles_ctx_set_batch_slab(zles_ctx *ctx, uint32_t buffers);
 /* Number of kernels launched through this context since creation (bench.py's gpu_launches). */
 uint64_t zles_ctx_launches(const zles_ctx *ctx);
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the context's

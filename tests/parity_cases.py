@@ -316,3 +316,35 @@ def wire_format_siblings(c, n):
             assert getattr(e, "code", None) == code, (code, e)
         else:
             raise AssertionError("no error")
+
+
+def batch_in_slabs(c, count):
+    """The host batch calls go through the device a slab of buffers at a time (results compacted on the device, moved into
+    the caller's buffers by a helper thread): same results whatever the slab size, errors and size retries included."""
+    import numpy as np
+    rng = np.random.default_rng(21)
+    src = T.fixture_raw() + T.gen("G5", 300000)
+    bufs = []
+    for i in range(count):
+        n = int(rng.integers(0, 6000)) if i % 7 else int(rng.integers(30000, 70000))
+        o = int(rng.integers(0, len(src) - n))
+        bufs.append(src[o:o + n])
+    want = None
+    for slab in (16384, 5, 64):
+        c.set_batch_slab(slab)
+        try:
+            zs = c.deflate_batch(bufs)
+            if want is None:
+                want = zs
+                for b, z in zip(bufs[:12], zs[:12]):
+                    assert zlib.decompress(z) == b and z == c.deflate(b)
+            assert zs == want, slab
+            assert c.inflate_batch(zs) == bufs, slab
+            mixed = list(zs)
+            mixed[3] = b"\x77\x00"
+            mixed[count // 2] = zlib.compress(bytes(100000), 9)      # needs far more room than 10 x its length: retried
+            res = c.inflate_batch(mixed, raise_on_error=False)
+            assert str(res[3]) == "Not compressed by deflate" and res[count // 2] == bytes(100000)
+            assert all(r == b for i, (r, b) in enumerate(zip(res, bufs)) if i not in (3, count // 2)), slab
+        finally:
+            c.set_batch_slab(16384)

@@ -229,3 +229,7 @@ def test_host_inflate_in_slabs(c):
 
 def test_raw_deflate_and_gzip(c):
     P.wire_format_siblings(c, 300001)
+
+
+def test_host_batch_in_slabs(c):
+    P.batch_in_slabs(c, 40)

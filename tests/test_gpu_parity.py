@@ -277,3 +277,7 @@ def test_host_inflate_in_slabs(c):
 
 def test_raw_deflate_and_gzip(c):
     P.wire_format_siblings(c, 20971527)
+
+
+def test_host_batch_in_slabs(c):
+    P.batch_in_slabs(c, 3000)

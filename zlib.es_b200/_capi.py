@@ -38,6 +38,7 @@ PROTOTYPES = {
     "zles_ctx_set_window_mode": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
     "zles_ctx_set_slab_blocks": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
     "zles_ctx_set_stream_min": (ctypes.c_int, [c_vp, ctypes.c_size_t]),
+    "zles_ctx_set_batch_slab": (ctypes.c_int, [c_vp, ctypes.c_uint32]),
     "zles_ctx_launches": (ctypes.c_uint64, [c_vp]),
     "zles_init": (ctypes.c_int, [ctypes.c_uint32]),
     "zles_shutdown": (None, []),

@@ -83,6 +83,10 @@ class Codec:
         """Blocks of 32 KiB per slab of the host-buffer inflate of our own streams (0 = automatic)."""
         self._check(self.L.zles_ctx_set_slab_blocks(self.h, blocks))
 
+    def set_batch_slab(self, buffers: int):
+        """Buffers per slab of the host batch calls (at most 16,384)."""
+        self._check(self.L.zles_ctx_set_batch_slab(self.h, buffers))
+
     def set_stream_min(self, nbytes: int):
         """Host-buffer inflate copies streams of at least ``nbytes`` in pieces that are decoded as they land."""
         self._check(self.L.zles_ctx_set_stream_min(self.h, nbytes))
@@ -253,7 +257,8 @@ class Codec:
         return [out[int(out_off[i]):int(out_off[i]) + int(out_len[i])].tobytes() for i in range(count)]
 
     def inflate_batch(self, bufs: Sequence, out_sizes: Iterable[int] | None = None, raise_on_error: bool = True):
-        """``[inflate(b) for b in bufs]``; ``out_sizes`` are capacity hints (default 131072 + 10 x input each)."""
+        """``[inflate(b) for b in bufs]``; ``out_sizes`` are capacity hints (default 10 x input + 64 each, the reference's own
+        first guess, /root/reference/src/inflate.ts:17; a stream that needs more is retried with the size it reports)."""
         count = len(bufs)
         if count == 0:
             return []
@@ -262,7 +267,7 @@ class Codec:
         np.cumsum(lens, out=in_off[1:])
         blob = np.frombuffer(b"".join(bytes(b) for b in bufs), dtype=np.uint8) if int(in_off[-1]) else np.zeros(1, np.uint8)
         if out_sizes is None:
-            caps = lens * np.uint64(10) + np.uint64(131072)
+            caps = lens * np.uint64(10) + np.uint64(64)
         else:
             caps = np.array(list(out_sizes), dtype=np.uint64)
         for _attempt in range(2):

@@ -734,8 +734,23 @@ __device__ unsigned long long g_inf_clk[8];
 #define INF_CLK_DECL do { } while (0)
 #endif
 
-__device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out) {
+// pieces (may be null): the block's tokens cut into four runs of about 8 KiB of output each — [count, bytes] x 4, the layout
+// the four-warp phase A leaves (inflate_spec.cuh) — so that phase B can give every piece its own warp (k_piece_sym).
+__device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 in_pos, u32 *tok, InfRes *res, u32 *ntok_out,
+                                                   u32 *pieces = nullptr) {
   const u32 lane = lane_id();
+  u32 cut_nt0 = 0, cut_nt1 = 0, cut_nt2 = 0, cut_o0 = 0, cut_o1 = 0, cut_o2 = 0, ncut = 0, thresh = SUB / 4;
+  // a cut after the tokens decoded so far, whenever the output has passed the next quarter of a block
+#define ZLES_CUT()                                                                   \
+  do {                                                                               \
+    while (o >= thresh && ncut < 3) {                                                \
+      if (ncut == 0) { cut_nt0 = nt; cut_o0 = o; }                                   \
+      else if (ncut == 1) { cut_nt1 = nt; cut_o1 = o; }                              \
+      else { cut_nt2 = nt; cut_o2 = o; }                                             \
+      ncut++;                                                                        \
+      thresh += SUB / 4;                                                             \
+    }                                                                                \
+  } while (0)
   InfWarpSmem *S = &T->w;
   TokReader r;
   r.init(in, n, in_pos);
@@ -843,6 +858,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
           if (mine) tok[nt + (u32)__popc(plain & lanemask_lt())] = tokv;
           nt += (u32)__popc(plain);
           o += sum;
+          ZLES_CUT();
           if (!last_stops) cur = last + (plast & 0xff);
           else if (plast & 0x100) {
             cur = last + (plast & 0xff);
@@ -916,6 +932,18 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
     if (bfinal) { status = SEG_FINAL; end_pos = (r.bitpos() + 7) >> 3; break; }
   }
 #undef ZLES_EMIT
+  ZLES_CUT();
+#undef ZLES_CUT
+  if (pieces && lane == 0) {
+    // cuts that were never reached leave empty pieces; the last piece takes the rest
+    const u32 n0 = ncut > 0 ? cut_nt0 : nt, o0 = ncut > 0 ? cut_o0 : o;
+    const u32 n1 = ncut > 1 ? cut_nt1 : nt, o1 = ncut > 1 ? cut_o1 : o;
+    const u32 n2 = ncut > 2 ? cut_nt2 : nt, o2 = ncut > 2 ? cut_o2 : o;
+    pieces[0] = n0; pieces[1] = o0;
+    pieces[2] = n1 - n0; pieces[3] = o1 - o0;
+    pieces[4] = n2 - n1; pieces[5] = o2 - o1;
+    pieces[6] = nt - n2; pieces[7] = o - o2;
+  }
   INF_CLK(0);
   INF_CNT(3, nt);
   // a stored segment: how far before end_pos its payload ends (0: the data block was the final one; 5: an empty stored
@@ -934,7 +962,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
 // tokens[j * SUB ...]; candidates beyond tok_segs (more than the output could hold) are not decoded.
 __global__ void __launch_bounds__(INF_THREADS)
 k_inf_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, u32 nseg, u32 *tokens, u32 *ntok, InfRes *res,
-             u32 *counter) {
+             u32 *pinfo, u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);
   TokWarpSmem *T = reinterpret_cast<TokWarpSmem *>(smem_raw) + warp_id();
   for (;;) {
@@ -942,7 +970,7 @@ k_inf_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos, 
     if (lane_id() == 0) j = atomicAdd(counter, 1u);
     j = __shfl_sync(ZLES_FULL, j, 0);
     if (j >= nseg) break;
-    inf_segment_tokens(T, in, n, seg_pos[j], tokens + (size_t)j * SUB, res + j, ntok + j);
+    inf_segment_tokens(T, in, n, seg_pos[j], tokens + (size_t)j * SUB, res + j, ntok + j, pinfo ? pinfo + (size_t)j * 8 : nullptr);
     __syncwarp();
   }
 }

@@ -355,6 +355,41 @@ __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_
   }
 }
 
+// ---- host forms of the batch calls: only the bytes that were produced travel back ----------------------------
+// coff[i] = where buffer i's result goes in the compacted output (exclusive scan of the produced lengths; a buffer whose
+// status is not 0 produced nothing); coff[count] = total.  Single CTA.
+__global__ void __launch_bounds__(1024) k_batch_prefix(const u64 *__restrict__ out_len, const int32_t *__restrict__ status, u32 count, u64 *coff) {
+  ZLES_SMEM_DECL(smem_raw);
+  u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
+  u64 carry = 0;
+  for (u32 base = 0; base < count; base += 1024) {
+    const u32 i = base + threadIdx.x;
+    const u32 v = (i < count && status[i] == 0) ? (u32)out_len[i] : 0;  // one result is < 4 GiB (a slab holds less than that)
+    u32 total;
+    const u32 ex = block_exscan(v, scratch, &total);
+    if (i < count) coff[i] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) coff[count] = carry;
+}
+
+// one CTA per buffer: its result from out + out_off[i] to packed + coff[i]
+__global__ void __launch_bounds__(128) k_batch_gather(const u8 *__restrict__ out, const u64 *__restrict__ out_off, const u64 *__restrict__ coff,
+                                                      u32 count, u8 *packed) {
+  for (u32 i = blockIdx.x; i < count; i += gridDim.x) {
+    const u64 n = coff[i + 1] - coff[i];
+    const u8 *src = out + out_off[i];
+    u8 *dst = packed + coff[i];
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      const u64 nv = n >> 4;
+      for (u64 k = threadIdx.x; k < nv; k += blockDim.x) reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(src)[k];
+      for (u64 k = (nv << 4) + threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+    } else {
+      for (u64 k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+    }
+  }
+}
+
 struct BatchPackParams {
   const u32 *tokens;
   const u32 *ntok;

@@ -14,7 +14,10 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -96,6 +99,8 @@ struct HostMail {
 
 }  // namespace
 
+constexpr u32 BATCH_SLAB_STREAMS = 16384;  // host batch calls: buffers per slab at most
+
 struct zles_ctx {
   int device = 0;
   zrt_stream_t stream{};
@@ -119,10 +124,15 @@ struct zles_ctx {
   // adler / misc
   DevBuf acc;
   // staging for the host forms
-  DevBuf d_in, d_out, d_off_in, d_off_out, d_len, d_status;
+  DevBuf d_in, d_out, d_off_in, d_off_out, d_len, d_status, d_coff, d_pack;
+  u32 batch_slab_streams = 16384;  // host batch calls: buffers per slab at most (BATCH_SLAB_STREAMS)
+  u8 *batch_stage = nullptr;  // pinned: compacted results of the host batch calls, double buffered
+  size_t batch_stage_cap = 0;
   HostMail *mail = nullptr;  // pinned
   u64 *slab_mail = nullptr;  // pinned: where each slab of a pipelined host-buffer deflate ends (bytes)
   size_t slab_mail_cap = 0;
+  u64 *cand_mail = nullptr;  // pinned: block starts read back by scan_block_starts
+  size_t cand_mail_cap = 0;
   CorpusTable *d_corpus = nullptr;
   CrcTables *d_crc = nullptr;  // CRC-32 tables (gzip), uploaded on first use
   DevBuf crc_part;
@@ -296,10 +306,14 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
                     &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo, &c->unit_ctr,
-                    &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status};
+                    &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status, &c->d_coff, &c->d_pack};
   for (DevBuf *b : bufs) b->release();
   if (c->slab_mail) zrt_host_free(c->slab_mail);
   c->slab_mail = nullptr;
+  if (c->cand_mail) zrt_host_free(c->cand_mail);
+  c->cand_mail = nullptr;
+  if (c->batch_stage) zrt_host_free(c->batch_stage);
+  c->batch_stage = nullptr;
   timing_collect(c);
   for (zrt_event_t e : c->event_pool) zrt_event_destroy(e);
   if (c->d_corpus) zrt_free(c->d_corpus);
@@ -340,6 +354,12 @@ extern "C" int zles_ctx_set_window_mode(zles_ctx *c, uint32_t mode) {
 extern "C" int zles_ctx_set_slab_blocks(zles_ctx *c, uint32_t blocks) {
   if (!c || (blocks && blocks < SUBS_PER_CHUNK) || blocks > (1u << 20)) return ZLES_E_ARG;
   c->inf_slab_blocks = (blocks / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
+  return 0;
+}
+
+extern "C" int zles_ctx_set_batch_slab(zles_ctx *c, uint32_t buffers) {
+  if (!c || buffers == 0) return ZLES_E_ARG;
+  c->batch_slab_streams = buffers < BATCH_SLAB_STREAMS ? buffers : BATCH_SLAB_STREAMS;
   return 0;
 }
 
@@ -1118,9 +1138,9 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
              c->ntok.as<u32>(), c->res.as<InfRes>(), c->pinfo.as<u32>(), &ctl->counter);
       c->pinfo_valid = true;
     } else {
-      c->pinfo_valid = false;
+      c->pinfo_valid = true;  // the one-warp decoder cuts every block into four pieces too
       LAUNCH(c, k_inf_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
-             c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), &ctl->counter);
+             c->tokens.as<u32>(), c->ntok.as<u32>(), c->res.as<InfRes>(), c->pinfo.as<u32>(), &ctl->counter);
     }
     LAUNCH(c, k_inf_check, (ncand + 255) / 256, 256, 0, (const InfRes *)c->res.as<InfRes>(), (const u64 *)c->cand.as<u64>(), ncand,
            (u64)n, has_final ? 1u : 0u, &ctl->ok, &ctl->total);
@@ -1381,9 +1401,18 @@ static int scan_block_starts(zles_ctx *c, const u8 *d_in, size_t n, u64 first, s
   u32 ncand = 0, cand_cap = 0;
   RET(inflate_scan(c, d_in, n, first, &ncand, &cand_cap));
   if (ncand == 0 || ncand > cand_cap) return -1;
-  starts.resize(ncand);
-  CK(zrt_d2h(starts.data(), c->cand.p, (size_t)ncand * 8, c->stream));
+  // through pinned memory, written by a kernel: a copy would queue behind whatever bulk device-to-host copy is in flight
+  if (c->cand_mail_cap < ncand) {
+    if (c->cand_mail) zrt_host_free(c->cand_mail);
+    c->cand_mail = nullptr;
+    c->cand_mail_cap = 0;
+    const size_t want = (size_t)ncand + ((size_t)ncand >> 1) + 1024;
+    CK(zrt_host_alloc(reinterpret_cast<void **>(&c->cand_mail), want * 8));
+    c->cand_mail_cap = want;
+  }
+  CK(zrt_mail(c->cand_mail, c->cand.p, (size_t)ncand * 8, c->stream));
   CK(zrt_sync(c->stream));
+  starts.assign(c->cand_mail, c->cand_mail + ncand);
   return 0;
 }
 
@@ -1574,32 +1603,181 @@ extern "C" int zles_dev_inflate_batch(zles_ctx *c, const uint8_t *d_in, const ui
   return (int)c->mail->ok;  // the LARGEST per-stream status (atomicMax), 0 if none: callers inspect status[]
 }
 
+// ---- host forms of the batch calls ---------------------------------------------------------------------------
+// The batch goes through the device a slab of buffers at a time (at most BATCH_SLAB_STREAMS buffers, about 64 MiB of
+// input and 256 MiB of output room): the workspace is sized by the slab, not by the batch; on the device the results are
+// compacted (k_batch_prefix + k_batch_gather) so that only the bytes that were produced cross PCIe, into a pinned staging
+// ring; a helper thread moves every result from the ring to its place in the caller's buffer while the GPU works on the
+// next slab.
+constexpr u64 BATCH_SLAB_IN = (u64)64 << 20, BATCH_SLAB_OUT = (u64)256 << 20;
+
+struct BatchJob {
+  u32 s0, s1;           // buffers [s0, s1)
+  int buf;              // staging buffer
+  zrt_event_t ready;    // recorded after the slab's copies to the staging buffer
+};
+
+static int batch_host(zles_ctx *c, bool inflate, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
+                      const uint64_t *out_off, uint64_t *out_len, int32_t *status) {
+  RET(resolve_ctx(c));
+  // slabs
+  std::vector<u32> sb{0};
+  for (u32 i = 0; i < count;) {
+    u32 j = i + 1;
+    while (j < count && j - i < c->batch_slab_streams && in_off[j + 1] - in_off[i] <= BATCH_SLAB_IN && out_off[j + 1] - out_off[i] <= BATCH_SLAB_OUT) j++;
+    sb.push_back(j);
+    i = j;
+  }
+  const u32 nslab = (u32)sb.size() - 1;
+  u64 max_in = 0, max_out = 0;
+  u32 max_cnt = 0;
+  for (u32 k = 0; k < nslab; k++) {
+    max_in = std::max<u64>(max_in, in_off[sb[k + 1]] - in_off[sb[k]]);
+    max_out = std::max<u64>(max_out, out_off[sb[k + 1]] - out_off[sb[k]]);
+    max_cnt = std::max(max_cnt, sb[k + 1] - sb[k]);
+  }
+  if (max_out >= 0xffffffffull) return ZLES_E_ARG;  // one buffer's room must be below 4 GiB
+  RET(c->d_in.reserve((size_t)max_in + 16));
+  RET(c->d_out.reserve((size_t)max_out + 16));
+  RET(c->d_off_in.reserve(((size_t)max_cnt + 1) * 8));
+  RET(c->d_off_out.reserve(((size_t)max_cnt + 1) * 8));
+  RET(c->d_len.reserve((size_t)max_cnt * 8));
+  RET(c->d_status.reserve((size_t)max_cnt * 4));
+  RET(c->d_coff.reserve(((size_t)max_cnt + 1) * 8));
+  // device-side compacted results, and their pinned landing place, double buffered: [bytes | out_len | status]
+  const size_t meta = (size_t)max_cnt * 12 + 64;
+  const size_t stage_bytes = (((size_t)max_out + 15) & ~(size_t)15) + meta;
+  RET(c->d_pack.reserve(2 * stage_bytes));
+  if (c->batch_stage_cap < 2 * stage_bytes) {
+    if (c->batch_stage) zrt_host_free(c->batch_stage);
+    c->batch_stage = nullptr;
+    c->batch_stage_cap = 0;
+    CK(zrt_host_alloc(reinterpret_cast<void **>(&c->batch_stage), 2 * stage_bytes));
+    c->batch_stage_cap = 2 * stage_bytes;
+  }
+  // helper thread: results from the staging ring to the caller's buffers
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<BatchJob> jobs;
+  bool closing = false;
+  int helper_err = 0;
+  u32 done_slabs = 0;
+  auto helper = [&]() {
+    zrt_set_device(c->device);
+    for (;;) {
+      BatchJob j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return closing || !jobs.empty(); });
+        if (jobs.empty()) return;
+        j = jobs.front();
+        jobs.pop_front();
+      }
+      if (zrt_event_sync(j.ready) != ZRT_OK) helper_err = 1;
+      const u8 *st = c->batch_stage + (size_t)j.buf * stage_bytes;
+      const u32 cnt = j.s1 - j.s0;
+      const u64 *lens = reinterpret_cast<const u64 *>(st + (((size_t)max_out + 15) & ~(size_t)15));
+      const int32_t *stat = reinterpret_cast<const int32_t *>(lens + max_cnt);
+      u64 o = 0;
+      for (u32 i = 0; i < cnt; i++) {
+        out_len[j.s0 + i] = lens[i];
+        status[j.s0 + i] = stat[i];
+        if (stat[i] == 0 && lens[i]) {
+          memcpy(out + out_off[j.s0 + i], st + o, (size_t)lens[i]);
+          o += lens[i];
+        }
+      }
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        done_slabs++;
+      }
+      cv.notify_all();
+    }
+  };
+#ifndef ZLES_EMU
+  std::thread th(helper);
+#endif
+  int rc = 0, worst = 0;
+  std::vector<zrt_event_t> evs;
+  std::vector<u64> oi, oo;
+  for (u32 k = 0; k < nslab && rc == 0; k++) {
+    const u32 s0 = sb[k], s1 = sb[k + 1], cnt = s1 - s0;
+    const int buf = (int)(k & 1);
+    oi.resize((size_t)cnt + 1);
+    oo.resize((size_t)cnt + 1);
+    for (u32 i = 0; i <= cnt; i++) { oi[i] = in_off[s0 + i] - in_off[s0]; oo[i] = out_off[s0 + i] - out_off[s0]; }
+    const size_t nin = (size_t)oi[cnt];
+    zrt_err_t e = ZRT_OK;
+    if (nin) e = zrt_h2d(c->d_in.p, in + in_off[s0], nin, c->stream);
+    if (e == ZRT_OK) e = zrt_h2d(c->d_off_in.p, oi.data(), ((size_t)cnt + 1) * 8, c->stream);
+    if (e == ZRT_OK) e = zrt_h2d(c->d_off_out.p, oo.data(), ((size_t)cnt + 1) * 8, c->stream);
+    if (e == ZRT_OK) e = zrt_sync(c->stream);  // the offset vectors are reused by the next slab
+    if (e != ZRT_OK) { rc = cuda_fail(e, "copy to device"); break; }
+    int r = inflate ? zles_dev_inflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), cnt, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
+                                             c->d_len.as<u64>(), c->d_status.as<int32_t>())
+                    : dev_deflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), oi.data(), cnt, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
+                                        c->d_len.as<u64>(), c->d_status.as<int32_t>());
+    if (r == ZLES_E_CUDA || r == ZLES_E_ARG || r == ZLES_E_NOMEM) { rc = r; break; }
+    if (r > worst) worst = r;
+    // the staging buffer of slab k - 2 must have been emptied by the helper before slab k's results land in it
+    if (k >= 2) {
+      std::unique_lock<std::mutex> lk(mu);
+#ifdef ZLES_EMU
+      (void)lk;
+#else
+      cv.wait(lk, [&] { return done_slabs + 2 > k; });
+#endif
+    }
+    u8 *d_pk = c->d_pack.as<u8>() + (size_t)buf * stage_bytes;
+    u8 *h_st = c->batch_stage + (size_t)buf * stage_bytes;
+    const size_t meta_off = ((size_t)max_out + 15) & ~(size_t)15;
+    LAUNCH(c, k_batch_prefix, 1, 1024, 64 * 4, (const u64 *)c->d_len.as<u64>(), (const int32_t *)c->d_status.as<int32_t>(), cnt, c->d_coff.as<u64>());
+    LAUNCH(c, k_batch_gather, cnt < 65535u ? cnt : 65535u, 128, 0, (const u8 *)c->d_out.as<u8>(), (const u64 *)c->d_off_out.as<u64>(),
+           (const u64 *)c->d_coff.as<u64>(), cnt, d_pk);
+    e = zrt_last_error();
+    // lengths and status words ride along in the packed buffer (the next slab's kernels rewrite d_len / d_status)
+    if (e == ZRT_OK) e = zrt_copy(d_pk + meta_off, c->d_len.p, (size_t)cnt * 8, c->stream);
+    if (e == ZRT_OK) e = zrt_copy(d_pk + meta_off + (size_t)max_cnt * 8, c->d_status.p, (size_t)cnt * 4, c->stream);
+    if (e == ZRT_OK) e = zrt_mail(&c->mail->total, c->d_coff.as<u64>() + cnt, 8, c->stream);
+    if (e == ZRT_OK) e = zrt_sync(c->stream);  // everything of this slab is in d_pk now
+    if (e != ZRT_OK) { rc = cuda_fail(e, "batch compaction"); break; }
+    const size_t produced = (size_t)c->mail->total;
+    zrt_event_t ev = timing_event(c);
+    evs.push_back(ev);
+    if (produced) e = zrt_d2h(h_st, d_pk, produced, c->out_stream);
+    if (e == ZRT_OK) e = zrt_d2h(h_st + meta_off, d_pk + meta_off, (size_t)max_cnt * 12, c->out_stream);
+    if (e == ZRT_OK) e = zrt_event_record(ev, c->out_stream);
+    if (e != ZRT_OK) { rc = cuda_fail(e, "copy to host"); break; }
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      jobs.push_back(BatchJob{s0, s1, buf, ev});
+    }
+    cv.notify_all();
+#ifdef ZLES_EMU
+    closing = true;
+    helper();  // the emulator build has no threads: the helper's loop runs inline and returns when the queue is empty
+    closing = false;
+#endif
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    closing = true;
+  }
+  cv.notify_all();
+#ifndef ZLES_EMU
+  th.join();
+#endif
+  for (zrt_event_t ev : evs) c->event_pool.push_back(ev);
+  if (rc) return rc;
+  if (helper_err) return cuda_fail(zrt_last_error(), "copy to host");
+  return worst;
+}
+
 extern "C" int zles_inflate_batch(zles_ctx *c, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
                                   const uint64_t *out_off, uint64_t *out_len, int32_t *status) {
   if (!count) return 0;
   if (!in || !in_off || !out || !out_off || !out_len || !status) return ZLES_E_ARG;
-  RET(resolve_ctx(c));
-  const size_t nin = in_off[count] - in_off[0], nout = out_off[count] - out_off[0];
-  RET(c->d_in.reserve(nin + 16));
-  RET(c->d_out.reserve(nout + 16));
-  RET(c->d_off_in.reserve(((size_t)count + 1) * 8));
-  RET(c->d_off_out.reserve(((size_t)count + 1) * 8));
-  RET(c->d_len.reserve((size_t)count * 8));
-  RET(c->d_status.reserve((size_t)count * 4));
-  std::vector<u64> oi(count + 1), oo(count + 1);
-  for (u32 i = 0; i <= count; i++) { oi[i] = in_off[i] - in_off[0]; oo[i] = out_off[i] - out_off[0]; }
-  CK(zrt_h2d(c->d_in.p, in + in_off[0], nin, c->stream));
-  CK(zrt_h2d(c->d_off_in.p, oi.data(), ((size_t)count + 1) * 8, c->stream));
-  CK(zrt_h2d(c->d_off_out.p, oo.data(), ((size_t)count + 1) * 8, c->stream));
-  CK(zrt_sync(c->stream));
-  int rc = zles_dev_inflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), count, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
-                                  c->d_len.as<u64>(), c->d_status.as<int32_t>());
-  if (rc == ZLES_E_CUDA || rc == ZLES_E_ARG) return rc;
-  CK(zrt_d2h(out + out_off[0], c->d_out.p, nout, c->stream));
-  CK(zrt_d2h(out_len, c->d_len.p, (size_t)count * 8, c->stream));
-  CK(zrt_d2h(status, c->d_status.p, (size_t)count * 4, c->stream));
-  CK(zrt_sync(c->stream));
-  return rc;
+  return batch_host(c, true, in, in_off, count, out, out_off, out_len, status);
 }
 
 extern "C" int zles_dev_deflate_batch(zles_ctx *c, const uint8_t *d_in, const uint64_t *d_in_off, uint32_t count, uint8_t *d_out,
@@ -1614,28 +1792,7 @@ extern "C" int zles_deflate_batch(zles_ctx *c, const uint8_t *in, const uint64_t
                                   const uint64_t *out_off, uint64_t *out_len, int32_t *status) {
   if (!count) return 0;
   if (!in || !in_off || !out || !out_off || !out_len || !status) return ZLES_E_ARG;
-  RET(resolve_ctx(c));
-  const size_t nin = in_off[count] - in_off[0], nout = out_off[count] - out_off[0];
-  RET(c->d_in.reserve(nin + 16));
-  RET(c->d_out.reserve(nout + 16));
-  RET(c->d_off_in.reserve(((size_t)count + 1) * 8));
-  RET(c->d_off_out.reserve(((size_t)count + 1) * 8));
-  RET(c->d_len.reserve((size_t)count * 8));
-  RET(c->d_status.reserve((size_t)count * 4));
-  std::vector<u64> oi(count + 1), oo(count + 1);
-  for (u32 i = 0; i <= count; i++) { oi[i] = in_off[i] - in_off[0]; oo[i] = out_off[i] - out_off[0]; }
-  if (nin) CK(zrt_h2d(c->d_in.p, in + in_off[0], nin, c->stream));
-  CK(zrt_h2d(c->d_off_in.p, oi.data(), ((size_t)count + 1) * 8, c->stream));
-  CK(zrt_h2d(c->d_off_out.p, oo.data(), ((size_t)count + 1) * 8, c->stream));
-  CK(zrt_sync(c->stream));
-  int rc = dev_deflate_batch(c, c->d_in.as<u8>(), c->d_off_in.as<u64>(), oi.data(), count, c->d_out.as<u8>(), c->d_off_out.as<u64>(),
-                             c->d_len.as<u64>(), c->d_status.as<int32_t>());
-  if (rc == ZLES_E_CUDA || rc == ZLES_E_ARG) return rc;
-  CK(zrt_d2h(out + out_off[0], c->d_out.p, nout, c->stream));
-  CK(zrt_d2h(out_len, c->d_len.p, (size_t)count * 8, c->stream));
-  CK(zrt_d2h(status, c->d_status.p, (size_t)count * 4, c->stream));
-  CK(zrt_sync(c->stream));
-  return rc;
+  return batch_host(c, false, in, in_off, count, out, out_off, out_len, status);
 }
 
 // Batch deflate: every buffer is its own zlib stream (header, blocks, Adler-32 trailer all

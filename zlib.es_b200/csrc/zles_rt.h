@@ -66,8 +66,14 @@ static __global__ void zrt_k_mail(unsigned *dst, const unsigned *src, unsigned n
   for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
   __threadfence_system();
 }
+static __global__ void zrt_k_mail_wide(unsigned *dst, const unsigned *src, size_t nwords) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
 static inline zrt_err_t zrt_mail(void *h, const void *d, size_t n, zrt_stream_t st) {
-  zrt_k_mail<<<1, 32, 0, st>>>(reinterpret_cast<unsigned *>(h), reinterpret_cast<const unsigned *>(d), (unsigned)(n / 4));
+  const size_t nw = n / 4;
+  if (nw <= 64) zrt_k_mail<<<1, 32, 0, st>>>(reinterpret_cast<unsigned *>(h), reinterpret_cast<const unsigned *>(d), (unsigned)nw);
+  else zrt_k_mail_wide<<<(unsigned)((nw + 1023) / 1024 < 64 ? (nw + 1023) / 1024 : 64), 256, 0, st>>>(reinterpret_cast<unsigned *>(h), reinterpret_cast<const unsigned *>(d), nw);
   return cudaGetLastError();
 }
 static inline zrt_err_t zrt_sync(zrt_stream_t st) { return cudaStreamSynchronize(st); }

@@ -225,6 +225,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def numa_nodes() -> int:
+    try:
+        return len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except OSError:
+        return 1
+
+
+def pinned_host(torch, nbytes: int, interleave: bool):
+    """A page-locked host buffer of nbytes (uint8 tensor).  interleave: its pages are spread over all NUMA nodes of the box
+    (set_mempolicy(MPOL_INTERLEAVE) around the first touch, then cudaHostRegister) — one process feeding GPUs on both
+    sockets from a buffer that sits on one node is limited by the socket interconnect, not by PCIe."""
+    import ctypes
+    import numpy as np
+    if interleave and numa_nodes() > 1:
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            nn = numa_nodes()
+            mask = ctypes.c_ulong((1 << nn) - 1)
+            if libc.syscall(238, 3, ctypes.byref(mask), ctypes.c_ulong(64)) == 0:   # set_mempolicy(MPOL_INTERLEAVE, all nodes)
+                try:
+                    arr = np.empty(nbytes, dtype=np.uint8)
+                    arr[::4096] = 0                                                  # first touch under the policy
+                finally:
+                    libc.syscall(238, 0, None, ctypes.c_ulong(0))                    # MPOL_DEFAULT
+                t = torch.from_numpy(arr)
+                if int(torch.cuda.cudart().cudaHostRegister(t.data_ptr(), nbytes, 0)) == 0:
+                    return t, "interleaved over %d NUMA nodes, cudaHostRegister" % nn
+        except Exception:
+            pass
+    return torch.empty(nbytes, dtype=torch.uint8).pin_memory(), "cudaHostAlloc (torch pin_memory)"
+
+
 def other_configs(c, torch, stream, dev):
     """BASELINE.json configs[1..3] on one GPU (parity-test cases; reported for context, best of 3, device-resident) and the
     parallel inflate of streams made by other encoders."""
@@ -404,8 +436,9 @@ def run_ours(args):
     # N = 1: zles_deflate + zles_inflate of the 8 GiB corpus on this GPU.  N > 1: one process (rank 0) drives all N GPUs
     # through the library's multi-GPU context; the other ranks wait.  Device tensors of the resident run are released first.
     src_host = None
+    host_how = None
     if rank == 0:
-        src_host = torch.empty(TOTAL, dtype=torch.uint8).pin_memory()
+        src_host, host_how = pinned_host(torch, TOTAL, multi)
     del src, comp, slice_
     try:
         del back
@@ -432,8 +465,8 @@ def run_ours(args):
             del tmp
         torch.cuda.empty_cache()
         hcap = c.deflate_bound(TOTAL)
-        h_comp = torch.empty(hcap, dtype=torch.uint8).pin_memory()
-        h_back = torch.empty(TOTAL, dtype=torch.uint8).pin_memory()
+        h_comp, _ = pinned_host(torch, hcap, multi)
+        h_back, _ = pinned_host(torch, TOTAL, multi)
         codec = zles.MultiCodec(list(range(world))) if multi else c
         e2e_steps = max(1, min(args.steps, 3))
         t_d = t_i = 0.0
@@ -451,6 +484,7 @@ def run_ours(args):
         assert torch.equal(h_back, src_host), "e2e round trip mismatch"
         e2e = {"value": round(TOTAL / ((t_d + t_i) / e2e_steps) / 1e9, 4), "unit": UNIT, "h2d_bytes_per_step": int(TOTAL + hc), "d2h_bytes_per_step": int(TOTAL + hc),
                "deflate_gbs": round(TOTAL / (t_d / e2e_steps) / 1e9, 4), "inflate_gbs": round(TOTAL / (t_i / e2e_steps) / 1e9, 4), "steps": e2e_steps,
+               "host_buffers": host_how, "numa_nodes": numa_nodes(),
                "how": ("zles_deflate + zles_inflate on pinned host buffers, wall clock around the calls" if not multi else
                        "zles_mgpu_deflate + zles_mgpu_inflate (one process, %d GPUs, pinned host buffers), wall clock around the calls" % world)}
         # the same calls with PAGEABLE host buffers (what a Node ArrayBuffer is): 1 GiB of the corpus, one warm-up + one timed pass

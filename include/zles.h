@@ -69,7 +69,7 @@ int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, 
  * Either way the stream stays within 3 % of the reference's size on the benchmark corpora ("Size"). */
 int zles_ctx_set_window_mode(zles_ctx *ctx, uint32_t mode);
 /* Host-buffer inflate of our own streams runs slab by slab (finished slabs are copied to the host while the next one is
- * decoded): blocks of 32 KiB per slab, a multiple of 4; 0 (default) = automatic (a quarter of the stream, 16..256 MiB). */
+ * decoded): blocks of 32 KiB per slab, a multiple of 4; 0 (default) = automatic (a quarter of the stream, 64..512 MiB; streams below 128 MiB are decoded in one go). */
 int zles_ctx_set_slab_blocks(zles_ctx *ctx, uint32_t blocks);
 /* Host-buffer inflate: a stream of at least `bytes` compressed bytes (default 96 MiB) is copied to the device in pieces
  * (a sixth of the threshold, doubling up to eight times that) that are scanned and decoded as they land, so that the copy

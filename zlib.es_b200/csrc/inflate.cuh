@@ -130,7 +130,8 @@ struct InfReader {
 // Builds the canonical arrays and the root LUT of one code from its lengths
 // (same assignment as generateHuffmanTable, /root/reference/src/huffman.ts:8-39:
 // by length, then ascending symbol; code <<= 1 per length).  n is a multiple of 32.
-__device__ __forceinline__ void inf_build(const u8 *lens, int n, int root, u16 *lut, u16 *sorted, InfTab *t, u16 *cur) {
+// canonical arrays of one code: per-length counts, first codes, offsets, and the symbols sorted by (length, symbol)
+__device__ __forceinline__ void inf_canon(const u8 *lens, int n, u16 *sorted, InfTab *t, u16 *cur) {
   const u32 lane = lane_id();
   if (lane < 16) t->cnt[lane] = 0;
   __syncwarp();
@@ -163,18 +164,21 @@ __device__ __forceinline__ void inf_build(const u8 *lens, int n, int root, u16 *
     }
     __syncwarp();
   }
-  for (u32 i = lane; i < (1u << root); i += 32) {
-    u32 code = 0, e = 0;
-    for (int l = 1; l <= root; l++) {
-      code = (code << 1) | ((i >> (l - 1)) & 1);
-      u32 d = code - t->first[l];
-      if (code >= t->first[l] && d < t->cnt[l]) {
-        e = ((u32)sorted[t->off[l] + d] << 4) | (u32)l;
-        break;
-      }
-    }
-    lut[i] = (u16)e;
+}
+// root-LUT entry of index i (the next `root` bits of the stream, LSB first): symbol << 4 | code length, 0 = no code of
+// at most `root` bits starts like this
+__device__ __forceinline__ u32 inf_lut_entry(u32 i, int root, const InfTab *t, const u16 *sorted) {
+  u32 code = 0;
+  for (int l = 1; l <= root; l++) {
+    code = (code << 1) | ((i >> (l - 1)) & 1);
+    const u32 d = code - t->first[l];
+    if (code >= t->first[l] && d < t->cnt[l]) return ((u32)sorted[t->off[l] + d] << 4) | (u32)l;
   }
+  return 0;
+}
+__device__ __forceinline__ void inf_build(const u8 *lens, int n, int root, u16 *lut, u16 *sorted, InfTab *t, u16 *cur) {
+  inf_canon(lens, n, sorted, t, cur);
+  for (u32 i = lane_id(); i < (1u << root); i += 32) lut[i] = (u16)inf_lut_entry(i, root, t, sorted);
   __syncwarp();
 }
 
@@ -539,10 +543,21 @@ __host__ __device__ __forceinline__ u64 seg_stored_src(u64 end_pos, u64 out_len,
 //   bits 8-23 literal value / length base / distance base | bit 24 length | bit 25 end of block | bit 26 invalid
 constexpr u32 TK_LEN = 1u << 24, TK_EOB = 1u << 25, TK_INV = 1u << 26;
 
+// What a token decoder keeps per warp besides its two 32-bit LUTs.  (No 16-bit LUTs as in InfWarpSmem: the 32-bit ones
+// are filled straight from the canonical arrays — 2.5 KB less per warp is two more CTAs per SM for k_inf_tokens.)
+struct TokCore {
+  u16 lut_d[1 << CL_ROOT];  // the code-length code's LUT while a header is parsed
+  u16 sorted_ll[288];
+  u16 sorted_d[64];
+  InfTab tab_ll, tab_d;
+  u16 cur[16];
+  u8 lens[352];  // [0,288) literal/length code lengths, [288,352) distance code lengths
+  u8 cl_lens[32];
+};
 struct TokWarpSmem {
   u32 lut_ll[1 << LL_ROOT];
   u32 lut_d[1 << D_ROOT];
-  InfWarpSmem w;  // code lengths, canonical arrays, 16-bit LUTs the 32-bit ones are expanded from
+  TokCore w;
 };
 constexpr int TOK_SMEM = (int)sizeof(TokWarpSmem) * INF_WARPS;
 
@@ -555,6 +570,24 @@ __device__ __forceinline__ u32 tk_entry_ll(u32 sym, u32 l) {
 __device__ __forceinline__ u32 tk_entry_d(u32 sym, u32 l) {
   if (sym >= 30) return TK_INV | l;
   return ((u32)c_dist_base[sym] << 8) | ((u32)c_dist_extra[sym] << 4) | l;
+}
+// both codes of a block from T->w.lens: canonical arrays and the 32-bit root LUTs.  Symbols the reference's tables do not
+// define (286, 287, distance codes 30..) are left out of the fast tables: they take the slow path, which hands the block
+// to the sequential decoder.
+__device__ __forceinline__ void tk_build_tables(TokWarpSmem *T) {
+  TokCore *S = &T->w;
+  inf_canon(S->lens, 288, S->sorted_ll, &S->tab_ll, S->cur);
+  for (u32 i = lane_id(); i < (1u << LL_ROOT); i += 32) {
+    const u32 e = inf_lut_entry(i, LL_ROOT, &S->tab_ll, S->sorted_ll);
+    T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0;
+  }
+  __syncwarp();
+  inf_canon(S->lens + 288, 32, S->sorted_d, &S->tab_d, S->cur);
+  for (u32 i = lane_id(); i < (1u << D_ROOT); i += 32) {
+    const u32 e = inf_lut_entry(i, D_ROOT, &S->tab_d, S->sorted_d);
+    T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0;
+  }
+  __syncwarp();
 }
 
 // warp-uniform bit reader for phase A: the bit buffer is kept as two 32-bit halves so that every
@@ -670,7 +703,7 @@ struct SpecReader : TokReader {
 };
 
 // dynamic block header for phase A (same as inf_read_dynamic_header, on the TokReader)
-__device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, InfWarpSmem *S, u32 &status) {
+__device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, TokCore *S, u32 &status) {
   const u32 lane = lane_id();
   const u32 HLIT = r.take(5) + 257;
   const u32 HDIST = r.take(5) + 1;
@@ -751,7 +784,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
       thresh += SUB / 4;                                                             \
     }                                                                                \
   } while (0)
-  InfWarpSmem *S = &T->w;
+  TokCore *S = &T->w;
   TokReader r;
   r.init(in, n, in_pos);
   u32 o = 0, nt = 0;
@@ -800,12 +833,7 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
     } else {
       if (!tk_read_dynamic_header(r, S, status)) break;
     }
-    inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
-    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
-    // invalid symbols (286, 287, distance 30, 31) are left out of the fast tables: they take the slow path, which rejects them
-    for (u32 i = lane; i < (1u << LL_ROOT); i += 32) { const u32 e = S->lut_ll[i]; T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0; }
-    for (u32 i = lane; i < (1u << D_ROOT); i += 32) { const u32 e = S->lut_d[i]; T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0; }
-    __syncwarp();
+    tk_build_tables(T);
     // symbol loop (/root/reference/src/inflate.ts:237-291 without the copy).  It cannot run away: every
     // token accounts for at least one output byte and a token is only emitted while o < SUB.
     // Every round, lane i decodes the token that would start i bits from the current position — both table

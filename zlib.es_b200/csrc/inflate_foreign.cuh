@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_hdr_scan(const u8 *__restrict__ in, u64
 // One block, from its BFINAL bit to its end-of-block code, into tokens.
 __device__ __forceinline__ void fb_block_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 bit, u32 *tok, u32 tok_cap, FbRes *res) {
   const u32 lane = lane_id();
-  InfWarpSmem *S = &T->w;
+  TokCore *S = &T->w;
   TokReader r;
   r.init(in, n, bit >> 3);
   r.skip((u32)(bit & 7));
@@ -193,10 +193,7 @@ __device__ __forceinline__ void fb_block_tokens(TokWarpSmem *T, const u8 *in, u6
   const u32 btype = r.take(2);
   u32 status = 0;
   if (btype == 2 && tk_read_dynamic_header(r, S, status)) {
-    inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
-    inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
-    for (u32 i = lane; i < (1u << LL_ROOT); i += 32) { const u32 e = S->lut_ll[i]; T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0; }
-    for (u32 i = lane; i < (1u << D_ROOT); i += 32) { const u32 e = S->lut_d[i]; T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0; }
+    tk_build_tables(T);
     __syncwarp();
     for (;;) {
       r.refill();

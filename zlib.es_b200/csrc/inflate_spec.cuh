@@ -58,7 +58,7 @@ __device__ __forceinline__ void spec_decode_at(const SpecReader &sr, const TokWa
 // One token the canonical way (codes longer than the root tables), at the reader's position; the reader moves past it.
 // Returns 0 = a token (tokv, olen), 1 = end of block, 2 = not a valid code.
 __device__ __forceinline__ u32 spec_slow_token(SpecReader &sr, const TokWarpSmem *T, u32 &tokv, u32 &olen, u32 &bits) {
-  const InfWarpSmem *S = &T->w;
+  const TokCore *S = &T->w;
   u32 lo, hi;
   sr.at(0, lo, hi);
   u32 e = T->lut_ll[lo & ((1u << LL_ROOT) - 1)];
@@ -208,7 +208,7 @@ k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos,
   ZLES_SMEM_DECL(smem_raw);
   SpecShared *Sh = reinterpret_cast<SpecShared *>(smem_raw);
   TokWarpSmem *T = &Sh->T;
-  InfWarpSmem *S = &T->w;
+  TokCore *S = &T->w;
   const u32 lane = lane_id(), w = warp_id(), tid = threadIdx.x;
   for (;;) {
     __syncthreads();  // everybody is done with the previous block's shared state
@@ -231,10 +231,7 @@ k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos,
         const u32 btype = r.take(2);
         u32 status = 0;
         if (btype == 2 && tk_read_dynamic_header(r, S, status)) {
-          inf_build(S->lens, 288, LL_ROOT, S->lut_ll, S->sorted_ll, &S->tab_ll, S->cur);
-          inf_build(S->lens + 288, 32, D_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
-          for (u32 i = lane; i < (1u << LL_ROOT); i += 32) { const u32 e = S->lut_ll[i]; T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0; }
-          for (u32 i = lane; i < (1u << D_ROOT); i += 32) { const u32 e = S->lut_d[i]; T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0; }
+          tk_build_tables(T);
           const u64 bp = r.bitpos();
           if (seg_end > in_pos && (seg_end << 3) > bp && (seg_end - in_pos) < (1u << 19)) {
             sym_start = (u32)(bp - bit0);

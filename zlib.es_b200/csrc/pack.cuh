@@ -165,14 +165,30 @@ __device__ __forceinline__ void pack_emit(PackState &st, const u64 *bits, const 
   __syncthreads();
   const u32 avail = st.carry_bits + total;
   const u32 nfull = avail >> 5;
-  for (u32 i = threadIdx.x; i < nfull; i += PACK_THREADS) {
-    const u32 v = st.stage[i];
-    if (st.wcur + i == 0 && st.head) {
-      u8 *p = reinterpret_cast<u8 *>(st.gw);
-      for (u32 k = st.head; k < 4; k++) p[k] = (u8)(v >> (8 * k));
-    } else {
-      st.gw[st.wcur + i] = v;
+  // full words go out with 128-bit stores (coalesced: a warp writes 512 contiguous bytes per instruction — to local HBM
+  // or, through a peer-mapped pointer, over NVLink); the words before the first 16-byte boundary of the destination and
+  // the up to three after the last one with 32-bit stores, the block's first partial word byte by byte
+  {
+    u32 *g = st.gw + st.wcur;
+    u32 pre = (u32)((16 - ((uintptr_t)g & 15)) & 15) >> 2;  // words up to the 16-byte boundary
+    if (st.wcur == 0 && st.head && pre == 0) pre = 4;       // the block's first word holds somebody else's bytes: never in a vector
+    pre = umin(pre, nfull);
+    const u32 nvec = (nfull - pre) >> 2;
+    for (u32 i = threadIdx.x; i < pre; i += PACK_THREADS) {
+      const u32 v = st.stage[i];
+      if (st.wcur + i == 0 && st.head) {
+        u8 *p = reinterpret_cast<u8 *>(st.gw);
+        for (u32 k = st.head; k < 4; k++) p[k] = (u8)(v >> (8 * k));
+      } else {
+        g[i] = v;
+      }
     }
+    uint4 *g4 = reinterpret_cast<uint4 *>(g + pre);
+    for (u32 i = threadIdx.x; i < nvec; i += PACK_THREADS) {
+      const u32 *sp = st.stage + pre + 4 * i;
+      g4[i] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    for (u32 i = pre + 4 * nvec + threadIdx.x; i < nfull; i += PACK_THREADS) g[i] = st.stage[i];
   }
   const u32 carry = st.stage[nfull];
   __syncthreads();

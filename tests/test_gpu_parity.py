@@ -281,3 +281,40 @@ def test_raw_deflate_and_gzip(c):
 
 def test_host_batch_in_slabs(c):
     P.batch_in_slabs(c, 3000)
+
+
+def test_large_pageable_buffers_are_staged(c):
+    # what the N-API addon passes are pageable ArrayBuffers: at 32 MiB and more they go through the pinned staging ring and
+    # its helper threads (stager.inl) — same bytes as with pinned buffers, in both directions, one and several devices
+    import torch
+    import zles
+    n = 200 << 20
+    with torch.cuda.stream(torch.cuda.current_stream()):
+        src = torch.empty(n, dtype=torch.uint8, device="cuda")
+        c.dev_corpus(3, 0, src.data_ptr(), n)
+    pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
+    pinned.copy_(src)
+    torch.cuda.synchronize()
+    pageable = np.array(pinned.numpy(), copy=True)
+    cap = c.deflate_bound(n)
+    z_pin = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    z_pag = np.empty(cap, dtype=np.uint8)
+    m1 = c.deflate_into(pinned.numpy(), z_pin.numpy())
+    m2 = c.deflate_into(pageable, z_pag)
+    assert m1 == m2 and bool((z_pin.numpy()[:m1] == z_pag[:m2]).all())
+    back = np.empty(n, dtype=np.uint8)
+    for smin in (96 << 20, 1 << 40):       # streaming path and plain path
+        c.set_stream_min(smin)
+        try:
+            back[:] = 0
+            assert c.inflate_into(z_pag[:m2], back) == n and bool((back == pageable).all())
+        finally:
+            c.set_stream_min(96 << 20)
+    mc = zles.MultiCodec([0, 0] if torch.cuda.device_count() < 2 else [0, 1])
+    try:
+        z2 = np.empty(cap, dtype=np.uint8)
+        assert mc.deflate_into(pageable, z2) == m1 and bool((z2[:m1] == z_pag[:m1]).all())
+        back[:] = 0
+        assert mc.inflate_into(z2[:m1], back) == n and bool((back == pageable).all())
+    finally:
+        mc.close()

@@ -101,6 +101,8 @@ struct HostMail {
 
 constexpr u32 BATCH_SLAB_STREAMS = 16384;  // host batch calls: buffers per slab at most
 
+#include "stager.inl"
+
 struct zles_ctx {
   int device = 0;
   zrt_stream_t stream{};
@@ -131,6 +133,7 @@ struct zles_ctx {
   HostMail *mail = nullptr;  // pinned
   u64 *slab_mail = nullptr;  // pinned: where each slab of a pipelined host-buffer deflate ends (bytes)
   size_t slab_mail_cap = 0;
+  StageRing ring_in, ring_out;  // pinned staging of large pageable host buffers (stager.inl)
   u64 *cand_mail = nullptr;  // pinned: block starts read back by scan_block_starts
   size_t cand_mail_cap = 0;
   CorpusTable *d_corpus = nullptr;
@@ -314,6 +317,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   c->cand_mail = nullptr;
   if (c->batch_stage) zrt_host_free(c->batch_stage);
   c->batch_stage = nullptr;
+  c->ring_in.release();
+  c->ring_out.release();
   timing_collect(c);
   for (zrt_event_t e : c->event_pool) zrt_event_destroy(e);
   if (c->d_corpus) zrt_free(c->d_corpus);
@@ -494,6 +499,7 @@ struct DeflatePipe {
   u8 *d_out;      // device staging for the raw deflate bytes (room for zles_deflate_bound)
   u8 *h_out;      // caller's buffer for them
   size_t h_cap;   // its capacity in bytes
+  Drainer *drain = nullptr;  // the caller's buffer is pageable: copies to it go through the pinned staging ring
   bool defer = false;  // pack slab by slab into d_out but leave the copy to the host to the caller (multi-GPU: a shard's
                        // place in the stream is only known once every shard before it has been laid out)
   bool done = false, overflow = false;
@@ -571,6 +577,18 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   }
   const u32 nslabs = (u32)slab_begin.size() - 1;
   const bool piped = pipe && h_src && nslabs > 1;
+  // a large pageable source is staged through pinned memory by helper threads (stager.inl), slab by slab
+  Feeder feeder;
+  bool staged = false;
+  if (h_src && n >= STAGE_MIN && host_is_pageable(h_src)) {
+    std::vector<StagePiece> pieces;
+    for (u32 si = 0; si < nslabs; si++) {
+      const size_t off = (size_t)slab_begin[si] * SUB, len = (size_t)umin64((u64)(slab_begin[si + 1] - slab_begin[si]) * SUB, (u64)n - off);
+      for (size_t o = 0; o < len; o += STAGE_SLOT)
+        pieces.push_back(StagePiece{h_src + off + o, const_cast<u8 *>(d_in) + off + o, std::min<size_t>(STAGE_SLOT, len - o), si});
+    }
+    staged = feeder.start(c->device, &c->ring_in, c->copy_stream, std::move(pieces), nslabs) == 0;
+  }
   std::vector<zrt_event_t> slab_ev;
   if (piped && !pipe->defer) {
     if (c->slab_mail_cap < nslabs) {
@@ -586,7 +604,11 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     const u32 b0 = slab_begin[si], b1 = slab_begin[si + 1];
     if (h_src) {
       const size_t off = (size_t)b0 * SUB, len = (size_t)umin64((u64)(b1 - b0) * SUB, (u64)n - off);
-      if (len) CK(zrt_h2d(const_cast<u8 *>(d_in) + off, h_src + off, len, c->copy_stream));
+      if (staged) {
+        if (!feeder.wait_group(si)) return cuda_fail(zrt_last_error(), "staged copy to device");
+      } else if (len) {
+        CK(zrt_h2d(const_cast<u8 *>(d_in) + off, h_src + off, len, c->copy_stream));
+      }
       zrt_event_t ev = timing_event(c);
       CK(zrt_event_record(ev, c->copy_stream));
       CK(zrt_stream_wait_event(c->stream, ev));
@@ -630,16 +652,21 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
       CK(zrt_event_sync(slab_ev[si]));
       const u64 end = c->slab_mail[si];
       if (end > pipe->h_cap) pipe->overflow = true;
-      if (!pipe->overflow && end > prev) CK(zrt_d2h(pipe->h_out + prev, pipe->d_out + prev, (size_t)(end - prev), c->copy_stream));
+      if (!pipe->overflow && end > prev) {
+        if (pipe->drain) { if (!pipe->drain->push(pipe->h_out + prev, pipe->d_out + prev, (size_t)(end - prev))) return cuda_fail(zrt_last_error(), "staged copy to host"); }
+        else CK(zrt_d2h(pipe->h_out + prev, pipe->d_out + prev, (size_t)(end - prev), c->copy_stream));
+      }
       prev = end;
       c->event_pool.push_back(slab_ev[si]);
     }
+    if (pipe->drain && !pipe->drain->finish()) return cuda_fail(zrt_last_error(), "staged copy to host");
     zrt_event_t ev = timing_event(c);
     CK(zrt_event_record(ev, c->copy_stream));
     CK(zrt_stream_wait_event(c->stream, ev));
     c->event_pool.push_back(ev);
     pipe->done = true;
   }
+  if (staged && !feeder.finish()) return cuda_fail(zrt_last_error(), "staged copy to device");
 
   LayoutParams yp;
   yp.blk_bits = c->blk_bits.as<u32>();
@@ -823,10 +850,12 @@ static int deflate_host(zles_ctx *c, int fmt, const uint8_t *in, size_t n, uint8
   zles_shard_info info;
   DeflatePipe pipe;
   DeflatePipe *pp = nullptr;
+  Drainer drain;
   if (out && cap >= H + T && c->d_out.reserve(zles_deflate_bound(n) + 16) == 0) {  // raw deflate bytes go to out + H .. cap - T
     pipe.d_out = c->d_out.as<u8>() + 2;
     pipe.h_out = out + H;
     pipe.h_cap = cap - H - T;
+    if (n >= STAGE_MIN && host_is_pageable(out) && drain.start(c->device, &c->ring_out, c->out_stream) == 0) pipe.drain = &drain;
     pp = &pipe;
   }
   // the host-to-device copy is pipelined with the matcher, and (long inputs) packing and the copy back with it too
@@ -1264,6 +1293,7 @@ struct SlabDecoder {
   u8 *h_out;
   size_t h_cap;
   u32 slab_blocks;
+  Drainer *drain = nullptr;  // the caller's buffer is pageable: finished slabs go through the pinned staging ring
   size_t slab_out = 0;
   zrt_event_t done[2], copied[2];
   bool copied_valid[2] = {false, false};
@@ -1299,7 +1329,10 @@ struct SlabDecoder {
     if (!(last && has_final) && olen != (b1 - b0) * (size_t)SUB) return -1;
     CK(zrt_event_record(done[k & 1], c->stream));
     CK(zrt_stream_wait_event(c->out_stream, done[k & 1]));
-    if (olen) CK(zrt_d2h(h_out + off, d_slab, olen, c->out_stream));
+    if (olen) {
+      if (drain) { if (!drain->push(h_out + off, d_slab, olen)) return cuda_fail(zrt_last_error(), "staged copy to host"); }
+      else CK(zrt_d2h(h_out + off, d_slab, olen, c->out_stream));
+    }
     CK(zrt_event_record(copied[k & 1], c->out_stream));
     copied_valid[k & 1] = true;
     total = off + olen;
@@ -1307,7 +1340,10 @@ struct SlabDecoder {
     return 0;
   }
   int finish() {
+    bool drained = true;
+    if (drain) drained = drain->finish();
     zrt_err_t e = zrt_sync(c->out_stream);
+    if (e == ZRT_OK && !drained) e = zrt_last_error();
     TRACE("slabs: copies done");
     if (have_events)
       for (int i = 0; i < 2; i++) { c->event_pool.push_back(done[i]); c->event_pool.push_back(copied[i]); }
@@ -1323,7 +1359,9 @@ static int inflate_slabs_to_host(zles_ctx *c, const u8 *d_in, size_t n, const st
   if (B == 0) return -1;
   // every block but the last stands for exactly 32 KiB: when those cannot fit, the general path reports the exact size
   if (B > 1 && (u64)(B - 1) * SUB > (u64)h_cap) return -1;
+  Drainer drain;
   SlabDecoder sd{c, d_in, has_final, h_out, h_cap, slab_blocks};
+  if (B * (size_t)SUB >= STAGE_MIN && host_is_pageable(h_out) && drain.start(c->device, &c->ring_out, c->out_stream) == 0) sd.drain = &drain;
   RET(sd.begin());
   int rc = 0;
   for (size_t b0 = 0; b0 < B && rc == 0; b0 += sd.slab_blocks) {
@@ -1350,16 +1388,31 @@ static int inflate_streaming_to_host(zles_ctx *c, const u8 *h_in, size_t n, u64 
   for (size_t sz = piece0; pb.back() < n; sz = sz < 8 * piece0 ? sz * 2 : sz) pb.push_back(pb.back() + sz < n ? pb.back() + sz : n);
   const size_t np = pb.size() - 1;
   std::vector<zrt_event_t> ev(np);
+  Feeder feeder;
+  bool staged = false;
+  if (n >= STAGE_MIN && host_is_pageable(h_in)) {  // a pageable source goes through the pinned staging ring (stager.inl)
+    std::vector<StagePiece> pieces;
+    for (size_t i = 0; i < np; i++)
+      for (size_t o = pb[i]; o < pb[i + 1]; o += STAGE_SLOT) pieces.push_back(StagePiece{h_in + o, d_in + o, std::min<size_t>(STAGE_SLOT, pb[i + 1] - o), (u32)i});
+    staged = feeder.start(c->device, &c->ring_in, c->copy_stream, std::move(pieces), (u32)np) == 0;
+  }
   for (size_t i = 0; i < np; i++) {
-    CK(zrt_h2d(d_in + pb[i], h_in + pb[i], pb[i + 1] - pb[i], c->copy_stream));
     ev[i] = timing_event(c);
+    if (staged) continue;  // recorded below, once the piece's copies have been enqueued
+    CK(zrt_h2d(d_in + pb[i], h_in + pb[i], pb[i + 1] - pb[i], c->copy_stream));
     CK(zrt_event_record(ev[i], c->copy_stream));
   }
+  Drainer drain;
   SlabDecoder sd{c, d_in, true, h_out, h_cap, c->inf_slab_blocks ? c->inf_slab_blocks : INF_SLAB_BLOCKS};
+  if (h_cap >= STAGE_MIN && host_is_pageable(h_out) && drain.start(c->device, &c->ring_out, c->out_stream) == 0) sd.drain = &drain;
   int rc = sd.begin();
   std::vector<u64> starts, found;
   size_t next = 0;  // first block not decoded yet
   for (size_t i = 0; i < np && rc == 0; i++) {
+    if (staged) {
+      if (!feeder.wait_group((u32)i)) { rc = cuda_fail(zrt_last_error(), "staged copy to device"); break; }
+      CK(zrt_event_record(ev[i], c->copy_stream));
+    }
     CK(zrt_stream_wait_event(c->stream, ev[i]));
     const size_t lo = i == 0 ? 0 : pb[i] - 16, hi = pb[i + 1];
     const int rs = scan_block_starts(c, d_in + lo, hi - lo, i == 0 ? first : 15, found);
@@ -1377,6 +1430,7 @@ static int inflate_streaming_to_host(zles_ctx *c, const u8 *h_in, size_t n, u64 
     }
   }
   for (size_t i = 0; i < np; i++) c->event_pool.push_back(ev[i]);
+  if (staged && !feeder.finish() && rc == 0) rc = cuda_fail(zrt_last_error(), "staged copy to device");
   zrt_err_t e = zrt_sync(c->copy_stream);  // whatever happens next needs the whole stream on the device
   const int rf = sd.finish();
   if (e != ZRT_OK) return cuda_fail(e, "copy to device");

@@ -190,19 +190,28 @@ def damaged_streams(c):
 def foreign_tier(c, n):
     """Streams of other encoders — zlib.es's own bit-concatenated blocks (no markers), system zlib at several
     levels (32 KiB history across blocks, stored and empty blocks) — are decoded by the block-parallel path
-    (k_hdr_scan / k_blk_tokens / k_blk_resolve or the symbolic-window passes), not by the sequential warp, and
+    (k_hdr_filter / k_fblk_map / k_fpiece_sym and the symbolic-window passes), not by the sequential warp, and
     give the reference's bytes."""
     import numpy as np
     rng = np.random.default_rng(11)
     data = (T.gen("G5", n // 2) + T.fixture_raw() + rng.integers(0, 256, 20000, dtype=np.uint8).tobytes())[:n]
     co = zlib.compressobj(6)
     flushed = co.compress(data[:50000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[50000:]) + co.flush()
+    cf = zlib.compressobj(6, zlib.DEFLATED, 15, 8, zlib.Z_FIXED)   # fixed-Huffman blocks only (src/inflate.ts:57-118)
+    fixed = cf.compress(data) + cf.flush()
+    # fixed, stored and dynamic blocks in one stream: raw-deflate pieces, each flushed to a byte boundary, under one zlib frame
+    def raw_piece(b, level, strategy, last):
+        cr = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        return cr.compress(b) + (cr.flush() if last else cr.flush(zlib.Z_FULL_FLUSH))
+    mixed = (b"\x78\x9c" + raw_piece(data[:70000], 6, zlib.Z_FIXED, False) + raw_piece(data[70000:90000], 0, zlib.Z_DEFAULT_STRATEGY, False)
+             + raw_piece(data[90000:], 6, zlib.Z_DEFAULT_STRATEGY, True) + zlib.adler32(data).to_bytes(4, "big"))
+    assert zlib.decompress(mixed) == data
     for name, z in [("zlib.es", O.deflate(data)), ("zlib1", zlib.compress(data, 1)), ("zlib6", zlib.compress(data, 6)),
                     ("zlib9", zlib.compress(data, 9)), ("zlib0", zlib.compress(data[:200000], 0)), ("sync-flush", flushed),
-                    ("fixture", T.fixture_compressed())]:
+                    ("fixture", T.fixture_compressed()), ("fixed", fixed), ("fixed+stored+dynamic", mixed)]:
         c.set_timing(True)
         out = c.inflate(z)
-        used = c.kernel_time("k_blk_resolve")[1] + c.kernel_time("k_run_resolve")[1]
+        used = c.kernel_time("k_fpiece_sym")[1]
         seq = c.kernel_time("k_inflate")[1]
         c.set_timing(False)
         assert out == O.inflate(z), name

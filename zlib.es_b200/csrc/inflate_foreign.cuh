@@ -3,32 +3,31 @@
 // (/root/reference/src/deflate.ts:20-34, src/lz77.ts:11-22,37) without any marker, so block
 // starts have to be found.
 //
-//   k_hdr_scan      every bit position of the stream is tested for being the start of a dynamic
+//   k_hdr_filter / k_hdr_verify
+//                   every bit position of the stream is tested for being the start of a dynamic
 //                   block (BTYPE=2): field ranges, a complete code-length code, code lengths that
 //                   decode without overrun into complete literal/length and distance codes with an
 //                   end-of-block code.  What passes is a candidate (false positives are harmless).
-//   k_blk_tokens    one warp per candidate decodes that ONE block into tokens (same decoder as
-//                   phase A of inflate.cuh) and records where it ends, how many bytes it stands
-//                   for and how far before its own start it reaches.
-//   (host)          walks the chain from the first block: the block after one that ends at bit e is
-//                   the candidate at bit e, until a BFINAL block.  Any gap (a stored or fixed block,
-//                   an error) hands the stream to the sequential decoder, which is exact about the
-//                   reference's behaviour on every input.
-//   k_blk_resolve   phase B when no block reaches before its own start (zlib.es streams): every
-//                   block is copied on its own warp.
-//   k_run_resolve / k_win_propagate / k_sym_finalize
-//                   phase B when blocks use the 32 KiB before them (system zlib): the chain is cut into
-//                   runs of >= 256 KiB; every run is resolved in parallel into 16-bit symbols, a byte
-//                   that comes from the unknown 32 KiB window before the run staying symbolic
-//                   (0x8000 | window offset, copied around like any other value); then the windows are
-//                   made concrete run after run (32 KiB each, cheap), and a last parallel pass
-//                   substitutes them (the two-pass scheme of pugz / rapidgzip).
+//   k_fblk_tokens   (inflate_fblk.cuh) one CTA per candidate decodes that ONE block, dynamic or fixed, into tokens — its
+//                   coded bits cut into up to 16 pieces decoded side by side — and records where it ends and how
+//                   many bytes it stands for.
+//   (host)          walks the chain from the first block: the block after one that ends at bit e is the candidate at
+//                   bit e, until a BFINAL block; a block the scan cannot recognise (a fixed block: its header is three
+//                   bits) is decoded on demand when the chain reaches it.  An error hands the stream to the sequential
+//                   decoder, which is exact about the reference's behaviour on every input.
+//   k_fpiece_sym / k_frun_merge / k_win_propagate / k_sym_finalize
+//                   phase B: every piece is resolved on its own warp into 16-bit symbols, a byte that comes from
+//                   before the piece staying symbolic (0x8000 | offset into the 32 KiB before it, copied around like
+//                   any other value); the pieces of a run of blocks (>= 128 KiB) are made concrete in order; what
+//                   reaches before a run refers to the run's window; the windows are made concrete run after run
+//                   (32 KiB each, cheap; skipped when no run kept a reference — zlib.es streams), and a last parallel
+//                   pass substitutes them (the two-pass scheme of pugz / rapidgzip).
 #pragma once
 #include "inflate.cuh"
 
 namespace zles {
 
-constexpr u32 FB_TOK = 131072 + 32;  // token capacity per block (a zlib.es block of 128 KiB of literals fits)
+constexpr u32 FB_TOK = 1u << 22;      // token capacity per block at most
 constexpr u32 FB_OK = 1;       // a decoded dynamic block
 
 struct FbRes {
@@ -37,7 +36,7 @@ struct FbRes {
   u32 ntok;
   u32 status;      // FB_OK or 0
   u32 bfinal;
-  u32 hist_need;   // how many bytes before the block's own start its matches reach
+  u32 npieces;     // pieces it was decoded in (inflate_fblk.cuh)
   u32 pad;
 };
 
@@ -143,149 +142,93 @@ struct FbStored {   // a stored-block candidate found by the scan
   u32 bfinal;
 };
 
-struct FbChainEnt { // one block of the accepted chain, as phase B needs it
-  u64 a;            // dynamic: offset of its tokens in the token buffer; stored: byte offset of its payload in the input
-  u32 b;            // dynamic: number of tokens; stored: LEN
-  u32 stored;
-};
-
-// thread per byte of the stream, 8 bit offsets each; candidates are appended in no particular order:
-// dynamic-block headers to cand[], stored-block headers to st[]; cnt[0] / cnt[1] count them
-__global__ void __launch_bounds__(256) k_hdr_scan(const u8 *__restrict__ in, u64 n, u64 first_bit, u64 *cand, u32 cap, FbStored *st, u32 st_cap,
-                                                  u32 *cnt) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 B = (u64)blockIdx.x * blockDim.x + threadIdx.x; B < n; B += stride) {
-    const u32 w = fb_bits(in, n, B << 3, 24);
+// The scan, in two steps.  k_hdr_filter: a thread per byte of the stream, 8 bit offsets each, everything from registers
+// (the CTA's 256 bytes + 16 are staged in shared memory once): stored-block headers (LEN = ~NLEN) go to st[], and a
+// position that could start a dynamic block — BTYPE, HLIT / HDIST in range, and a code-length code that is complete
+// (or a single code), its Kraft sum taken three 3-bit lengths at a time from a 512-entry table — to surv[]: about one
+// bit position in a thousand.  k_hdr_verify: a thread per survivor runs the full test (fb_header_ok).  Candidates are
+// appended in no particular order.  cnt[0] = dynamic candidates, cnt[1] = stored candidates, cnt[2] = survivors.
+constexpr int HS_THREADS = 256;
+constexpr int HS_HALO_WORDS = 4;
+constexpr int HS_SMEM = 1024 + (HS_THREADS / 4 + HS_HALO_WORDS) * 4;
+__global__ void __launch_bounds__(HS_THREADS) k_hdr_filter(const u8 *__restrict__ in, u64 n, u64 first_bit, u64 *surv, u32 surv_cap, FbStored *st,
+                                                           u32 st_cap, u32 *cnt) {
+  ZLES_SMEM_DECL(smem_raw);
+  u16 *lut = reinterpret_cast<u16 *>(smem_raw);                 // [512]
+  u32 *tile = reinterpret_cast<u32 *>(smem_raw + 1024);         // [HS_THREADS / 4 + HS_HALO_WORDS]
+  const u32 tid = threadIdx.x;
+  for (u32 i = tid; i < 512; i += HS_THREADS) {
+    u32 k = 0, used = 0;
+    for (u32 q = 0; q < 3; q++) {
+      const u32 l = (i >> (3 * q)) & 7;
+      if (l) { k += 128u >> l; used++; }
+    }
+    lut[i] = (u16)(k | (used << 12));
+  }
+  const bool aligned = ((uintptr_t)in & 3) == 0;
+  const u64 ntiles = (n + HS_THREADS - 1) / HS_THREADS;
+  for (u64 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    __syncthreads();
+    const u64 base = t * HS_THREADS;
+    if (tid < HS_THREADS / 4 + HS_HALO_WORDS) {
+      const u64 b = base + 4 * tid;
+      u32 w = 0;
+      if (aligned && b + 4 <= n) {
+        w = __ldg(reinterpret_cast<const u32 *>(in + b));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (b + q < n) w |= (u32)in[b + q] << (8 * q);
+      }
+      tile[tid] = w;
+    }
+    __syncthreads();
+    const u64 B = base + tid;
+    if (B >= n) continue;
+    const u32 k = tid >> 2, sh = (tid & 3) * 8;
+    const u32 w0 = tile[k], w1 = tile[k + 1], w2 = tile[k + 2], w3 = tile[k + 3];
+    const u32 x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh);  // the 96 bits from byte B on
+#pragma unroll
     for (u32 s = 0; s < 8; s++) {
-      const u32 h = w >> s;
       const u64 bit = (B << 3) + s;
       if (bit < first_bit) continue;
-      if (((h >> 1) & 3) == 0) {
+      const u32 h = __funnelshift_r(x0, x1, s);
+      const u32 bt = (h >> 1) & 3;
+      if (bt == 0) {
         // a stored block (RFC 1951 3.2.4): after the 3 header bits and the pad, LEN and its complement
-        const u64 q = (bit + 3 + 7) >> 3;
-        if (q + 4 <= n) {
-          const u32 len = (u32)in[q] | ((u32)in[q + 1] << 8), nlen = (u32)in[q + 2] | ((u32)in[q + 3] << 8);
-          if ((len ^ nlen) == 0xffffu && q + 4 + len <= n) {
-            const u32 o = atomicAdd(cnt + 1, 1u);
-            if (o < st_cap) { st[o].bit = bit; st[o].len = len; st[o].bfinal = h & 1; }
-          }
+        const u32 qo = (s + 10) >> 3;  // 1 or 2 bytes after B
+        const u32 v = __funnelshift_r(x0, x1, 8 * qo);
+        const u32 len = v & 0xffffu, nlen = v >> 16;
+        if ((len ^ nlen) == 0xffffu && B + qo + 4 + len <= n) {
+          const u32 o = atomicAdd(cnt + 1, 1u);
+          if (o < st_cap) { st[o].bit = bit; st[o].len = len; st[o].bfinal = h & 1; }
         }
-      } else if (((h >> 1) & 3) == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29) {  // quick reject, then the full test
-        if (fb_header_ok(in, n, bit)) {
-          const u32 o = atomicAdd(cnt, 1u);
-          if (o < cap) cand[o] = bit;
+      } else if (bt == 2 && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29) {
+        const u32 hclen = ((h >> 13) & 15) + 4;
+        const u32 lo = __funnelshift_r(x0, x1, s + 17), hi = __funnelshift_r(x1, x2, s + 17);  // the 3-bit lengths of the code-length code
+        const u64 v = (((u64)hi << 32) | lo) & ((1ull << (3 * hclen)) - 1);
+        u32 acc = 0;
+#pragma unroll
+        for (u32 q = 0; q < 7; q++) acc += lut[(u32)(v >> (9 * q)) & 511];
+        if ((acc & 0xfff) == 128 || (acc >> 12) == 1) {  // encoders emit complete codes (or a single one)
+          const u32 o = atomicAdd(cnt + 2, 1u);
+          if (o < surv_cap) surv[o] = bit;
         }
       }
     }
   }
 }
 
-// One block, from its BFINAL bit to its end-of-block code, into tokens.
-__device__ __forceinline__ void fb_block_tokens(TokWarpSmem *T, const u8 *in, u64 n, u64 bit, u32 *tok, u32 tok_cap, FbRes *res) {
-  const u32 lane = lane_id();
-  TokCore *S = &T->w;
-  TokReader r;
-  r.init(in, n, bit >> 3);
-  r.skip((u32)(bit & 7));
-  r.refill();
-  u32 o = 0, nt = 0, mytok = 0, turn = lane, left = 32, ok = 0, hist = 0;
-  const u32 bfinal = r.take(1);
-  const u32 btype = r.take(2);
-  u32 status = 0;
-  if (btype == 2 && tk_read_dynamic_header(r, S, status)) {
-    tk_build_tables(T);
-    __syncwarp();
-    for (;;) {
-      r.refill();
-      u32 e = T->lut_ll[r.lo & ((1u << LL_ROOT) - 1)];
-      if ((e & 15) == 0) {
-        u32 sym, l;
-        if (!inf_slow(r.bits64(), &S->tab_ll, S->sorted_ll, sym, l)) break;
-        e = tk_entry_ll(sym, l);
-        if (e & TK_INV) break;
-      }
-      r.skip(e & 15);
-      if (e & TK_EOB) { ok = 1; break; }
-      if (nt >= tok_cap || o >= 0x7fff0000u) break;
-      u32 t;
-      if (e < TK_LEN) {
-        t = e >> 8;
-        o++;
-      } else {
-        const u32 len = ((e >> 8) & 0xffff) + r.take((e >> 4) & 15);
-        r.refill();
-        u32 d = T->lut_d[r.lo & ((1u << D_ROOT) - 1)];
-        if ((d & 15) == 0) {
-          u32 sym, l;
-          if (!inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) break;
-          d = tk_entry_d(sym, l);
-          if (d & TK_INV) break;
-        }
-        r.skip(d & 15);
-        const u32 dist = (d >> 8) + r.take((d >> 4) & 15);
-        if (dist > o) hist = umax(hist, dist - o);
-        t = 0x80000000u | ((len - 3) << 16) | (dist - 1);
-        o += len;
-      }
-      if (turn == 0) mytok = t;
-      turn = (turn - 1) & 31;
-      nt++;
-      if (--left == 0) { tok[nt - 32 + lane] = mytok; left = 32; }
-    }
-    if (r.past_end()) ok = 0;  // consumed bits the buffer does not have: the sequential decoder knows what the reference does
-  }
-  if (lane < (nt & 31)) tok[(nt & ~31u) + lane] = mytok;
-  if (lane == 0) {
-    res->end_bit = r.bitpos();
-    res->out_len = o;
-    res->ntok = nt;
-    res->status = ok ? FB_OK : 0;
-    res->bfinal = bfinal;
-    res->hist_need = hist;
-    res->pad = 0;
-  }
-}
-
-// candidate j's tokens go to tokens + tok_off[j] (room for tok_cap[j], a multiple of 32)
-__global__ void __launch_bounds__(INF_THREADS)
-k_blk_tokens(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ cand, u32 ncand, u32 *tokens, const u64 *__restrict__ tok_off,
-             const u32 *__restrict__ tok_cap, FbRes *res, u32 *counter) {
-  ZLES_SMEM_DECL(smem_raw);
-  TokWarpSmem *T = reinterpret_cast<TokWarpSmem *>(smem_raw) + warp_id();
-  for (;;) {
-    u32 j = 0;
-    if (lane_id() == 0) j = atomicAdd(counter, 1u);
-    j = __shfl_sync(ZLES_FULL, j, 0);
-    if (j >= ncand) break;
-    fb_block_tokens(T, in, n, cand[j], tokens + tok_off[j], tok_cap[j], res + j);
-    __syncwarp();
-  }
-}
-
-// run r = chain entries [run_first[r], run_first[r + 1]) written at out + run_off[r]
-__global__ void __launch_bounds__(RES_THREADS)
-k_blk_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ chain, const u32 *__restrict__ run_first,
-              const u64 *__restrict__ run_off, u32 nruns, const u8 *__restrict__ in, u8 *out, u64 cap, u32 *problems) {
-  ZLES_SMEM_DECL(smem_raw);
-  const u32 r = blockIdx.x * RES_WARPS + warp_id();
-  if (r >= nruns) return;
-  ResState st;
-  const u64 off = run_off[r];
-  st.base = out + off;
-  st.ring = smem_raw + warp_id() * RES_RING;
-  st.room = (u32)umin64(off >= cap ? 0 : cap - off, 0xffffffffull);
-  st.limit = 0xffffffffu;
-  st.o = 0;
-  st.bad = 0;
-  for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
-    const FbChainEnt e = chain[i];
-    if (e.stored) {
-      if (!res_bytes(st, in + e.a, e.b)) break;
-    } else if (!res_tokens(st, tokens + e.a, e.b)) {
-      break;
+__global__ void __launch_bounds__(128) k_hdr_verify(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ surv, u32 surv_cap, u64 *cand, u32 cap,
+                                                    u32 *cnt) {
+  const u32 ns = umin(cnt[2], surv_cap);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+    const u64 bit = surv[i];
+    if (fb_header_ok(in, n, bit)) {
+      const u32 o = atomicAdd(cnt, 1u);
+      if (o < cap) cand[o] = bit;
     }
   }
-  if (st.bad && lane_id() == 0) atomicOr(problems, st.bad);
 }
 
 // ---- chains with history across blocks: symbolic 32 KiB windows -------------------------------------
@@ -293,7 +236,7 @@ constexpr u32 SYM_WIN = 32768;          // deflate's window
 constexpr u32 SYM_REF = 0x8000;         // symbol >= SYM_REF: byte (sym & 0x7fff) of the window before the run
 constexpr u32 SYM_RING = 16384;         // u16 entries mirrored in shared memory per warp (>= 32 x 258)
 constexpr int SYM_SMEM = (int)(RES_WARPS * SYM_RING * 2);
-constexpr u32 SYM_RUN = 262144;         // target bytes per run
+constexpr u32 SYM_RUN = 131072;         // bytes per run at least (the last run of a stream may be shorter)
 
 struct SymState {
   u16 *base;    // the run's symbols
@@ -375,41 +318,11 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
   st.o = o;
 }
 
-template <u32 RING = SYM_RING>
-__device__ __forceinline__ void sym_bytes(SymState &st, const u8 *__restrict__ srcp, u32 len) {
-  constexpr u32 RM = RING - 1;
-  for (u32 q = lane_id(); q < len; q += 32) {
-    const u16 v = srcp[q];
-    st.base[st.o + q] = v;
-    st.ring[(st.o + q) & RM] = v;
-  }
-  __syncwarp();
-  st.o += len;
-}
-
-// pass 1: run r = chain entries [run_first[r], run_first[r + 1]), symbols at sym + run_off[r]
-__global__ void __launch_bounds__(RES_THREADS)
-k_run_resolve(const u32 *__restrict__ tokens, const FbChainEnt *__restrict__ chain, const u32 *__restrict__ run_first,
-              const u64 *__restrict__ run_off, u32 nruns, const u8 *__restrict__ in, u16 *sym) {
-  ZLES_SMEM_DECL(smem_raw);
-  const u32 r = blockIdx.x * RES_WARPS + warp_id();
-  if (r >= nruns) return;
-  SymState st;
-  st.base = sym + run_off[r];
-  st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SYM_RING;
-  st.o = 0;
-  st.refs = 0;
-  st.vfrom = 0;
-  for (u32 i = run_first[r]; i < run_first[r + 1]; i++) {
-    const FbChainEnt e = chain[i];
-    if (e.stored) sym_bytes(st, in + e.a, e.b);
-    else sym_tokens(st, tokens + e.a, e.b);
-  }
-}
-
 // pass 2, one CTA: win[r] = the last 32 KiB of run r, concrete; win[-1] (before the stream) is all zeros, which is
 // what the reference's inflate reads there (/root/reference/src/inflate.ts:287-290).  Runs are >= 32 KiB except the last.
-__global__ void __launch_bounds__(1024) k_win_propagate(const u16 *__restrict__ sym, const u64 *__restrict__ run_off, u32 nruns, u8 *win) {
+__global__ void __launch_bounds__(1024) k_win_propagate(const u16 *__restrict__ sym, const u64 *__restrict__ run_off, u32 nruns, u8 *win,
+                                                        const u32 *__restrict__ any_refs) {
+  if (*any_refs == 0) return;  // no run refers to its window: nothing to make concrete (k_frun_merge)
   for (u32 r = 0; r + 1 < nruns; r++) {
     const u64 end = run_off[r + 1];
     const u8 *prev = r ? win + (size_t)(r - 1) * SYM_WIN : nullptr;

@@ -32,6 +32,7 @@
 #include "inflate.cuh"
 #include "inflate_foreign.cuh"
 #include "inflate_spec.cuh"
+#include "inflate_fblk.cuh"
 #include "lz77.cuh"
 #include "pack.cuh"
 
@@ -95,6 +96,7 @@ struct HostMail {
   u32 adler;
   u8 head[8];           // zlib header / trailer staging
   InfRes res0;
+  u64 fres0[4];         // an FbRes (a block decoded on demand)
 };
 
 }  // namespace
@@ -121,7 +123,8 @@ struct zles_ctx {
   // deflate workspace
   DevBuf tokens, ntok, hist, scratch, adler_part, codes, blk_bits, blk_off, summary;
   // inflate workspace
-  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain, fsym, fwin, pinfo;
+  DevBuf tile_cnt, cand, res, ctl, seg_pos, seg_off, fres, run_first, fstored, fchain, fsym, fwin, pinfo, fjobs, fpieces, fsurv, fmeta, ftab, fmaps, finfo, fitems;
+  std::vector<DevBuf> dem_slabs;  // token room of blocks decoded on demand (inflate_foreign)
   bool pinfo_valid = false;  // phase A left the blocks as pieces (k_inf_tokens4) for a piece-parallel phase B
   // adler / misc
   DevBuf acc;
@@ -259,14 +262,16 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
   e = zrt_set_smem(k_inf_resolve, RES_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_resolve)");
-  e = zrt_set_smem(k_blk_tokens, TOK_SMEM);
-  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_tokens)");
-  e = zrt_set_smem(k_run_resolve, SYM_SMEM);
-  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_run_resolve)");
+  e = zrt_set_smem(k_fblk_map, FB_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_fblk_map)");
+  e = zrt_set_smem(k_fblk_prefix, FB_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_fblk_prefix)");
+  e = zrt_set_smem(k_fblk_head, TOK_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_fblk_head)");
+  e = zrt_set_smem(k_fpiece_sym, SEG_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_fpiece_sym)");
   e = zrt_set_smem(k_piece_sym, SEG_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_piece_sym)");
-  e = zrt_set_smem(k_blk_resolve, RES_SMEM);
-  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_blk_resolve)");
   e = zrt_set_smem(k_inf_tokens4, SPEC_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens4)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
@@ -308,9 +313,10 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   zrt_set_device(c->device);
   zrt_sync(c->stream);
   DevBuf *bufs[] = {&c->tokens, &c->ntok,     &c->hist,      &c->scratch, &c->adler_part, &c->codes,  &c->blk_bits, &c->blk_off,
-                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo, &c->unit_ctr,
+                    &c->summary, &c->tile_cnt, &c->cand,    &c->res,        &c->ctl,    &c->seg_pos,  &c->seg_off, &c->fres, &c->run_first, &c->fstored, &c->fchain, &c->fsym, &c->fwin, &c->pinfo, &c->fjobs, &c->fpieces, &c->fsurv, &c->fmeta, &c->ftab, &c->fmaps, &c->finfo, &c->fitems, &c->unit_ctr,
                     &c->acc,    &c->d_in,     &c->d_out,     &c->d_off_in, &c->d_off_out, &c->d_len,  &c->d_status, &c->d_coff, &c->d_pack};
   for (DevBuf *b : bufs) b->release();
+  for (DevBuf &b : c->dem_slabs) b.release();
   if (c->slab_mail) zrt_host_free(c->slab_mail);
   c->slab_mail = nullptr;
   if (c->cand_mail) zrt_host_free(c->cand_mail);
@@ -965,26 +971,59 @@ static int read_ctl(zles_ctx *c, InfCtl *h) {
   return 0;
 }
 
-// Returns 0 (decoded), a positive status, or -1 when the stream is not something this path handles.
-static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
-  if (n < first + 8 || (u64)n >= (1ull << 40)) return -1;
+// The four kernels that decode jobs [job0, job0 + njobs) of c->fjobs (host copy: hjobs[0 .. njobs)) into tokens
+// (inflate_fblk.cuh); aux0: where their meta / tables go.  Results in c->fres / c->fpieces.
+static int fblk_decode(zles_ctx *c, const u8 *d_in, size_t n, const FbJob *hjobs, u32 njobs, u32 job0, u32 aux0) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
+  const FbJob *jobs = c->fjobs.as<FbJob>();
+  std::vector<FbItem> items;
+  for (u32 i = 0; i < njobs; i++)
+    for (u32 p0 = 0; p0 < hjobs[i].np; p0 += FB_WARPS) items.push_back(FbItem{i, p0});
+  const u32 nitems = (u32)items.size();
+  if (nitems == 0) return 0;
+  RET(c->fitems.reserve((size_t)nitems * sizeof(FbItem)));
+  const u32 grid = nitems < 2 * (u32)c->sm_count ? nitems : 2 * (u32)c->sm_count;  // two CTAs per SM (shared memory, registers)
+  CK(zrt_h2d(c->fitems.p, items.data(), (size_t)nitems * sizeof(FbItem), c->stream));
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  LAUNCH(c, k_fblk_head, (njobs + INF_WARPS - 1) / INF_WARPS, INF_THREADS, TOK_SMEM, d_in, (u64)n, jobs, njobs, job0, aux0, c->fmeta.as<FbMeta>(),
+         c->ftab.as<TokWarpSmem>());
+  LAUNCH(c, k_fblk_map, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0, aux0,
+         (const FbMeta *)c->fmeta.as<FbMeta>(), (const TokWarpSmem *)c->ftab.as<TokWarpSmem>(), c->fmaps.as<u32>(), c->finfo.as<TaPiece>(), &ctl->counter);
+  LAUNCH(c, k_fblk_chain, (njobs + 127) / 128, 128, 0, jobs, njobs, job0, aux0, (const FbMeta *)c->fmeta.as<FbMeta>(), (const u32 *)c->fmaps.as<u32>(),
+         c->finfo.as<TaPiece>(), c->fres.as<FbRes>(), c->fpieces.as<FbPiece>(), (u64)n);
+  LAUNCH(c, k_fblk_prefix, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0, aux0,
+         (const FbMeta *)c->fmeta.as<FbMeta>(), (const TokWarpSmem *)c->ftab.as<TokWarpSmem>(), (const TaPiece *)c->finfo.as<TaPiece>(),
+         c->fres.as<FbRes>(), c->fpieces.as<FbPiece>(), &ctl->ok);
+  CK(zrt_last_error());
+  CK(zrt_sync(c->stream));  // `items` is host heap memory (and the caller reads the results next)
+  return 0;
+}
+
+// Returns 0 (decoded), a positive status, or -1 when the stream is not something this path handles.
+constexpr u32 FB_DEMAND_MAX = 16384;               // blocks decoded on demand per stream at most (a few launches and a read-back each)
+constexpr u64 FB_DEMAND_SPAN = 8ull * 65536;       // hint for a block decoded on demand: 64 KiB of stream at most
+constexpr size_t FB_DEM_SLAB = (size_t)16 << 20;   // tokens per slab of on-demand token room (64 MiB)
+static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
+  if (n < first + 1 || (u64)n >= (1ull << 40)) return -1;
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  const u64 nbits = (u64)n * 8;
   const u64 dcap64 = (u64)n / 64 + 1024;   // a dynamic block is rarely shorter than 64 bytes
   const u64 scap64 = (u64)n / 16 + 4096;   // stored-block candidates: any LEN / ~LEN pair in the data looks like one
-  if (scap64 > 0x7fffffffull) return -1;
-  const u32 dcap = (u32)dcap64, scap = (u32)scap64;
-  if (c->cand.reserve((size_t)dcap * 8) || c->fstored.reserve((size_t)scap * sizeof(FbStored))) return -1;
+  const u64 vcap64 = (u64)n / 8 + 4096;    // survivors of the filter: about a bit position in a thousand
+  const u32 dcap = (u32)dcap64, scap = (u32)scap64, vcap = (u32)vcap64;
+  if (c->cand.reserve((size_t)dcap * 8) || c->fstored.reserve((size_t)scap * sizeof(FbStored)) || c->fsurv.reserve((size_t)vcap * 8)) return -1;
   CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
   {
-    const u64 want = ((u64)n + 255) / 256;
+    const u64 want = ((u64)n + HS_THREADS - 1) / HS_THREADS;
     const u32 grid = (u32)umin64(want, (u64)c->sm_count * 32);
-    LAUNCH(c, k_hdr_scan, grid, 256, 0, d_in, (u64)n, first * 8, c->cand.as<u64>(), dcap, c->fstored.as<FbStored>(), scap, &ctl->ncand);
+    LAUNCH(c, k_hdr_filter, grid, HS_THREADS, HS_SMEM, d_in, (u64)n, first * 8, c->fsurv.as<u64>(), vcap, c->fstored.as<FbStored>(), scap, &ctl->ncand);
+    LAUNCH(c, k_hdr_verify, (u32)c->sm_count * 4, 128, 0, d_in, (u64)n, (const u64 *)c->fsurv.as<u64>(), vcap, c->cand.as<u64>(), dcap, &ctl->ncand);
   }
   CK(zrt_last_error());
   InfCtl h;
   RET(read_ctl(c, &h));
-  const u32 ncand = h.ncand, nst = h.counter;  // k_hdr_scan counts into (ncand, counter)
-  if (ncand > dcap || nst > scap || ncand + nst == 0) return -1;
+  const u32 ncand = h.ncand, nst = h.counter;  // the scan counts into (ncand, counter, ok)
+  if (ncand > dcap || nst > scap || h.ok > vcap) return -1;
   std::vector<u64> cand(ncand);
   std::vector<FbStored> stv(nst);
   if (ncand) CK(zrt_d2h(cand.data(), c->cand.p, (size_t)ncand * 8, c->stream));
@@ -992,62 +1031,127 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   CK(zrt_sync(c->stream));
   std::sort(cand.begin(), cand.end());
   std::sort(stv.begin(), stv.end(), [](const FbStored &a, const FbStored &b) { return a.bit < b.bit; });
-  // token room per dynamic candidate: a block's tokens are bounded by its compressed span (the next
-  // candidate's start); 4 tokens per compressed byte is far above what encoders produce
-  std::vector<u64> tok_off(ncand + 1, 0);
-  std::vector<u32> tok_cap(ncand, 0);
+  // jobs: one per dynamic candidate — the next candidate's start is the hint of where the block ends — and room for the
+  // blocks decoded on demand; pieces: theirs, and as many again plus a piece per tile of the stream for those
+  std::vector<FbJob> jobs(ncand);
+  u64 tok_total = 0, npieces = 0;
   for (u32 i = 0; i < ncand; i++) {
-    const u64 span = ((i + 1 < ncand ? cand[i + 1] : (u64)n * 8) - cand[i] + 7) / 8;
-    u64 capt = span * 4 + 256;
-    if (capt > FB_TOK) capt = FB_TOK;
-    tok_cap[i] = (u32)((capt + 31) & ~31ull);
-    tok_off[i + 1] = tok_off[i] + tok_cap[i];
+    const u64 hint = i + 1 < ncand ? cand[i + 1] : nbits;
+    FbJob &J = jobs[i];
+    J.bit = cand[i];
+    J.hint_end = hint;
+    J.tok_cap = (u32)fb_tok_room(hint - cand[i]);
+    J.flags = 0;
+    J.piece0 = (u32)npieces;
+    J.np = fb_planned_pieces(hint - cand[i]);
+    J.tok = reinterpret_cast<u32 *>(tok_total);  // offset for now
+    tok_total += J.tok_cap;
+    npieces += J.np;
   }
+  const u64 pieces_cap = npieces * 2 + nbits / TA_TILE + 4096;
+  const size_t njob_cap = (size_t)ncand + FB_DEMAND_MAX, naux = (size_t)ncand + 1;
+  if (pieces_cap > 0x7fffffffull) return -1;
+  if (c->fjobs.reserve(njob_cap * sizeof(FbJob)) || c->fres.reserve(njob_cap * sizeof(FbRes)) || c->fpieces.reserve((size_t)pieces_cap * 2 * sizeof(FbPiece)) ||
+      c->fmaps.reserve((size_t)pieces_cap * TA_ENT * 4) || c->finfo.reserve((size_t)pieces_cap * sizeof(TaPiece)) ||
+      c->fmeta.reserve(naux * sizeof(FbMeta)) || c->ftab.reserve(naux * sizeof(TokWarpSmem)) || c->tokens.reserve((size_t)tok_total * 4 + 256))
+    return -1;
   std::vector<FbRes> res(ncand);
   if (ncand) {
-    if (c->tokens.reserve((size_t)tok_off[ncand] * 4) || c->fres.reserve((size_t)ncand * sizeof(FbRes)) ||
-        c->seg_off.reserve((size_t)(ncand + 1) * 8) || c->run_first.reserve((size_t)ncand * 4))
-      return -1;
-    CK(zrt_h2d(c->cand.p, cand.data(), (size_t)ncand * 8, c->stream));
-    CK(zrt_h2d(c->seg_off.p, tok_off.data(), (size_t)ncand * 8, c->stream));
-    CK(zrt_h2d(c->run_first.p, tok_cap.data(), (size_t)ncand * 4, c->stream));
-    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
-    LAUNCH(c, k_blk_tokens, inflate_grid(c, ncand), INF_THREADS, TOK_SMEM, d_in, (u64)n, (const u64 *)c->cand.as<u64>(), ncand,
-           c->tokens.as<u32>(), (const u64 *)c->seg_off.as<u64>(), (const u32 *)c->run_first.as<u32>(), c->fres.as<FbRes>(), &ctl->counter);
-    CK(zrt_last_error());
+    for (u32 i = 0; i < ncand; i++) jobs[i].tok = c->tokens.as<u32>() + reinterpret_cast<u64>(jobs[i].tok);
+    CK(zrt_h2d(c->fjobs.p, jobs.data(), (size_t)ncand * sizeof(FbJob), c->stream));
+    RET(fblk_decode(c, d_in, n, jobs.data(), ncand, 0u, 0u));
     CK(zrt_d2h(res.data(), c->fres.p, (size_t)ncand * sizeof(FbRes), c->stream));
     CK(zrt_sync(c->stream));
   }
+  // blocks the scan did not find (fixed blocks, dynamic blocks with an incomplete code): decoded when the chain reaches them
+  u32 ndem = 0;
+  size_t dem_slab = 0, dem_used = 0;
+  auto demand = [&](u64 pos, FbRes &r, bool was_long) -> int {
+    const auto nx = std::upper_bound(cand.begin(), cand.end(), pos);
+    u64 hint = nx != cand.end() ? *nx : nbits;
+    if (was_long) {  // a candidate that turned out longer than up to the next one (a false positive inside it): four times the room
+      hint = pos + (hint - pos) * 4;
+      if (hint > nbits) hint = nbits;
+    } else if (hint > pos + FB_DEMAND_SPAN) {
+      hint = pos + FB_DEMAND_SPAN;
+    }
+    for (;;) {  // again with a longer hint when the block turns out longer than its room
+      if (ndem >= FB_DEMAND_MAX) return -1;
+      const u64 capt = fb_tok_room(hint - pos);
+      const u32 np = fb_planned_pieces(hint - pos);
+      if (capt > 0xffffffe0ull || npieces + np > pieces_cap) return -1;
+      // room: the current slab, or the next one
+      for (;; dem_slab++, dem_used = 0) {
+        if (dem_slab >= c->dem_slabs.size()) c->dem_slabs.emplace_back();
+        DevBuf &sl = c->dem_slabs[dem_slab];
+        if (sl.cap == 0 && sl.reserve((FB_DEM_SLAB > capt ? FB_DEM_SLAB : (size_t)capt) * 4)) return -1;
+        if ((dem_used + capt) * 4 <= sl.cap) break;
+      }
+      FbJob J;
+      J.bit = pos; J.hint_end = hint; J.tok = c->dem_slabs[dem_slab].as<u32>() + dem_used; J.tok_cap = (u32)capt; J.flags = FB_JOB_COMPACT;
+      J.piece0 = (u32)npieces; J.np = np;
+      const u32 ji = ncand + ndem;
+      CK(zrt_h2d(c->fjobs.as<FbJob>() + ji, &J, sizeof(FbJob), c->stream));
+      RET(fblk_decode(c, d_in, n, &J, 1u, ji, ncand));
+      LAUNCH(c, k_fblk_compact, 1, FB_THREADS, 0, (const FbJob *)c->fjobs.as<FbJob>(), ji, (const FbRes *)c->fres.as<FbRes>(), c->fpieces.as<FbPiece>());
+      CK(zrt_last_error());
+      CK(zrt_mail(&c->mail->fres0[0], c->fres.as<FbRes>() + ji, sizeof(FbRes), c->stream));
+      CK(zrt_sync(c->stream));  // also: J is on the stack
+      memcpy(&r, &c->mail->fres0[0], sizeof(FbRes));
+      ndem++;
+      if (r.status == FB_LONG && hint < nbits) {
+        hint = pos + (hint - pos) * 4;
+        if (hint > nbits) hint = nbits;
+        continue;
+      }
+      if (r.status != FB_OK) return -1;
+      dem_used += ((size_t)r.ntok + 31) & ~(size_t)31;
+      npieces += (r.npieces + 1) / 2;  // the pieces the block really has keep their slots
+      return 0;
+    }
+  };
   // chain walk: the block after one that ends at bit e starts at bit e
-  std::vector<FbChainEnt> chain;
-  std::vector<u64> blk_off;  // output offset of every chain entry
-  u64 pos = first * 8, total = 0;
-  bool self_contained = true;
+  std::vector<FbEnt> chain;
+  u64 pos = first * 8, total = 0, nwarps = 0;
   for (;;) {
-    if (chain.size() > (size_t)ncand + nst) return -1;
+    if (chain.size() > (size_t)ncand + nst + FB_DEMAND_MAX) return -1;
+    if (pos + 3 > nbits) return -1;
     const auto it = std::lower_bound(cand.begin(), cand.end(), pos);
+    const auto is = std::lower_bound(stv.begin(), stv.end(), pos, [](const FbStored &a, u64 p) { return a.bit < p; });
     u32 bfinal;
     u64 next;
-    if (it != cand.end() && *it == pos) {
+    FbEnt en;
+    memset(&en, 0, sizeof(en));
+    en.out_off = total;
+    en.warp0 = (u32)nwarps;
+    if (it != cand.end() && *it == pos && res[(size_t)(it - cand.begin())].status == FB_OK) {
       const FbRes &r = res[(size_t)(it - cand.begin())];
-      if (r.status != FB_OK) return -1;
-      if (r.hist_need) self_contained = false;  // (before the start of the output the reference reads zeros: so does the window scheme)
-      chain.push_back(FbChainEnt{tok_off[(size_t)(it - cand.begin())], r.ntok, 0});
-      blk_off.push_back(total);
-      total += r.out_len;
+      en.job = (u32)(it - cand.begin());
+      en.len = r.out_len;
       bfinal = r.bfinal;
       next = r.end_bit;
-    } else {
-      const auto is = std::lower_bound(stv.begin(), stv.end(), pos, [](const FbStored &a, u64 p) { return a.bit < p; });
-      if (is == stv.end() || is->bit != pos) return -1;  // a fixed block, or not a block at all: sequential path
+      nwarps += r.npieces;
+    } else if (is != stv.end() && is->bit == pos) {
       const u64 q = (pos + 3 + 7) >> 3;
-      chain.push_back(FbChainEnt{q + 4, is->len, 1});
-      blk_off.push_back(total);
-      total += is->len;
+      en.src = q + 4;
+      en.len = is->len;
+      en.stored = 1;
       bfinal = is->bfinal;
       next = (q + 4 + is->len) * 8;
+      nwarps += FB_STORED_WARPS;
+    } else {
+      FbRes r;
+      const int rc = demand(pos, r, it != cand.end() && *it == pos && res[(size_t)(it - cand.begin())].status == FB_LONG);
+      if (rc) return rc;  // not a block this path decodes (BTYPE 3, a damaged stored block, garbage): sequential path
+      en.job = ncand + ndem - 1;
+      en.len = r.out_len;
+      bfinal = r.bfinal;
+      next = r.end_bit;
+      nwarps += r.npieces;
     }
-    if (total >= 0xfff00000ull) return -1;  // run-relative offsets are 32-bit
+    chain.push_back(en);
+    total += en.len;
+    if (total >= (1ull << 46) || nwarps >= 0x7fff0000ull) return -1;
     if (bfinal) break;
     if (next <= pos) return -1;
     pos = next;
@@ -1055,60 +1159,44 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   *out_len = (size_t)total;
   if (total > cap) return ZLES_E_OUTPUT_FULL;
   const u32 nblk = (u32)chain.size();
+  // runs of whole blocks, at least SYM_RUN bytes each (the last one may be shorter); long streams take longer runs so that
+  // the serial window propagation stays short
   std::vector<u32> run_first;
   std::vector<u64> run_off;
-  if (self_contained) {
-    // no block reaches before its own start (zlib.es's own streams): every block is copied on its own warp
-    for (u32 i = 0; i < nblk; i++) { run_first.push_back(i); run_off.push_back(blk_off[i]); }
-    const u32 nruns = nblk;
-    run_first.push_back(nblk);
-    RET(c->fchain.reserve((size_t)nblk * sizeof(FbChainEnt)));
-    RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
-    RET(c->seg_off.reserve((size_t)nruns * 8));
-    CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbChainEnt), c->stream));
-    CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
-    CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)nruns * 8, c->stream));
-    CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
-    CK(zrt_sync(c->stream));  // the vectors are host heap memory
-    LAUNCH(c, k_blk_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, RES_SMEM, (const u32 *)c->tokens.as<u32>(),
-           (const FbChainEnt *)c->fchain.as<FbChainEnt>(), (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns, d_in,
-           d_out, (u64)cap, &ctl->ok_res);
-    CK(zrt_last_error());
-    RET(read_ctl(c, &h));
-    if (h.ok_res != 0) return -1;
-    return 0;
-  }
-  // blocks use the 32 KiB before them (system zlib): runs of >= SYM_RUN bytes resolved in parallel into 16-bit
-  // symbols with symbolic windows, windows made concrete run after run, then substituted (inflate_foreign.cuh)
   {
+    u64 target = total / 2048;
+    if (target < SYM_RUN) target = SYM_RUN;
     u64 acc = 0;
     for (u32 i = 0; i < nblk; i++) {
-      if (i == 0 || acc >= SYM_RUN) { run_first.push_back(i); run_off.push_back(blk_off[i]); acc = 0; }
-      acc += (i + 1 < nblk ? blk_off[i + 1] : total) - blk_off[i];
+      if (i == 0 || acc >= target) { run_first.push_back(i); run_off.push_back(chain[i].out_off); acc = 0; }
+      acc += chain[i].len;
     }
   }
   const u32 nruns = (u32)run_first.size();
   run_first.push_back(nblk);
   run_off.push_back(total);
   if (c->fsym.reserve((size_t)total * 2 + 64) || c->fwin.reserve((size_t)nruns * SYM_WIN)) return -1;
-  RET(c->fchain.reserve((size_t)nblk * sizeof(FbChainEnt)));
+  RET(c->fchain.reserve((size_t)nblk * sizeof(FbEnt)));
   RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
   RET(c->seg_off.reserve((size_t)(nruns + 1) * 8));
-  CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbChainEnt), c->stream));
+  CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbEnt), c->stream));
   CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
   CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)(nruns + 1) * 8, c->stream));
-  CK(zrt_sync(c->stream));  // the vectors are host heap memory
-  LAUNCH(c, k_run_resolve, (nruns + RES_WARPS - 1) / RES_WARPS, RES_THREADS, SYM_SMEM, (const u32 *)c->tokens.as<u32>(),
-         (const FbChainEnt *)c->fchain.as<FbChainEnt>(), (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns, d_in,
-         c->fsym.as<u16>());
-  LAUNCH(c, k_win_propagate, 1, 1024, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns, c->fwin.as<u8>());
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  LAUNCH(c, k_fpiece_sym, (u32)((nwarps + RES_WARPS - 1) / RES_WARPS), RES_THREADS, SEG_SMEM, (const FbJob *)c->fjobs.as<FbJob>(),
+         (const FbPiece *)c->fpieces.as<FbPiece>(), (const FbEnt *)c->fchain.as<FbEnt>(), nblk, (u32)nwarps, d_in, c->fsym.as<u16>());
+  LAUNCH(c, k_frun_merge, nruns < (u32)c->sm_count * 8 ? nruns : (u32)c->sm_count * 8, MRG_THREADS, 0, (const FbJob *)c->fjobs.as<FbJob>(),
+         (const FbRes *)c->fres.as<FbRes>(), (const FbPiece *)c->fpieces.as<FbPiece>(), (const FbEnt *)c->fchain.as<FbEnt>(),
+         (const u32 *)c->run_first.as<u32>(), nruns, c->fsym.as<u16>(), &ctl->ok_res);
+  LAUNCH(c, k_win_propagate, 1, 1024, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns, c->fwin.as<u8>(),
+         (const u32 *)&ctl->ok_res);
   {
     dim3 grid(16, nruns < 4096 ? nruns : 4096);
     LAUNCH(c, k_sym_finalize, grid, 256, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns,
            (const u8 *)c->fwin.as<u8>(), d_out);
   }
   CK(zrt_last_error());
-  CK(zrt_sync(c->stream));
+  CK(zrt_sync(c->stream));  // the vectors are host heap memory
   return 0;
 }
 
@@ -1150,6 +1238,9 @@ static int inflate_decode(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u32 
                           size_t *out_len, bool has_final = true, bool ours_only = false) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   bool fast = ncand_all >= 1 && ncand_all <= cand_cap;
+  // one of our blocks takes at most SUB + 10 bytes of stream (stored): a stream with fewer markers than that is somebody
+  // else's, and decoding its first block on one warp only to find that out costs more than the whole block-parallel tier
+  if ((u64)n > (u64)ncand_all * (SUB + 4096)) fast = false;
   const u32 ncand = ncand_all;
   if (fast) {  // workspace for phase A; failing to get it only costs the fast path
     if (c->tokens.reserve((size_t)ncand * SUB * 4) || c->ntok.reserve((size_t)ncand * 4) || c->res.reserve((size_t)ncand * sizeof(InfRes)) ||

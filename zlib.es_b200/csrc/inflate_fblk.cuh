@@ -45,7 +45,9 @@ constexpr u32 TA_EOB = 64;              // nx[]: bits 0-5 the token's length, bi
 constexpr u32 TA_X_EOB = 0x80000000u;   // exit of a chain: it read the end-of-block code, which ends at (x & 0x7fffffff)
 constexpr u32 TA_X_BAD = 0xffffffffu;   // ... it ran into something that is no code
 constexpr u32 FB_JOB_COMPACT = 1;       // leave the block's tokens contiguous at the start of its room (blocks decoded on demand)
-constexpr u32 FB_LONG = 2;              // FbRes.status: the block did not end within the room its hint gave it
+constexpr u32 FB_JOB_CONT = 2;          // `bit` is a token start inside the block whose header and tables are at `aux`: decode on from there
+constexpr u32 FB_LONG = 2;              // FbRes.status: the block did not end within the room its hint gave it; the result stands for its
+                                        // tokens up to end_bit (a token start): decode on from there (FB_JOB_CONT)
 
 struct FbJob {
   u64 bit;        // position of the block's BFINAL bit
@@ -55,6 +57,8 @@ struct FbJob {
   u32 flags;
   u32 piece0;     // its first piece in the per-piece arrays (maps, infos; its token runs are pieces[2 * piece0 ...])
   u32 np;         // pieces planned: fb_planned_pieces(hint_end - bit)
+  u32 aux;        // where its header / tables are kept between the kernels (FbMeta, TokWarpSmem)
+  u32 pad;
 };
 struct FbItem {   // a work item of k_fblk_map / k_fblk_prefix: pieces [p0, p0 + FB_WARPS) of job `ji` of the launch
   u32 ji, p0;
@@ -90,10 +94,10 @@ struct TaWarp {
   u16 list[TA_CHUNK];
 };
 struct TaPiece {      // what step 1 leaves about a piece
-  u32 mpos;           // where all its live chains had become one (a tile boundary or just behind it); 0 = they never did
-  u32 mtiles;         // tiles before that
+  u32 mpos;           // where all its live chains had become one; 0 = they never did
+  u32 soff;           // where the merged chain's tokens are stored in the piece's token room (what comes before them: fewer)
   u32 sexit;          // the merged chain's exit: a position, TA_X_EOB | position, or TA_X_BAD
-  u32 snt, sob, sfin; // tokens / bytes of the merged chain from mpos on (stored at tokP + mtiles * TA_TILE / 2), the bit after its end-of-block code
+  u32 snt, sob, sfin; // tokens / bytes of the merged chain from mpos on (stored at tokP + soff), the bit after its end-of-block code
   u32 entry;          // k_fblk_chain: where the block's chain enters the piece,
   u32 merged;         // ... whether that leads into the merged chain,
   u32 on_chain, pad;  // ... whether the chain gets here at all (1; 2: it ends here)
@@ -102,7 +106,7 @@ constexpr u32 TA_X_MERGED = 0xfffffffeu;  // map[]: this entry's chain is the me
 
 struct FbMeta {       // a block's header, parsed (k_fblk_head)
   u32 mode;           // 1: tables built, the fields below are valid
-  u32 bfinal, sym_start, piece_bits, pcap, hard_end, pad0, pad1;
+  u32 bfinal, sym_start, piece_bits, pcap, hard_end, fixed, pad1;
 };
 struct FbShared {
   TokWarpSmem T;
@@ -117,7 +121,10 @@ struct TaSrc {
   u64 n;
   const u32 *words;
   u32 skew;
+  u32 fixed_run;  // the block uses the fixed code: an end-of-block code followed by the header of another non-final fixed block
+                  // (0, 01) is walked over like a token — a run of fixed blocks decodes as one (ta_tile)
   __device__ __forceinline__ void init(const u8 *in_, u64 n_) {
+    fixed_run = 0;
     in = in_; n = n_;
     skew = (u32)((uintptr_t)in_ & 3);
     words = reinterpret_cast<const u32 *>(in_ - skew);
@@ -192,15 +199,16 @@ __device__ __forceinline__ void ta_bits_at(const TaWarp *W, u32 sh, u32 p, u32 &
 
 // Stages the tile that starts at block-relative bit t0 and fills nx[] for its positions; positions at or behind
 // hard_end hold no code.  Returns sh, the bit offset of position 0 in words[0].
-__device__ __forceinline__ u32 ta_tile(TaWarp *W, const TokWarpSmem *T, const TaSrc &src, u64 bit0, u32 t0, u32 hard_end) {
+__device__ __forceinline__ u32 ta_tile(TaWarp *W, const TokWarpSmem *T, const TaSrc &src, u64 bit0, u32 t0, u32 hard_end, u32 upto = TA_TILE) {
   const u32 lane = lane_id();
   const u64 a = bit0 + t0 + ((u64)src.skew << 3);
   const u64 w0 = a >> 5;
   const u32 sh = (u32)(a & 31);
+  const u32 nr = umin(TA_TILE / 32, ((upto + 127) / 128) * 4);  // rounds: only the first `upto` positions are needed
   __syncwarp();
-  for (u32 i = lane; i < TA_WORDS; i += 32) W->words[i] = src.load_word(w0 + i);
+  for (u32 i = lane; i < nr + 4; i += 32) W->words[i] = src.load_word(w0 + i);
   __syncwarp();
-  for (u32 r = 0; r < TA_TILE / 32; r += 4) {  // four independent positions per lane in flight
+  for (u32 r = 0; r < nr; r += 4) {  // four independent positions per lane in flight
     u32 v[4];
 #pragma unroll
     for (u32 k = 0; k < 4; k++) {
@@ -216,10 +224,17 @@ __device__ __forceinline__ u32 ta_tile(TaWarp *W, const TokWarpSmem *T, const Ta
         ta_bits_at(W, sh, p, lo, hi);
         v[k] = ta_decode(T, lo, hi, tokv, olen);
       }
+      if (src.fixed_run && (v[k] & TA_EOB) && (v[k] & 63)) {  // an end-of-block code of the fixed code: what follows it?
+        u32 lo, hi;
+        ta_bits_at(W, sh, p, lo, hi);
+        if (((lo >> (v[k] & 63)) & 7) == 2) v[k] = (v[k] & 63) + 3;  // BFINAL = 0, BTYPE = 01: the chain goes on behind the header
+      }
       if (v[k] == 0 || t0 + p >= hard_end) v[k] = TA_EOB;  // no code starts here
       W->nx[p] = (u8)v[k];
     }
   }
+  // (a partial tile: no stale marks up to the end of the last chunk ta_emit_marked looks at)
+  for (u32 p = nr * 32 + lane; p < umin(TA_TILE, ((upto + TA_CHUNK - 1) / TA_CHUNK) * TA_CHUNK); p += 32) W->nx[p] = (u8)TA_EOB;
   __syncwarp();
   return sh;
 }
@@ -249,9 +264,10 @@ __device__ __forceinline__ void ta_walk_marking(TaWarp *W, u32 t0, u32 stop, u32
 // The marked tokens, decoded a lane per token and appended to tokP[nt ...] (room for cap): 512 positions at a time
 // (16 per lane, their marks gathered from nx[]), their positions compacted into a list first.  acc collects, per
 // lane, the bytes they stand for.  Returns false when the room is used up.
-__device__ __forceinline__ bool ta_emit_marked(TaWarp *W, const TokWarpSmem *T, u32 sh, u32 *tokP, u32 cap, u32 &nt, u32 &acc) {
+__device__ __forceinline__ bool ta_emit_marked(TaWarp *W, const TokWarpSmem *T, u32 sh, u32 *tokP, u32 cap, u32 &nt, u32 &acc, u32 upto = TA_TILE) {
   const u32 lane = lane_id();
-  for (u32 ch = 0; ch < TA_TILE / TA_CHUNK; ch++) {
+  const u32 nch = umin(TA_TILE / TA_CHUNK, (upto + TA_CHUNK - 1) / TA_CHUNK);  // (marks only in the first `upto` positions)
+  for (u32 ch = 0; ch < nch; ch++) {
     const uint4 q = *reinterpret_cast<const uint4 *>(W->nx + ch * TA_CHUNK + lane * 16);
     // bit 7 of the 16 bytes -> a 16-bit mask (byte k of a word to bit k: the multiply gathers the four bits)
     const u32 n0 = ((((q.x >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 15, n1 = ((((q.y >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 15;
@@ -274,14 +290,22 @@ __device__ __forceinline__ bool ta_emit_marked(TaWarp *W, const TokWarpSmem *T, 
       W->list[o++] = (u16)(ch * TA_CHUNK + lane * 16 + b);
     }
     __syncwarp();
-    for (u32 k = lane; k < total; k += 32) {
-      u32 lo, hi, tokv, olen;
-      ta_bits_at(W, sh, W->list[k], lo, hi);
-      ta_decode(T, lo, hi, tokv, olen);
-      tokP[nt + k] = tokv;
-      acc += olen;
+    for (u32 k0 = 0; k0 < total; k0 += 32) {
+      const u32 k = k0 + lane;
+      u32 tokv = 0, olen = 0;
+      bool keep = false;
+      if (k < total) {
+        u32 lo, hi;
+        ta_bits_at(W, sh, W->list[k], lo, hi);
+        keep = (ta_decode(T, lo, hi, tokv, olen) & TA_EOB) == 0;  // (an end-of-block code inside a run of fixed blocks is no token)
+      }
+      const u32 bal = __ballot_sync(ZLES_FULL, keep);
+      if (keep) {
+        tokP[nt + (u32)__popc(bal & lanemask_lt())] = tokv;
+        acc += olen;
+      }
+      nt += (u32)__popc(bal);
     }
-    nt += total;
     __syncwarp();
   }
   return true;
@@ -295,46 +319,73 @@ __device__ __forceinline__ void ta_map_piece(TaWarp *W, const TokWarpSmem *T, co
                                              u32 *map, TaPiece *info, u32 *tokP, u32 pcap) {
   const u32 lane = lane_id();
   u32 cA = q0 + lane, cB = q0 + 32 + lane;
-  u32 mpos = 0, mtiles = 0, c = 0, state = 0, fin = 0, snt = 0, acc = 0;
+  u32 mpos = 0, soff = 0, c = 0, state = 0, fin = 0, snt = 0, acc = 0;
   const u32 qend = q0 + piece_bits;
-  u32 ntile = 0;
-  for (u32 t0 = q0; t0 - q0 < piece_bits && t0 < hard_end; t0 += TA_TILE, ntile++) {
+  for (u32 t0 = q0; t0 - q0 < piece_bits && t0 < hard_end; t0 += TA_TILE) {
     const u32 tend = t0 + TA_TILE;
+    if (mpos != 0 && (state != 0 || c >= tend)) continue;
+    const u32 sh = ta_tile(W, T, src, bit0, t0, hard_end);
     if (mpos == 0) {
-      ta_tile(W, T, src, bit0, t0, hard_end);
-      bool more;
-      do {  // (the vote every fourth step: a chain that has left the tile just idles)
-        more = false;
+      // The chains, position by position: everybody steps up to the foremost live chain; when all live chains stand on
+      // that position they have become one (most data: after a few tokens).  Data whose codes all have about the same
+      // length never gets there: after a while the chains just run to the end of the tile.
+      bool merged = false;
+      for (u32 round = 0; round < 48; round++) {
+        const bool liveA = cA < TA_X_EOB, liveB = cB < TA_X_EOB;
+        const u32 front = __reduce_max_sync(ZLES_FULL, umax(liveA ? cA : 0u, liveB ? cB : 0u));
+        if (front == 0) break;  // no chain left
+        const bool same = (!liveA || cA == front) && (!liveB || cB == front);
+        if (__all_sync(ZLES_FULL, same)) { merged = front < umin(qend, hard_end); break; }
+        if (front >= tend) break;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (cA < tend) {
+        for (int u = 0; u < 3; u++) {
+          if (cA < front) {
             const u32 v = W->nx[cA - t0];
             cA = (v & TA_EOB) ? ((v & 63) ? ((cA + (v & 63)) | TA_X_EOB) : TA_X_BAD) : cA + v;
-            more = true;
           }
-          if (cB < tend) {
+          if (cB < front) {
             const u32 v = W->nx[cB - t0];
             cB = (v & TA_EOB) ? ((v & 63) ? ((cB + (v & 63)) | TA_X_EOB) : TA_X_BAD) : cB + v;
-            more = true;
           }
         }
-      } while (__any_sync(ZLES_FULL, more));
-      // have the live chains become one?
-      const bool liveA = cA < TA_X_EOB, liveB = cB < TA_X_EOB;
-      const u32 mine = liveA ? cA : (liveB ? cB : 0xffffffffu);
-      const u32 lo = __reduce_min_sync(ZLES_FULL, mine);
-      const bool same = (!liveA || cA == lo) && (!liveB || cB == lo);
-      if (lo != 0xffffffffu && __all_sync(ZLES_FULL, same) && tend < qend && tend < hard_end) {
-        mpos = lo;
-        mtiles = ntile + 1;
-        c = lo;
+      }
+      if (!merged) {
+        bool more;
+        do {  // (the vote every fourth step: a chain that has left the tile just idles)
+          more = false;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (cA < tend) {
+              const u32 v = W->nx[cA - t0];
+              cA = (v & TA_EOB) ? ((v & 63) ? ((cA + (v & 63)) | TA_X_EOB) : TA_X_BAD) : cA + v;
+              more = true;
+            }
+            if (cB < tend) {
+              const u32 v = W->nx[cB - t0];
+              cB = (v & TA_EOB) ? ((v & 63) ? ((cB + (v & 63)) | TA_X_EOB) : TA_X_BAD) : cB + v;
+              more = true;
+            }
+          }
+        } while (__any_sync(ZLES_FULL, more));
+        // at the end of a tile every live chain stands on its first token start behind it: have they become one?
+        const bool liveA = cA < TA_X_EOB, liveB = cB < TA_X_EOB;
+        const u32 front = __reduce_max_sync(ZLES_FULL, umax(liveA ? cA : 0u, liveB ? cB : 0u));
+        const bool same = (!liveA || cA == front) && (!liveB || cB == front);
+        merged = front != 0 && __all_sync(ZLES_FULL, same) && front < umin(qend, hard_end);
+      }
+      if (merged) {
+        const bool liveA = cA < TA_X_EOB, liveB = cB < TA_X_EOB;
+        mpos = liveA ? cA : cB;
+        mpos = __reduce_max_sync(ZLES_FULL, (liveA || liveB) ? mpos : 0u);
+        c = mpos;
+        soff = umin(((mpos - q0) / 2 + 64) & ~31u, pcap);
         if (liveA) cA = TA_X_MERGED;
         if (liveB) cB = TA_X_MERGED;
       }
-    } else if (state == 0 && c < tend) {
-      const u32 sh = ta_tile(W, T, src, bit0, t0, hard_end);
+    }
+    if (mpos != 0 && state == 0 && c < tend) {  // the merged chain: its tokens right away
       ta_walk_marking(W, t0, 0xffffffffu, c, state, fin);
-      if (!ta_emit_marked(W, T, sh, tokP + (size_t)mtiles * (TA_TILE / 2), pcap - mtiles * (TA_TILE / 2), snt, acc)) state = 2;
+      if (!ta_emit_marked(W, T, sh, tokP + soff, pcap - soff, snt, acc)) state = 2;
     }
   }
   if (mpos == 0) {
@@ -347,7 +398,7 @@ __device__ __forceinline__ void ta_map_piece(TaWarp *W, const TokWarpSmem *T, co
   const u32 sob = __reduce_add_sync(ZLES_FULL, acc);
   if (lane == 0) {
     info->mpos = mpos;
-    info->mtiles = mtiles;
+    info->soff = soff;
     info->snt = snt;
     info->sob = sob;
     info->sfin = fin;
@@ -364,9 +415,10 @@ __device__ __forceinline__ u32 ta_emit_piece(TaWarp *W, const TokWarpSmem *T, co
   nt = 0;
   for (u32 t0 = q0; t0 - q0 < piece_bits && t0 < hard_end && state == 0 && c < stop; t0 += TA_TILE) {
     if (c >= t0 + TA_TILE) continue;  // (a token longer than what is left of a tile)
-    const u32 sh = ta_tile(W, T, src, bit0, t0, hard_end);
+    const u32 upto = stop - t0 < TA_TILE ? stop - t0 : TA_TILE;  // nothing behind `stop` is looked at
+    const u32 sh = ta_tile(W, T, src, bit0, t0, hard_end, upto);
     ta_walk_marking(W, t0, stop, c, state, fin);
-    if (!ta_emit_marked(W, T, sh, tokP, cap, nt, acc)) state = 2;
+    if (!ta_emit_marked(W, T, sh, tokP, cap, nt, acc, upto)) state = 2;
   }
   ob = __reduce_add_sync(ZLES_FULL, acc);
   if (state == 0) {
@@ -376,11 +428,11 @@ __device__ __forceinline__ u32 ta_emit_piece(TaWarp *W, const TokWarpSmem *T, co
   return state;
 }
 
-// The kernels.  Job j of a launch is jobs[job0 + j]; what is only needed between the kernels (meta, tables, maps, infos,
-// chains) lives at index aux0 + j (blocks decoded on demand share one such slot).
+// The kernels.  Job j of a launch is jobs[job0 + j]; its header and tables live at index jobs[].aux between the kernels
+// (blocks decoded on demand share one such slot).
 // k_fblk_head: a warp per block — the header, the tables (stored for the other kernels), how the coded bits are cut.
 __global__ void __launch_bounds__(INF_THREADS)
-k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u32 njobs, u32 job0, u32 aux0, FbMeta *meta, TokWarpSmem *tabs) {
+k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u32 njobs, u32 job0, FbMeta *meta, TokWarpSmem *tabs) {
   ZLES_SMEM_DECL(smem_raw);
   TokWarpSmem *T = reinterpret_cast<TokWarpSmem *>(smem_raw) + warp_id();
   TokCore *S = &T->w;
@@ -390,8 +442,23 @@ k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u3
   if (ji >= njobs) return;
   const FbJob J = jobs[job0 + ji];
   const u64 bit0 = J.bit & ~7ull;
+  const u64 span = J.hint_end > J.bit ? J.hint_end - J.bit : 0;
   FbMeta m;
-  m.mode = 0; m.bfinal = 0; m.sym_start = 0; m.piece_bits = TA_TILE; m.pcap = 0; m.hard_end = 0; m.pad0 = 0; m.pad1 = 0;
+  if (J.flags & FB_JOB_CONT) {  // the tables are there already: only the cut changes
+    m = meta[J.aux];
+    if (m.mode) {
+      m.mode = 0;
+      m.hard_end = (u32)umin64(nbits - bit0, 0x7fff0000ull);
+      m.sym_start = (u32)(J.bit - bit0);
+      m.piece_bits = fb_piece_bits(span);
+      m.pcap = m.piece_bits / 2;
+      if (m.sym_start < m.hard_end && J.np >= 1 && (u64)J.np * m.pcap <= J.tok_cap) m.mode = 1;
+    }
+    __syncwarp();
+    if (lane == 0) meta[J.aux] = m;
+    return;
+  }
+  m.mode = 0; m.bfinal = 0; m.sym_start = 0; m.piece_bits = TA_TILE; m.pcap = 0; m.hard_end = 0; m.fixed = 0; m.pad1 = 0;
   if (J.bit + 3 <= nbits) {
     TokReader r;
     r.init(in, n, J.bit >> 3);
@@ -407,6 +474,7 @@ k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u3
       for (u32 i = lane; i < 352; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : i < 320 ? 5 : 0);
       __syncwarp();
       ok = true;
+      m.fixed = m.bfinal ? 0 : 1;  // (a final block is followed by nothing)
     }
     if (ok && !r.past_end()) {
       tk_build_tables(T);
@@ -414,7 +482,6 @@ k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u3
       m.hard_end = (u32)umin64(nbits - bit0, 0x7fff0000ull);
       if (bp - bit0 < m.hard_end) {
         m.sym_start = (u32)(bp - bit0);
-        const u64 span = J.hint_end > J.bit ? J.hint_end - J.bit : 0;
         m.piece_bits = fb_piece_bits(span);
         m.pcap = m.piece_bits / 2;
         if (J.np >= 1 && (u64)J.np * m.pcap <= J.tok_cap) m.mode = 1;
@@ -424,20 +491,20 @@ k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u3
   __syncwarp();
   if (m.mode) {  // the tables, for k_fblk_map and k_fblk_prefix
     const u32 *s4 = reinterpret_cast<const u32 *>(T);
-    u32 *d4 = reinterpret_cast<u32 *>(tabs + aux0 + ji);
+    u32 *d4 = reinterpret_cast<u32 *>(tabs + J.aux);
     for (u32 i = lane; i < sizeof(TokWarpSmem) / 4; i += 32) d4[i] = s4[i];
   }
-  if (lane == 0) meta[aux0 + ji] = m;
+  if (lane == 0) meta[J.aux] = m;
 }
 
 // shared by k_fblk_map and k_fblk_prefix: loads the tables of the item's job.  False = nothing to do for this item.
 __device__ __forceinline__ bool fb_item_begin(FbShared *Sh, const FbItem it, const FbMeta *__restrict__ meta, const TokWarpSmem *__restrict__ tabs,
-                                              u32 aux0, FbMeta &m) {
-  m = meta[aux0 + it.ji];
+                                              u32 aux, FbMeta &m) {
+  m = meta[aux];
   if (!m.mode) return false;
   // pieces that start behind the end of the stream do not exist
   if ((u64)m.sym_start + (u64)it.p0 * m.piece_bits >= m.hard_end) return false;
-  const u32 *s4 = reinterpret_cast<const u32 *>(tabs + aux0 + it.ji);
+  const u32 *s4 = reinterpret_cast<const u32 *>(tabs + aux);
   u32 *d4 = reinterpret_cast<u32 *>(&Sh->T);
   for (u32 i = threadIdx.x; i < sizeof(TokWarpSmem) / 4; i += FB_THREADS) d4[i] = s4[i];
   __syncthreads();
@@ -446,7 +513,7 @@ __device__ __forceinline__ bool fb_item_begin(FbShared *Sh, const FbItem it, con
 
 // k_fblk_map: step 1.  A work item is sixteen pieces of one block, a warp each.
 __global__ void __launch_bounds__(FB_THREADS)
-k_fblk_map(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, const FbItem *__restrict__ items, u32 nitems, u32 job0, u32 aux0,
+k_fblk_map(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, const FbItem *__restrict__ items, u32 nitems, u32 job0,
            const FbMeta *__restrict__ meta, const TokWarpSmem *__restrict__ tabs, u32 *maps, TaPiece *infos, u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);
   FbShared *Sh = reinterpret_cast<FbShared *>(smem_raw);
@@ -460,9 +527,10 @@ k_fblk_map(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, con
     __syncthreads();
     if (Sh->item >= nitems) break;
     const FbItem it = items[Sh->item];
-    FbMeta m;
-    if (!fb_item_begin(Sh, it, meta, tabs, aux0, m)) continue;
     const FbJob J = jobs[job0 + it.ji];
+    FbMeta m;
+    if (!fb_item_begin(Sh, it, meta, tabs, J.aux, m)) continue;
+    src.fixed_run = m.fixed;
     const u32 p = it.p0 + w;
     if (p >= J.np) continue;
     const u64 q0 = (u64)m.sym_start + (u64)p * m.piece_bits;
@@ -473,76 +541,101 @@ k_fblk_map(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, con
   }
 }
 
-// k_fblk_chain: step 2, a thread per block.  The block's first token starts after its header; piece p + 1 is entered
-// where piece p was left.  Leaves the result (status, end, what the merged chains stand for) and the token runs of the
-// merged chains; k_fblk_prefix adds the runs before them.
+// k_fblk_chain: step 2, a warp per block.  The block's first token starts after its header; piece p + 1 is entered where
+// piece p was left.  Where a piece is left does not depend on where it was entered once its chains have become one
+// (TA_X_MERGED -> sexit), so 32 pieces are chained per round: lane i assumes piece i - 1 was entered through its merged
+// chain — true as long as every lane before it found just that — and the round ends at the first piece for which it is
+// not, whose exit then is exact.  Leaves the result (status, end, what the merged chains stand for) and the token runs of
+// the merged chains; k_fblk_prefix adds the runs before them.
 __global__ void __launch_bounds__(128)
-k_fblk_chain(const FbJob *__restrict__ jobs, u32 njobs, u32 job0, u32 aux0, const FbMeta *__restrict__ meta, const u32 *__restrict__ maps, TaPiece *infos,
+k_fblk_chain(const FbJob *__restrict__ jobs, u32 njobs, u32 job0, const FbMeta *__restrict__ meta, const u32 *__restrict__ maps, TaPiece *infos,
              FbRes *res, FbPiece *pieces, u64 n) {
-  const u32 ji = blockIdx.x * blockDim.x + threadIdx.x;
+  const u32 ji = blockIdx.x * 4 + warp_id(), lane = lane_id();
   if (ji >= njobs) return;
   const u32 j = job0 + ji;
   const FbJob J = jobs[j];
-  const FbMeta m = meta[aux0 + ji];
+  const FbMeta m = meta[J.aux];
   const u64 bit0 = J.bit & ~7ull;
-  FbRes r0;
-  r0.end_bit = 0; r0.out_len = 0; r0.ntok = 0; r0.status = 0; r0.bfinal = m.bfinal; r0.npieces = 0; r0.pad = 0;
   FbPiece *pc = pieces + 2 * (size_t)J.piece0;
   TaPiece *inf = infos + J.piece0;
-  u32 status = 0, last = 0;
-  for (u32 p = 0; p < J.np; p++) inf[p].on_chain = 0;
+  u32 status = 0, last = 0, fin = 0, total_tok = 0, total_out = 0;
   if (m.mode) {
-    u32 e = m.sym_start, fin = 0;
+    u32 e = m.sym_start;  // where the next piece is entered
     status = FB_LONG;
-    for (u32 p = 0; p < J.np; p++) {
+    for (u32 p0 = 0; p0 < J.np && status == FB_LONG;) {
+      const u32 p = p0 + lane;
+      const bool have = p < J.np;
       const u64 q0 = (u64)m.sym_start + (u64)p * m.piece_bits;
-      if (q0 >= m.hard_end) { status = 0; break; }  // the stream ends before the block does
-      if (e < q0 || e - q0 >= TA_ENT) { status = 0; break; }
-      last = p;
-      u32 x = maps[(size_t)(J.piece0 + p) * TA_ENT + (e - (u32)q0)];
-      const u32 mg = x == TA_X_MERGED;
-      if (mg) x = inf[p].sexit;
-      inf[p].entry = e;
-      inf[p].merged = mg;
-      inf[p].on_chain = 1;
-      if (x == TA_X_BAD) { status = 0; break; }
-      if (x & TA_X_EOB) { status = FB_OK; fin = x & 0x7fffffffu; inf[p].on_chain = 2; break; }
-      e = x;
+      // the exit of the piece before (lane 0: exact; the others: if it was entered through its merged chain)
+      u32 prev = e;
+      if (lane > 0 && have) { prev = inf[p - 1].mpos ? inf[p - 1].sexit : TA_X_BAD; }
+      u32 x = TA_X_BAD;
+      const bool enter = have && q0 < m.hard_end && prev < TA_X_EOB && prev >= q0 && prev - q0 < TA_ENT;
+      if (enter) x = maps[(size_t)(J.piece0 + p) * TA_ENT + (prev - (u32)q0)];
+      const bool mg = x == TA_X_MERGED;
+      const u32 exit = mg ? inf[p].sexit : x;
+      const bool stop = have && (!mg || exit >= TA_X_EOB);  // the chain of assumptions ends here: this piece's exit is exact
+      const u32 nhave = (u32)__popc(__ballot_sync(ZLES_FULL, have));  // lanes 0 .. nhave - 1 have a piece (nhave >= 1)
+      const u32 sb = __ballot_sync(ZLES_FULL, stop);
+      const u32 first = sb ? (u32)__ffs((int)sb) - 1 : 32u;
+      const u32 upto = umin(first, nhave - 1);
+      if (lane <= upto) {
+        inf[p].entry = prev;
+        inf[p].merged = mg;
+        inf[p].on_chain = 1;
+        if (mg) {
+          total_tok += inf[p].snt;
+          total_out += inf[p].sob;
+        }
+      }
+      const u32 xe = __shfl_sync(ZLES_FULL, exit, (int)upto);
+      last = p0 + upto;
+      if (xe == TA_X_BAD) status = 0;
+      else if (xe & TA_X_EOB) { status = FB_OK; fin = xe & 0x7fffffffu; }
+      else { e = xe; fin = xe; }
+      p0 += upto + 1;
     }
-    if (status == FB_OK && bit0 + fin > (n << 3)) status = 0;  // the end-of-block code took bits the stream does not have
-    r0.end_bit = bit0 + fin;
+    if (status == FB_OK && lane == 0) inf[last].on_chain = 2;
+    if (bit0 + fin > (n << 3)) status = 0;  // the end-of-block code took bits the stream does not have
   }
-  u32 total_tok = 0, total_out = 0;
-  if (status == FB_OK) {
-    for (u32 p = 0; p <= last; p++) {
+  total_tok = __reduce_add_sync(ZLES_FULL, total_tok);
+  total_out = __reduce_add_sync(ZLES_FULL, total_out);
+  __syncwarp();
+  if (status) {  // the token runs of the merged chains (those before them: k_fblk_prefix)
+    for (u32 p = lane; p <= last; p += 32) {
       FbPiece e0, e1;
       e0.tok_off = 0; e0.cnt = 0; e0.bytes = 0; e0.pad = 0;
       e1 = e0;
       if (inf[p].merged) {
-        e1.tok_off = p * m.pcap + inf[p].mtiles * (TA_TILE / 2);
+        e1.tok_off = p * m.pcap + inf[p].soff;
         e1.cnt = inf[p].snt;
         e1.bytes = inf[p].sob;
-        total_tok += e1.cnt;
-        total_out += e1.bytes;
       }
       pc[2 * p] = e0;
       pc[2 * p + 1] = e1;
     }
+    for (u32 p = last + 1 + lane; p < J.np; p += 32) inf[p].on_chain = 0;
   } else {
-    for (u32 p = 0; p <= last && p < J.np; p++) inf[p].on_chain = 0;  // nothing for k_fblk_prefix to do
+    for (u32 p = lane; p < J.np; p += 32) inf[p].on_chain = 0;  // nothing for k_fblk_prefix to do
   }
-  r0.status = status;
-  r0.out_len = total_out;
-  r0.ntok = total_tok;
-  r0.npieces = status == FB_OK ? 2 * (last + 1) : 0;
-  res[j] = r0;
+  if (lane == 0) {
+    FbRes r0;
+    r0.end_bit = bit0 + fin;
+    r0.out_len = status ? total_out : 0;
+    r0.ntok = status ? total_tok : 0;
+    r0.status = status;
+    r0.bfinal = m.bfinal;
+    r0.npieces = status ? 2 * (last + 1) : 0;
+    r0.pad = 0;
+    res[j] = r0;
+  }
 }
 
 // k_fblk_prefix: step 3.  The pieces of the chain from their true entries, up to where their chains had become one (a
 // piece whose chains never did: all of it).  Adds its token runs to the block's result; a piece that does not come out
 // as step 1 said fails the block.
 __global__ void __launch_bounds__(FB_THREADS)
-k_fblk_prefix(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, const FbItem *__restrict__ items, u32 nitems, u32 job0, u32 aux0,
+k_fblk_prefix(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, const FbItem *__restrict__ items, u32 nitems, u32 job0,
               const FbMeta *__restrict__ meta, const TokWarpSmem *__restrict__ tabs, const TaPiece *__restrict__ infos, FbRes *res, FbPiece *pieces,
               u32 *counter) {
   ZLES_SMEM_DECL(smem_raw);
@@ -560,9 +653,10 @@ k_fblk_prefix(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, 
     const u32 j = job0 + it.ji;
     const FbJob J = jobs[j];
     // nothing to do for a block that did not chain up, or for pieces behind its last (the chain fills on_chain from piece 0 on)
-    if (res[j].status != FB_OK || infos[(size_t)J.piece0 + it.p0].on_chain == 0) continue;
+    if (res[j].status == 0 || infos[(size_t)J.piece0 + it.p0].on_chain == 0) continue;
     FbMeta m;
-    if (!fb_item_begin(Sh, it, meta, tabs, aux0, m)) continue;
+    if (!fb_item_begin(Sh, it, meta, tabs, J.aux, m)) continue;
+    src.fixed_run = m.fixed;
     const u32 p = it.p0 + w;
     if (p >= J.np) continue;
     const TaPiece I = infos[(size_t)J.piece0 + p];
@@ -570,11 +664,11 @@ k_fblk_prefix(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, 
     const bool mg = I.merged != 0, is_last = I.on_chain == 2;
     u32 nt = 0, ob = 0, fin = 0;
     const u32 st = ta_emit_piece(W, &Sh->T, src, J.bit & ~7ull, m.sym_start + p * m.piece_bits, m.piece_bits, m.hard_end, I.entry,
-                                 mg ? I.mpos : 0xffffffffu, J.tok + (size_t)p * m.pcap, mg ? I.mtiles * (TA_TILE / 2) : m.pcap, nt, ob, fin);
+                                 mg ? I.mpos : 0xffffffffu, J.tok + (size_t)p * m.pcap, mg ? I.soff : m.pcap, nt, ob, fin);
     if (lane == 0) {
       bool ok;
       if (mg) ok = st == 0 && fin == I.mpos;  // the run must end exactly where the merged chain starts
-      else ok = st != 2 && (st == 1) == is_last && (!is_last || (J.bit & ~7ull) + fin == res[j].end_bit);
+      else ok = st != 2 && (st == 1) == is_last && (!is_last || (J.bit & ~7ull) + fin == res[j].end_bit);  // (on_chain 2: the end-of-block code is in it)
       if (!ok) {
         atomicExch(&res[j].status, 0u);
       } else {
@@ -594,7 +688,7 @@ __global__ void __launch_bounds__(FB_THREADS) k_fblk_compact(const FbJob *__rest
   u32 *tok = J.tok;
   FbPiece *pc = pieces + 2 * (size_t)J.piece0;
   const u32 tid = threadIdx.x;
-  const u32 nslots = res[j].status == FB_OK ? res[j].npieces : 0;
+  const u32 nslots = res[j].status ? res[j].npieces : 0;
   u32 total = 0;
   for (u32 q = 0; q < nslots; q++) {  // runs move down, never up, in order
     const u32 cnt = pc[q].cnt, src0 = pc[q].tok_off, dst0 = total;
@@ -620,8 +714,57 @@ struct FbEnt {      // one block of the accepted chain
   u32 len;          // bytes it stands for
   u32 stored;
   u32 warp0;        // k_fpiece_sym: its first warp (a warp per token run; FB_STORED_WARPS for a stored block)
+  u32 slot0;        // its first token run in the stream-wide numbering of token runs (a stored block counts as one)
+  u32 nslots;
 };
 constexpr u32 FB_STORED_WARPS = 16;
+
+// the last entry e with key(e) <= g (ents[0] has key 0)
+template <typename F>
+__device__ __forceinline__ u32 fb_find_ent(u32 nent, u32 g, F key) {
+  u32 lo = 0, hi = nent;
+  while (hi - lo > 1) {
+    const u32 mid = (lo + hi) >> 1;
+    if (key(mid) <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// where every token run of a coded entry starts inside the entry (FbPiece.pad): a warp per entry
+__global__ void __launch_bounds__(128)
+k_fslot_scan(const FbJob *__restrict__ jobs, FbPiece *pieces, const FbEnt *__restrict__ ents, u32 nent) {
+  const u32 e = blockIdx.x * 4 + warp_id(), lane = lane_id();
+  if (e >= nent) return;
+  const FbEnt en = ents[e];
+  if (en.stored) return;
+  FbPiece *pc = pieces + 2 * (size_t)jobs[en.job].piece0;
+  u32 base = 0;
+  for (u32 q0 = 0; q0 < en.nslots; q0 += 32) {
+    const u32 q = q0 + lane;
+    const u32 b = q < en.nslots ? pc[q].bytes : 0;
+    u32 inc = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u32 t = __shfl_up_sync(ZLES_FULL, inc, d);
+      if (lane >= (u32)d) inc += t;
+    }
+    if (q < en.nslots) pc[q].pad = base + inc - b;
+    base += __shfl_sync(ZLES_FULL, inc, 31);
+  }
+}
+
+// run r starts with the stream's token run run_first[r]: where its bytes start (run_off[nruns] = total)
+__global__ void __launch_bounds__(128)
+k_frun_offsets(const FbJob *__restrict__ jobs, const FbPiece *__restrict__ pieces, const FbEnt *__restrict__ ents, u32 nent,
+               const u32 *__restrict__ run_first, u32 nruns, u64 total, u64 *run_off) {
+  const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > nruns) return;
+  if (r == nruns) { run_off[r] = total; return; }
+  const u32 f = run_first[r];
+  const u32 e = fb_find_ent(nent, f, [&](u32 i) { return ents[i].slot0; });
+  const FbEnt en = ents[e];
+  run_off[r] = en.out_off + (en.stored ? 0u : pieces[2 * (size_t)jobs[en.job].piece0 + (f - en.slot0)].pad);
+}
 
 // one warp per (chain entry, token run): the run's tokens into 16-bit symbols at sym + where its bytes go
 __global__ void __launch_bounds__(RES_THREADS)
@@ -630,12 +773,7 @@ k_fpiece_sym(const FbJob *__restrict__ jobs, const FbPiece *__restrict__ pieces,
   ZLES_SMEM_DECL(smem_raw);
   const u32 g = blockIdx.x * RES_WARPS + warp_id();
   if (g >= nwarps) return;
-  u32 lo = 0, hi = nent;  // the last entry whose first warp is <= g
-  while (hi - lo > 1) {
-    const u32 mid = (lo + hi) >> 1;
-    if (ents[mid].warp0 <= g) lo = mid; else hi = mid;
-  }
-  const FbEnt en = ents[lo];
+  const FbEnt en = ents[fb_find_ent(nent, g, [&](u32 i) { return ents[i].warp0; })];
   const u32 p = g - en.warp0;
   if (en.stored) {  // the entry's warps share the copy
     const u32 a = (u32)((u64)en.len * p / FB_STORED_WARPS), b = (u32)((u64)en.len * (p + 1) / FB_STORED_WARPS);
@@ -645,65 +783,58 @@ k_fpiece_sym(const FbJob *__restrict__ jobs, const FbPiece *__restrict__ pieces,
     return;
   }
   const FbJob J = jobs[en.job];
-  const FbPiece *pc = pieces + 2 * (size_t)J.piece0;
-  const FbPiece me = pc[p];
+  const FbPiece me = pieces[2 * (size_t)J.piece0 + p];
   if (me.cnt == 0) return;
-  u64 before = 0;
-  for (u32 q = lane_id(); q < p; q += 32) before += pc[q].bytes;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(ZLES_FULL, before, d);
   SymState st;
   st.ring = reinterpret_cast<u16 *>(smem_raw) + warp_id() * SEG_RING;
-  st.base = sym + en.out_off + before;
+  st.base = sym + en.out_off + me.pad;
   st.o = 0;
   st.refs = 0;
   st.vfrom = 0;
   sym_tokens<SEG_RING>(st, J.tok + me.tok_off, me.cnt);
 }
 
-// run r = chain entries [run_first[r], run_first[r + 1]): its token runs made concrete in order.  A reference that lands
+// run r = the stream's token runs [run_first[r], run_first[r + 1]), made concrete in order.  A reference that lands
 // inside the run takes what is there (a byte, or a reference into the run's window already); one that reaches before the
 // run becomes a reference into the 32 KiB before the run.  any_refs is set when a run other than the first keeps one.
 constexpr int MRG_THREADS = 512;
 __global__ void __launch_bounds__(MRG_THREADS)
-k_frun_merge(const FbJob *__restrict__ jobs, const FbRes *__restrict__ res, const FbPiece *__restrict__ pieces, const FbEnt *__restrict__ ents,
-             const u32 *__restrict__ run_first, u32 nruns, u16 *sym, u32 *any_refs) {
+k_frun_merge(const FbJob *__restrict__ jobs, const FbPiece *__restrict__ pieces, const FbEnt *__restrict__ ents, u32 nent,
+             const u32 *__restrict__ run_first, const u64 *__restrict__ run_off, u32 nruns, u16 *sym, u32 *any_refs) {
   for (u32 r = blockIdx.x; r < nruns; r += gridDim.x) {
-    const u32 e0 = run_first[r], e1 = run_first[r + 1];
-    const u64 run_base = ents[e0].out_off;
+    const u32 f0 = run_first[r], f1 = run_first[r + 1];
+    const u64 run_base = run_off[r];
     u32 kept = 0;
-    for (u32 e = e0; e < e1; e++) {
+    u32 e = fb_find_ent(nent, f0, [&](u32 i) { return ents[i].slot0; });
+    for (u32 f = f0; f < f1; f++) {
+      while (e + 1 < nent && ents[e + 1].slot0 <= f) e++;
       const FbEnt en = ents[e];
-      if (en.stored) continue;
-      const FbPiece *pc = pieces + 2 * (size_t)jobs[en.job].piece0;
-      const u32 nslots = res[en.job].npieces;
-      u64 pstart = en.out_off;
-      for (u32 p = 0; p < nslots; p++) {
-        const u32 bytes = pc[p].bytes;
-        if (bytes == 0) continue;
-        u16 *s = sym + pstart;
-        const long long rel = (long long)(pstart - run_base) - (long long)SYM_WIN;
-        for (u32 i0 = threadIdx.x; i0 < bytes; i0 += 4 * MRG_THREADS) {  // four independent elements per thread and round
-          u32 v[4];
+      if (en.stored) continue;  // concrete already
+      const FbPiece me = pieces[2 * (size_t)jobs[en.job].piece0 + (f - en.slot0)];
+      const u32 bytes = me.bytes;
+      if (bytes == 0) continue;
+      const u64 pstart = en.out_off + me.pad;
+      u16 *s = sym + pstart;
+      const long long rel = (long long)(pstart - run_base) - (long long)SYM_WIN;
+      for (u32 i0 = threadIdx.x; i0 < bytes; i0 += 4 * MRG_THREADS) {  // four independent elements per thread and round
+        u32 v[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) { const u32 i = i0 + u * MRG_THREADS; v[u] = i < bytes ? s[i] : 0u; }
-          bool ch[4];
+        for (int u = 0; u < 4; u++) { const u32 i = i0 + u * MRG_THREADS; v[u] = i < bytes ? s[i] : 0u; }
+        bool ch[4];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            ch[u] = v[u] >= SYM_REF;
-            if (ch[u]) {
-              const long long q = rel + (long long)(v[u] & 0x7fff);
-              if (q >= 0) v[u] = sym[run_base + (u64)q];
-              else v[u] = SYM_REF | (u32)(q + (long long)SYM_WIN);
-              if (v[u] >= SYM_REF) kept = 1;
-            }
+        for (int u = 0; u < 4; u++) {
+          ch[u] = v[u] >= SYM_REF;
+          if (ch[u]) {
+            const long long q = rel + (long long)(v[u] & 0x7fff);
+            if (q >= 0) v[u] = sym[run_base + (u64)q];
+            else v[u] = SYM_REF | (u32)(q + (long long)SYM_WIN);
+            if (v[u] >= SYM_REF) kept = 1;
           }
-#pragma unroll
-          for (int u = 0; u < 4; u++) { const u32 i = i0 + u * MRG_THREADS; if (i < bytes && ch[u]) s[i] = (u16)v[u]; }
         }
-        __syncthreads();  // the next run reads what this one wrote
-        pstart += bytes;
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const u32 i = i0 + u * MRG_THREADS; if (i < bytes && ch[u]) s[i] = (u16)v[u]; }
       }
+      __syncthreads();  // the next token run reads what this one wrote
     }
     if (kept && r > 0) atomicOr(any_refs, 1u);
   }

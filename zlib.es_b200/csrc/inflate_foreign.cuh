@@ -18,7 +18,7 @@
 //   k_fpiece_sym / k_frun_merge / k_win_propagate / k_sym_finalize
 //                   phase B: every piece is resolved on its own warp into 16-bit symbols, a byte that comes from
 //                   before the piece staying symbolic (0x8000 | offset into the 32 KiB before it, copied around like
-//                   any other value); the pieces of a run of blocks (>= 128 KiB) are made concrete in order; what
+//                   any other value); the pieces of a run (>= 128 KiB, mostly) are made concrete in order; what
 //                   reaches before a run refers to the run's window; the windows are made concrete run after run
 //                   (32 KiB each, cheap; skipped when no run kept a reference — zlib.es streams), and a last parallel
 //                   pass substitutes them (the two-pass scheme of pugz / rapidgzip).
@@ -318,20 +318,27 @@ __device__ __forceinline__ void sym_tokens(SymState &st, const u32 *__restrict__
   st.o = o;
 }
 
-// pass 2, one CTA: win[r] = the last 32 KiB of run r, concrete; win[-1] (before the stream) is all zeros, which is
-// what the reference's inflate reads there (/root/reference/src/inflate.ts:287-290).  Runs are >= 32 KiB except the last.
+// pass 2, one CTA: win[r] = the 32 KiB of output that end where run r ends, concrete; win[-1] (before the stream) is all
+// zeros, which is what the reference's inflate reads there (/root/reference/src/inflate.ts:287-290).  A run shorter
+// than 32 KiB takes the rest from the window before it.  Every thread keeps 32 symbols in flight.
 __global__ void __launch_bounds__(1024) k_win_propagate(const u16 *__restrict__ sym, const u64 *__restrict__ run_off, u32 nruns, u8 *win,
                                                         const u32 *__restrict__ any_refs) {
   if (*any_refs == 0) return;  // no run refers to its window: nothing to make concrete (k_frun_merge)
   for (u32 r = 0; r + 1 < nruns; r++) {
-    const u64 end = run_off[r + 1];
+    const u64 beg = run_off[r], end = run_off[r + 1];
+    const u32 own = (u32)umin64(end - beg, (u64)SYM_WIN);  // the window's last `own` bytes are this run's
     const u8 *prev = r ? win + (size_t)(r - 1) * SYM_WIN : nullptr;
-    for (u32 k = threadIdx.x; k < SYM_WIN; k += 1024) {
-      const u16 v = sym[end - SYM_WIN + k];
-      u8 b;
-      if (v < SYM_REF) b = (u8)v;
-      else b = prev ? prev[v & 0x7fff] : (u8)0;
-      win[(size_t)r * SYM_WIN + k] = b;
+    u8 *cur = win + (size_t)r * SYM_WIN;
+    u32 v[SYM_WIN / 1024];
+#pragma unroll
+    for (u32 i = 0; i < SYM_WIN / 1024; i++) {
+      const u32 k = threadIdx.x + i * 1024;
+      v[i] = k >= SYM_WIN - own ? (u32)sym[end - SYM_WIN + k] : SYM_REF | (k + own);  // (k + own < SYM_WIN: the window before, shifted)
+    }
+#pragma unroll
+    for (u32 i = 0; i < SYM_WIN / 1024; i++) {
+      const u32 k = threadIdx.x + i * 1024;
+      cur[k] = v[i] < SYM_REF ? (u8)v[i] : (prev ? prev[v[i] & 0x7fff] : (u8)0);
     }
     __syncthreads();
   }

@@ -972,8 +972,8 @@ static int read_ctl(zles_ctx *c, InfCtl *h) {
 }
 
 // The four kernels that decode jobs [job0, job0 + njobs) of c->fjobs (host copy: hjobs[0 .. njobs)) into tokens
-// (inflate_fblk.cuh); aux0: where their meta / tables go.  Results in c->fres / c->fpieces.
-static int fblk_decode(zles_ctx *c, const u8 *d_in, size_t n, const FbJob *hjobs, u32 njobs, u32 job0, u32 aux0) {
+// (inflate_fblk.cuh).  Results in c->fres / c->fpieces.
+static int fblk_decode(zles_ctx *c, const u8 *d_in, size_t n, const FbJob *hjobs, u32 njobs, u32 job0) {
   InfCtl *ctl = c->ctl.as<InfCtl>();
   const FbJob *jobs = c->fjobs.as<FbJob>();
   std::vector<FbItem> items;
@@ -985,13 +985,13 @@ static int fblk_decode(zles_ctx *c, const u8 *d_in, size_t n, const FbJob *hjobs
   const u32 grid = nitems < 2 * (u32)c->sm_count ? nitems : 2 * (u32)c->sm_count;  // two CTAs per SM (shared memory, registers)
   CK(zrt_h2d(c->fitems.p, items.data(), (size_t)nitems * sizeof(FbItem), c->stream));
   CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
-  LAUNCH(c, k_fblk_head, (njobs + INF_WARPS - 1) / INF_WARPS, INF_THREADS, TOK_SMEM, d_in, (u64)n, jobs, njobs, job0, aux0, c->fmeta.as<FbMeta>(),
+  LAUNCH(c, k_fblk_head, (njobs + INF_WARPS - 1) / INF_WARPS, INF_THREADS, TOK_SMEM, d_in, (u64)n, jobs, njobs, job0, c->fmeta.as<FbMeta>(),
          c->ftab.as<TokWarpSmem>());
-  LAUNCH(c, k_fblk_map, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0, aux0,
+  LAUNCH(c, k_fblk_map, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0,
          (const FbMeta *)c->fmeta.as<FbMeta>(), (const TokWarpSmem *)c->ftab.as<TokWarpSmem>(), c->fmaps.as<u32>(), c->finfo.as<TaPiece>(), &ctl->counter);
-  LAUNCH(c, k_fblk_chain, (njobs + 127) / 128, 128, 0, jobs, njobs, job0, aux0, (const FbMeta *)c->fmeta.as<FbMeta>(), (const u32 *)c->fmaps.as<u32>(),
+  LAUNCH(c, k_fblk_chain, (njobs + 3) / 4, 128, 0, jobs, njobs, job0, (const FbMeta *)c->fmeta.as<FbMeta>(), (const u32 *)c->fmaps.as<u32>(),
          c->finfo.as<TaPiece>(), c->fres.as<FbRes>(), c->fpieces.as<FbPiece>(), (u64)n);
-  LAUNCH(c, k_fblk_prefix, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0, aux0,
+  LAUNCH(c, k_fblk_prefix, grid, FB_THREADS, FB_SMEM, d_in, (u64)n, jobs, (const FbItem *)c->fitems.as<FbItem>(), nitems, job0,
          (const FbMeta *)c->fmeta.as<FbMeta>(), (const TokWarpSmem *)c->ftab.as<TokWarpSmem>(), (const TaPiece *)c->finfo.as<TaPiece>(),
          c->fres.as<FbRes>(), c->fpieces.as<FbPiece>(), &ctl->ok);
   CK(zrt_last_error());
@@ -1001,7 +1001,7 @@ static int fblk_decode(zles_ctx *c, const u8 *d_in, size_t n, const FbJob *hjobs
 
 // Returns 0 (decoded), a positive status, or -1 when the stream is not something this path handles.
 constexpr u32 FB_DEMAND_MAX = 16384;               // blocks decoded on demand per stream at most (a few launches and a read-back each)
-constexpr u64 FB_DEMAND_SPAN = 8ull * 65536;       // hint for a block decoded on demand: 64 KiB of stream at most
+constexpr u64 FB_DEMAND_SPAN = 8ull << 20;         // hint for a block decoded on demand: 1 MiB of stream at most (all its pieces at once)
 constexpr size_t FB_DEM_SLAB = (size_t)16 << 20;   // tokens per slab of on-demand token room (64 MiB)
 static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 *d_out, size_t cap, size_t *out_len) {
   if (n < first + 1 || (u64)n >= (1ull << 40)) return -1;
@@ -1044,6 +1044,8 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
     J.flags = 0;
     J.piece0 = (u32)npieces;
     J.np = fb_planned_pieces(hint - cand[i]);
+    J.aux = i;
+    J.pad = 0;
     J.tok = reinterpret_cast<u32 *>(tok_total);  // offset for now
     tok_total += J.tok_cap;
     npieces += J.np;
@@ -1059,99 +1061,116 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   if (ncand) {
     for (u32 i = 0; i < ncand; i++) jobs[i].tok = c->tokens.as<u32>() + reinterpret_cast<u64>(jobs[i].tok);
     CK(zrt_h2d(c->fjobs.p, jobs.data(), (size_t)ncand * sizeof(FbJob), c->stream));
-    RET(fblk_decode(c, d_in, n, jobs.data(), ncand, 0u, 0u));
+    RET(fblk_decode(c, d_in, n, jobs.data(), ncand, 0u));
     CK(zrt_d2h(res.data(), c->fres.p, (size_t)ncand * sizeof(FbRes), c->stream));
     CK(zrt_sync(c->stream));
   }
-  // blocks the scan did not find (fixed blocks, dynamic blocks with an incomplete code): decoded when the chain reaches them
+  // Blocks the scan did not find (fixed blocks, dynamic blocks with an incomplete code) are decoded when the chain
+  // reaches them; a block that turns out longer than the room its hint gave it (FB_LONG: a false candidate inside it, or
+  // a hint that was a guess) is decoded on from where that room ended, with four times the room.
   u32 ndem = 0;
   size_t dem_slab = 0, dem_used = 0;
-  auto demand = [&](u64 pos, FbRes &r, bool was_long) -> int {
-    const auto nx = std::upper_bound(cand.begin(), cand.end(), pos);
-    u64 hint = nx != cand.end() ? *nx : nbits;
-    if (was_long) {  // a candidate that turned out longer than up to the next one (a false positive inside it): four times the room
-      hint = pos + (hint - pos) * 4;
-      if (hint > nbits) hint = nbits;
-    } else if (hint > pos + FB_DEMAND_SPAN) {
-      hint = pos + FB_DEMAND_SPAN;
+  auto demand = [&](u64 pos, u64 hint, u32 flags, u32 aux, FbRes &r) -> int {
+    if (ndem >= FB_DEMAND_MAX) return -1;
+    const u64 capt = fb_tok_room(hint - pos);
+    const u32 np = fb_planned_pieces(hint - pos);
+    if (capt > 0xffffffe0ull || npieces + np > pieces_cap) return -1;
+    // room: the current slab, or the next one
+    for (;; dem_slab++, dem_used = 0) {
+      if (dem_slab >= c->dem_slabs.size()) c->dem_slabs.emplace_back();
+      DevBuf &sl = c->dem_slabs[dem_slab];
+      if (sl.cap == 0 && sl.reserve((FB_DEM_SLAB > capt ? FB_DEM_SLAB : (size_t)capt) * 4)) return -1;
+      if ((dem_used + capt) * 4 <= sl.cap) break;
     }
-    for (;;) {  // again with a longer hint when the block turns out longer than its room
-      if (ndem >= FB_DEMAND_MAX) return -1;
-      const u64 capt = fb_tok_room(hint - pos);
-      const u32 np = fb_planned_pieces(hint - pos);
-      if (capt > 0xffffffe0ull || npieces + np > pieces_cap) return -1;
-      // room: the current slab, or the next one
-      for (;; dem_slab++, dem_used = 0) {
-        if (dem_slab >= c->dem_slabs.size()) c->dem_slabs.emplace_back();
-        DevBuf &sl = c->dem_slabs[dem_slab];
-        if (sl.cap == 0 && sl.reserve((FB_DEM_SLAB > capt ? FB_DEM_SLAB : (size_t)capt) * 4)) return -1;
-        if ((dem_used + capt) * 4 <= sl.cap) break;
-      }
-      FbJob J;
-      J.bit = pos; J.hint_end = hint; J.tok = c->dem_slabs[dem_slab].as<u32>() + dem_used; J.tok_cap = (u32)capt; J.flags = FB_JOB_COMPACT;
-      J.piece0 = (u32)npieces; J.np = np;
-      const u32 ji = ncand + ndem;
-      CK(zrt_h2d(c->fjobs.as<FbJob>() + ji, &J, sizeof(FbJob), c->stream));
-      RET(fblk_decode(c, d_in, n, &J, 1u, ji, ncand));
-      LAUNCH(c, k_fblk_compact, 1, FB_THREADS, 0, (const FbJob *)c->fjobs.as<FbJob>(), ji, (const FbRes *)c->fres.as<FbRes>(), c->fpieces.as<FbPiece>());
-      CK(zrt_last_error());
-      CK(zrt_mail(&c->mail->fres0[0], c->fres.as<FbRes>() + ji, sizeof(FbRes), c->stream));
-      CK(zrt_sync(c->stream));  // also: J is on the stack
-      memcpy(&r, &c->mail->fres0[0], sizeof(FbRes));
-      ndem++;
-      if (r.status == FB_LONG && hint < nbits) {
-        hint = pos + (hint - pos) * 4;
-        if (hint > nbits) hint = nbits;
-        continue;
-      }
-      if (r.status != FB_OK) return -1;
-      dem_used += ((size_t)r.ntok + 31) & ~(size_t)31;
-      npieces += (r.npieces + 1) / 2;  // the pieces the block really has keep their slots
-      return 0;
-    }
+    FbJob J;
+    J.bit = pos; J.hint_end = hint; J.tok = c->dem_slabs[dem_slab].as<u32>() + dem_used; J.tok_cap = (u32)capt; J.flags = FB_JOB_COMPACT | flags;
+    J.piece0 = (u32)npieces; J.np = np; J.aux = aux; J.pad = 0;
+    const u32 ji = ncand + ndem;
+    CK(zrt_h2d(c->fjobs.as<FbJob>() + ji, &J, sizeof(FbJob), c->stream));
+    RET(fblk_decode(c, d_in, n, &J, 1u, ji));
+    LAUNCH(c, k_fblk_compact, 1, FB_THREADS, 0, (const FbJob *)c->fjobs.as<FbJob>(), ji, (const FbRes *)c->fres.as<FbRes>(), c->fpieces.as<FbPiece>());
+    CK(zrt_last_error());
+    CK(zrt_mail(&c->mail->fres0[0], c->fres.as<FbRes>() + ji, sizeof(FbRes), c->stream));
+    CK(zrt_sync(c->stream));  // also: J is on the stack
+    memcpy(&r, &c->mail->fres0[0], sizeof(FbRes));
+    ndem++;
+    if (r.status != FB_OK && r.status != FB_LONG) return -1;
+    dem_used += ((size_t)r.ntok + 31) & ~(size_t)31;
+    npieces += (r.npieces + 1) / 2;  // the pieces the block really has keep their slots
+    return 0;
   };
   // chain walk: the block after one that ends at bit e starts at bit e
   std::vector<FbEnt> chain;
-  u64 pos = first * 8, total = 0, nwarps = 0;
+  u64 pos = first * 8, total = 0, nwarps = 0, nflat = 0;
+  auto push = [&](FbEnt en) {
+    en.out_off = total;
+    en.warp0 = (u32)nwarps;
+    en.slot0 = (u32)nflat;
+    nwarps += en.stored ? FB_STORED_WARPS : en.nslots;
+    nflat += en.nslots;
+    total += en.len;
+    chain.push_back(en);
+  };
   for (;;) {
-    if (chain.size() > (size_t)ncand + nst + FB_DEMAND_MAX) return -1;
+    if (chain.size() > (size_t)ncand + nst + 2 * (size_t)FB_DEMAND_MAX) return -1;
     if (pos + 3 > nbits) return -1;
     const auto it = std::lower_bound(cand.begin(), cand.end(), pos);
     const auto is = std::lower_bound(stv.begin(), stv.end(), pos, [](const FbStored &a, u64 p) { return a.bit < p; });
+    const bool is_cand = it != cand.end() && *it == pos && res[(size_t)(it - cand.begin())].status != 0;
     u32 bfinal;
     u64 next;
     FbEnt en;
     memset(&en, 0, sizeof(en));
-    en.out_off = total;
-    en.warp0 = (u32)nwarps;
-    if (it != cand.end() && *it == pos && res[(size_t)(it - cand.begin())].status == FB_OK) {
-      const FbRes &r = res[(size_t)(it - cand.begin())];
-      en.job = (u32)(it - cand.begin());
-      en.len = r.out_len;
-      bfinal = r.bfinal;
-      next = r.end_bit;
-      nwarps += r.npieces;
-    } else if (is != stv.end() && is->bit == pos) {
+    if (!is_cand && is != stv.end() && is->bit == pos) {
       const u64 q = (pos + 3 + 7) >> 3;
       en.src = q + 4;
       en.len = is->len;
       en.stored = 1;
+      en.nslots = 1;
       bfinal = is->bfinal;
       next = (q + 4 + is->len) * 8;
-      nwarps += FB_STORED_WARPS;
+      push(en);
     } else {
       FbRes r;
-      const int rc = demand(pos, r, it != cand.end() && *it == pos && res[(size_t)(it - cand.begin())].status == FB_LONG);
-      if (rc) return rc;  // not a block this path decodes (BTYPE 3, a damaged stored block, garbage): sequential path
-      en.job = ncand + ndem - 1;
-      en.len = r.out_len;
+      u32 aux;
+      u64 span;
+      if (is_cand) {
+        const size_t ci = (size_t)(it - cand.begin());
+        r = res[ci];
+        en.job = (u32)ci;
+        aux = (u32)ci;
+        span = jobs[ci].hint_end - pos;
+      } else {
+        // not a block this path decodes (BTYPE 3, a damaged stored block, garbage)?  Then the sequential path.
+        const auto nx = std::upper_bound(cand.begin(), cand.end(), pos);
+        u64 hint = nx != cand.end() ? *nx : nbits;
+        if (hint > pos + FB_DEMAND_SPAN) hint = pos + FB_DEMAND_SPAN;
+        span = hint - pos;
+        aux = ncand;
+        const int rc = demand(pos, hint, 0, aux, r);
+        if (rc) return rc;
+        en.job = ncand + ndem - 1;
+      }
+      for (;;) {
+        en.len = r.out_len;
+        en.nslots = r.npieces;
+        push(en);
+        if (r.status == FB_OK) break;
+        // FB_LONG: on from where the room ended
+        const u64 from = r.end_bit;
+        if (from <= pos || from >= nbits) return -1;
+        span *= 4;
+        u64 hint = from + span;
+        if (hint > nbits) hint = nbits;
+        const int rc = demand(from, hint, FB_JOB_CONT, aux, r);
+        if (rc) return rc;
+        en.job = ncand + ndem - 1;
+        pos = from;
+      }
       bfinal = r.bfinal;
       next = r.end_bit;
-      nwarps += r.npieces;
     }
-    chain.push_back(en);
-    total += en.len;
-    if (total >= (1ull << 46) || nwarps >= 0x7fff0000ull) return -1;
+    if (total >= (1ull << 46) || nwarps >= 0x7fff0000ull || nflat >= 0x7fff0000ull) return -1;
     if (bfinal) break;
     if (next <= pos) return -1;
     pos = next;
@@ -1159,35 +1178,48 @@ static int inflate_foreign(zles_ctx *c, const u8 *d_in, size_t n, u64 first, u8 
   *out_len = (size_t)total;
   if (total > cap) return ZLES_E_OUTPUT_FULL;
   const u32 nblk = (u32)chain.size();
-  // runs of whole blocks, at least SYM_RUN bytes each (the last one may be shorter); long streams take longer runs so that
-  // the serial window propagation stays short
+  // Runs: about `target` bytes of output each, cut at token runs — a long block (a run of fixed blocks decoded as one can
+  // be the whole stream) is cut in proportion to its token runs; where exactly a run starts is worked out on the device
+  // (k_frun_offsets).  Long streams take longer runs so that the serial window propagation stays short.
   std::vector<u32> run_first;
-  std::vector<u64> run_off;
   {
-    u64 target = total / 2048;
+    u64 target = total / 1024;
     if (target < SYM_RUN) target = SYM_RUN;
     u64 acc = 0;
     for (u32 i = 0; i < nblk; i++) {
-      if (i == 0 || acc >= target) { run_first.push_back(i); run_off.push_back(chain[i].out_off); acc = 0; }
-      acc += chain[i].len;
+      const FbEnt &en = chain[i];
+      if (i == 0 || acc >= target) { run_first.push_back(en.slot0); acc = 0; }
+      u64 k = en.len / target;  // cut this entry into k parts?
+      if (k > en.nslots) k = en.nslots;
+      if (k >= 2) {
+        for (u64 q = 1; q < k; q++) {
+          const u32 f = en.slot0 + (u32)(q * en.nslots / k);
+          if (f > run_first.back()) run_first.push_back(f);
+        }
+        acc = en.len / k;
+      } else {
+        acc += en.len;
+      }
     }
   }
   const u32 nruns = (u32)run_first.size();
-  run_first.push_back(nblk);
-  run_off.push_back(total);
+  run_first.push_back((u32)nflat);
   if (c->fsym.reserve((size_t)total * 2 + 64) || c->fwin.reserve((size_t)nruns * SYM_WIN)) return -1;
   RET(c->fchain.reserve((size_t)nblk * sizeof(FbEnt)));
   RET(c->run_first.reserve((size_t)(nruns + 1) * 4));
   RET(c->seg_off.reserve((size_t)(nruns + 1) * 8));
   CK(zrt_h2d(c->fchain.p, chain.data(), (size_t)nblk * sizeof(FbEnt), c->stream));
   CK(zrt_h2d(c->run_first.p, run_first.data(), (size_t)(nruns + 1) * 4, c->stream));
-  CK(zrt_h2d(c->seg_off.p, run_off.data(), (size_t)(nruns + 1) * 8, c->stream));
   CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  const FbEnt *d_ents = c->fchain.as<FbEnt>();
+  LAUNCH(c, k_fslot_scan, (nblk + 3) / 4, 128, 0, (const FbJob *)c->fjobs.as<FbJob>(), c->fpieces.as<FbPiece>(), d_ents, nblk);
+  LAUNCH(c, k_frun_offsets, (nruns + 1 + 127) / 128, 128, 0, (const FbJob *)c->fjobs.as<FbJob>(), (const FbPiece *)c->fpieces.as<FbPiece>(), d_ents, nblk,
+         (const u32 *)c->run_first.as<u32>(), nruns, (u64)total, c->seg_off.as<u64>());
   LAUNCH(c, k_fpiece_sym, (u32)((nwarps + RES_WARPS - 1) / RES_WARPS), RES_THREADS, SEG_SMEM, (const FbJob *)c->fjobs.as<FbJob>(),
-         (const FbPiece *)c->fpieces.as<FbPiece>(), (const FbEnt *)c->fchain.as<FbEnt>(), nblk, (u32)nwarps, d_in, c->fsym.as<u16>());
+         (const FbPiece *)c->fpieces.as<FbPiece>(), d_ents, nblk, (u32)nwarps, d_in, c->fsym.as<u16>());
   LAUNCH(c, k_frun_merge, nruns < (u32)c->sm_count * 8 ? nruns : (u32)c->sm_count * 8, MRG_THREADS, 0, (const FbJob *)c->fjobs.as<FbJob>(),
-         (const FbRes *)c->fres.as<FbRes>(), (const FbPiece *)c->fpieces.as<FbPiece>(), (const FbEnt *)c->fchain.as<FbEnt>(),
-         (const u32 *)c->run_first.as<u32>(), nruns, c->fsym.as<u16>(), &ctl->ok_res);
+         (const FbPiece *)c->fpieces.as<FbPiece>(), d_ents, nblk, (const u32 *)c->run_first.as<u32>(), (const u64 *)c->seg_off.as<u64>(), nruns,
+         c->fsym.as<u16>(), &ctl->ok_res);
   LAUNCH(c, k_win_propagate, 1, 1024, 0, (const u16 *)c->fsym.as<u16>(), (const u64 *)c->seg_off.as<u64>(), nruns, c->fwin.as<u8>(),
          (const u32 *)&ctl->ok_res);
   {

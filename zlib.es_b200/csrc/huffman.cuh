@@ -21,6 +21,12 @@ constexpr int HUF_WARPS = 4;
 constexpr int HUF_THREADS = HUF_WARPS * 32;
 constexpr u32 HDR_BYTES = 576;  // >= ceil((14 + 19*3 + 316*14) / 8) = 562
 constexpr u32 HUF_STORED = 0xffffffffu;  // BlockCodes::hdr_nbits of a block that is smaller stored (BTYPE=0) than coded
+// bytes a block of `bits` bits takes in the stream: padded to a byte when it ends the stream, else followed by the empty
+// stored block that makes the next block start on a byte (3 bits + pad, LEN, NLEN); bit 31 set: `bits` holds the bytes already
+__host__ __device__ __forceinline__ u32 seg_bytes_of(u32 bits, bool final_block) {
+  if (bits & 0x80000000u) return bits & 0x7fffffffu;
+  return final_block ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4;
+}
 
 struct BlockCodes {       // written by k_huff, read by k_pack
   u32 ll[288];            // (bit-reversed code << 8) | length, 0 for unused symbols
@@ -184,15 +190,11 @@ __device__ __forceinline__ void huf_putbits(u32 *buf, u32 &pos, u32 v, u32 nb) {
   pos += nb;
 }
 
-// own_len[b] = input bytes of block b: n and table describe them as in LzParams (one stream, or a batch table).
-__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 first_block, u32 nblocks, BlockCodes *codes, u32 *blk_bits,
-                                                      u64 n, const BatchBlk *__restrict__ table) {
-  ZLES_SMEM_DECL(smem_raw);
-  HufWarpSmem *S = reinterpret_cast<HufWarpSmem *>(smem_raw) + warp_id();
+// Codes, header bits and coded size of one block from its symbol counts in S->freq (the end-of-block symbol is added
+// here): leaves the codes in S->code, the header in S->hdr; hbits = header bits after BFINAL / BTYPE, bits = what the
+// symbols and their extra bits take.  One warp.
+__device__ __forceinline__ void huf_block(HufWarpSmem *S, u32 &hbits_out, u32 &bits_out) {
   const u32 lane = lane_id();
-  const u32 b = first_block + blockIdx.x * HUF_WARPS + warp_id();
-  if (b >= nblocks) return;  // whole warp leaves; no CTA barrier below
-  for (u32 i = lane; i < 320; i += 32) S->freq[i] = hist[(size_t)b * 320 + i];
   __syncwarp();
   if (lane == 0) S->freq[256] = 1;  // EOB, src/deflate.ts:58
   __syncwarp();
@@ -276,6 +278,26 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hi
     bits += S->freq[i] * (S->len[i] + e);
   }
   bits = __reduce_add_sync(ZLES_FULL, bits);
+  hbits_out = hbits;
+  bits_out = bits;
+}
+
+constexpr u32 BLK_BYTES = 0x80000000u;   // blk_bits[]: bit 31 set = the low bits are the block's BYTES in the stream, marker or final pad
+                                         // included (a chunk written as one block: its first block carries all of it, the others 0)
+constexpr u32 HUF_MERGE_MAX = 8192;      // chunks that compress to less than this many bytes are tried as one block
+constexpr u32 HUF_MERGED = 0x4d524730u;  // BlockCodes::pad_[0] of the first block of such a chunk; pad_[1] = its blocks
+
+// own_len[b] = input bytes of block b: n and table describe them as in LzParams (one stream, or a batch table).
+__global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hist, u32 first_block, u32 nblocks, BlockCodes *codes, u32 *blk_bits,
+                                                      u64 n, const BatchBlk *__restrict__ table) {
+  ZLES_SMEM_DECL(smem_raw);
+  HufWarpSmem *S = reinterpret_cast<HufWarpSmem *>(smem_raw) + warp_id();
+  const u32 lane = lane_id();
+  const u32 b = first_block + blockIdx.x * HUF_WARPS + warp_id();
+  if (b >= nblocks) return;  // whole warp leaves; no CTA barrier below
+  for (u32 i = lane; i < 320; i += 32) S->freq[i] = hist[(size_t)b * 320 + i];
+  u32 hbits, bits;
+  huf_block(S, hbits, bits);
   BlockCodes *C = codes + b;
   for (u32 i = lane; i < 288; i += 32) C->ll[i] = S->code[i];
   C->d[lane] = S->code[288 + lane];
@@ -294,6 +316,54 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hi
       C->hdr_nbits = hbits;
       blk_bits[b] = coded;
     }
+  }
+}
+
+// One block per chunk where four headers cost more than they save: the reference writes one dynamic block per 128 KiB
+// chunk (/root/reference/src/deflate.ts:20-34), we write four — on input that compresses to a few hundred bytes per
+// chunk (zeros, short periods) the three extra headers and markers are a third of the output.  A warp per chunk whose
+// four blocks are all coded and small: the code of the summed counts, and if header + symbols + one marker come out
+// smaller than the four blocks, the chunk's first block takes the code and the whole chunk's bytes, the others nothing
+// (k_pack then writes one header, the tokens of all four, one end-of-block code, one marker).  Such a stream is still
+// plain zlib, but no longer a run of 32 KiB blocks: our inflate decodes it with the block-parallel tier for other
+// encoders' streams (inflate_fblk.cuh).
+__global__ void __launch_bounds__(HUF_THREADS) k_huff_merge(const u32 *__restrict__ hist, u32 first_block, u32 end_block, u32 nblocks_total,
+                                                            u32 last_is_final, BlockCodes *codes, u32 *blk_bits) {
+  ZLES_SMEM_DECL(smem_raw);
+  HufWarpSmem *S = reinterpret_cast<HufWarpSmem *>(smem_raw) + warp_id();
+  const u32 lane = lane_id();
+  const u32 b0 = (first_block / SUBS_PER_CHUNK + blockIdx.x * HUF_WARPS + warp_id()) * SUBS_PER_CHUNK;
+  if (b0 < first_block || b0 >= end_block) return;
+  const u32 cnt = umin(SUBS_PER_CHUNK, nblocks_total - b0);
+  if (cnt < 2 || b0 + cnt > end_block) return;
+  // what the blocks take on their own
+  u32 sep = 0;
+  bool ok = true;
+  for (u32 k = 0; k < cnt; k++) {
+    if (codes[b0 + k].hdr_nbits == HUF_STORED) ok = false;
+    sep += seg_bytes_of(blk_bits[b0 + k], last_is_final && b0 + k + 1 == nblocks_total);
+  }
+  if (!ok || sep >= HUF_MERGE_MAX) return;
+  for (u32 i = lane; i < 320; i += 32) {
+    u32 f = 0;
+    for (u32 k = 0; k < cnt; k++) f += hist[(size_t)(b0 + k) * 320 + i];
+    S->freq[i] = f;
+  }
+  __syncwarp();
+  u32 hbits, bits;
+  huf_block(S, hbits, bits);  // (sets the end-of-block count to 1)
+  const u32 merged = seg_bytes_of(3 + hbits + bits, last_is_final && b0 + cnt == nblocks_total);
+  if (merged >= sep) return;
+  BlockCodes *C = codes + b0;
+  for (u32 i = lane; i < 288; i += 32) C->ll[i] = S->code[i];
+  C->d[lane] = S->code[288 + lane];
+  for (u32 i = lane; i < HDR_BYTES / 4; i += 32) reinterpret_cast<u32 *>(C->hdr)[i] = S->hdr[i];
+  if (lane == 0) {
+    C->hdr_nbits = hbits;
+    C->pad_[0] = HUF_MERGED;
+    C->pad_[1] = cnt;
+    blk_bits[b0] = BLK_BYTES | merged;
+    for (u32 k = 1; k < cnt; k++) blk_bits[b0 + k] = BLK_BYTES;
   }
 }
 

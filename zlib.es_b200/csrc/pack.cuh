@@ -40,9 +40,7 @@ struct LayoutParams {
   u64 *summary;          // [0]=total bytes, [1]=sum d mod p, [2]=sum (n - i) d[i] mod p (i local to the shard)
 };
 
-__host__ __device__ __forceinline__ u32 seg_bytes(u32 bits, bool final_block) {
-  return final_block ? (bits + 7) >> 3 : ((bits + 3 + 7) >> 3) + 4;
-}
+__host__ __device__ __forceinline__ u32 seg_bytes(u32 bits, bool final_block) { return seg_bytes_of(bits, final_block); }
 
 // single CTA
 __global__ void __launch_bounds__(1024) k_layout(const LayoutParams P) {
@@ -211,14 +209,16 @@ __device__ __forceinline__ void pack_finish(PackState &st) {
 // Appends deflate blocks [b0, b1) bit-concatenated and then either the final pad
 // (src/deflate.ts:35-37) or the empty stored block that makes the next block byte aligned.
 // raw[b] = the block's own input bytes (for stored blocks), raw_len = their number.
+// merged: the blocks are written as ONE block — the header and code of block b0, the tokens of all, one end-of-block code
+// (k_huff_merge).
 __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *tokens, const u32 *ntok, const BlockCodes *codes,
-                                           u32 b0, u32 b1, bool final_chunk, const u8 *raw, u32 raw_len) {
+                                           u32 b0, u32 b1, bool final_chunk, const u8 *raw, u32 raw_len, bool merged = false) {
   const u32 tid = threadIdx.x;
   u64 bits[PACK_ITEMS];
   u32 nb[PACK_ITEMS];
   for (u32 b = b0; b < b1; b++) {
-    const BlockCodes *C = codes + b;
-    if (C->hdr_nbits == HUF_STORED) {  // BTYPE=0: header byte, LEN, NLEN, the bytes; then the marker unless final
+    const BlockCodes *C = codes + (merged ? b0 : b);
+    if (!merged && C->hdr_nbits == HUF_STORED) {  // BTYPE=0: header byte, LEN, NLEN, the bytes; then the marker unless final
       const bool fin = final_chunk && b + 1 == b1;
       const u32 nitems = 2 + (raw_len + 3) / 4 + (fin ? 0 : 2);  // 8 + 32 header bits | payload words | 8 + 32 marker bits
       for (u32 base = 0; base < nitems; base += PACK_TILE) {
@@ -242,13 +242,15 @@ __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *
       }
       continue;
     }
-    for (u32 i = tid; i < 320; i += PACK_THREADS) ctab[i] = i < 288 ? C->ll[i] : C->d[i - 288];
-    __syncthreads();
+    if (!merged || b == b0) {
+      for (u32 i = tid; i < 320; i += PACK_THREADS) ctab[i] = i < 288 ? C->ll[i] : C->d[i - 288];
+      __syncthreads();
+    }
     // block header: BFINAL, BTYPE=2 (src/deflate.ts:21-28), then the code-length header in 32-bit pieces
     const u32 hbits = C->hdr_nbits;
-    const u32 hwords = (hbits + 31) >> 5;
-    const u32 bfinal = (final_chunk && b + 1 == b1) ? 1u : 0u;
-    for (u32 base = 0; base < hwords + 1; base += PACK_TILE) {
+    const u32 hwords = (merged && b != b0) ? 0xffffffffu : (hbits + 31) >> 5;  // (no header inside a merged chunk)
+    const u32 bfinal = (final_chunk && (merged || b + 1 == b1)) ? 1u : 0u;
+    for (u32 base = 0; hwords != 0xffffffffu && base < hwords + 1; base += PACK_TILE) {
 #pragma unroll
       for (int k = 0; k < PACK_ITEMS; k++) {
         const u32 i = base + tid * PACK_ITEMS + k;
@@ -292,7 +294,7 @@ __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *
       pack_emit(st, bits, nb);
     }
     // end of block (src/deflate.ts:222-226); after the chunk's last block the sync marker or the final pad
-    {
+    if (!merged || b + 1 == b1) {
       const u32 cur = (st.wcur << 5) + st.carry_bits;  // bit position inside the aligned word stream
 #pragma unroll
       for (int k = 0; k < PACK_ITEMS; k++) { bits[k] = 0; nb[k] = 0; }
@@ -322,10 +324,16 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(const PackParams P) {
   u32 *scratch = ctab + 320;
   const u32 b = P.first_block + blockIdx.x;
   if (b >= P.nblocks) return;
+  if (P.blk_bits[b] == BLK_BYTES) return;  // inside a chunk written as one block: its first block's CTA writes it
   PackState st;
   pack_begin(st, stage, scratch, P.out + P.blk_off[b]);
-  pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, P.last_is_final && b + 1 == P.nblocks, P.in + (u64)b * SUB,
-             (u32)umin64((u64)SUB, P.n - (u64)b * SUB));
+  if (P.blk_bits[b] & BLK_BYTES) {
+    const u32 cnt = P.codes[b].pad_[1];
+    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + cnt, P.last_is_final && b + cnt == P.nblocks, P.in, 0, true);
+  } else {
+    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, P.last_is_final && b + 1 == P.nblocks, P.in + (u64)b * SUB,
+               (u32)umin64((u64)SUB, P.n - (u64)b * SUB));
+  }
   pack_finish(st);
 }
 

@@ -117,6 +117,7 @@ struct zles_ctx {
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
   u32 pair_mode = 1;  // zles_ctx_set_window_mode
+  bool merge_chunks = true;  // k_huff_merge (ZLES_NO_MERGE=1 in the environment turns it off: a debugging aid)
   size_t inf_stream_min = (size_t)96 << 20;  // host-buffer inflate: streams at least this long are copied in pieces, scanned and decoded as they land
   u32 inf_slab_blocks = 0;  // host-buffer inflate of our own streams: blocks per slab (inflate_slabs_to_host); 0 = automatic
   DevBuf unit_ctr;    // k_lz hands its units out from this counter
@@ -258,6 +259,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_lz_batch)");
   e = zrt_set_smem(k_huff, HUF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff)");
+  e = zrt_set_smem(k_huff_merge, HUF_SMEM);
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_huff_merge)");
   e = zrt_set_smem(k_inflate, INF_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inflate)");
   e = zrt_set_smem(k_inf_resolve, RES_SMEM);
@@ -297,6 +300,7 @@ extern "C" int zles_ctx_create(int device, zles_ctx **out) {
   e = zrt_stream_create(&c->out_stream);
   if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); delete c; return cuda_fail(e, "cudaStreamCreate"); }
   c->sm_count = zrt_sm_count(device);
+  { const char *e = getenv("ZLES_NO_MERGE"); if (e && *e && *e != '0') c->merge_chunks = false; }
   void *m = nullptr;
   e = zrt_host_alloc(&m, sizeof(HostMail));
   if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); zrt_stream_destroy(c->out_stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
@@ -626,6 +630,11 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
            c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);
+    if (c->merge_chunks) {  // one block per chunk where four headers cost more than they save (k_huff_merge)
+      const u32 nch = (b1 - b0 + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
+      LAUNCH(c, k_huff_merge, (nch + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1, nblocks,
+             is_last ? 1u : 0u, c->codes.as<BlockCodes>(), c->blk_bits.as<u32>());
+    }
     if (piped) {  // this slab's offsets, its bits, and where it ends (for the host, which copies it out below)
       LAUNCH(c, k_layout_slab, 1, 1024, LAYOUT_SMEM, (const u32 *)c->blk_bits.as<u32>(), b0, b1, nblocks, is_last ? 1u : 0u,
              c->summary.as<u64>() + 4, c->blk_off.as<u64>(), c->summary.as<u64>() + 5);

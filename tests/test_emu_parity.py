@@ -42,8 +42,11 @@ def test_adler(c):
                                     ("G5", 140000), ("G2", 200000)])
 def test_deflate_roundtrip(c, name, n):
     data = T.gen(name, n)
-    # size bound: only where one 32 KiB block's header is not the bulk of the output (see DESIGN.md "size")
-    P.roundtrip(c, data, check_size=name in ("RAW", "REPEAT", "G3", "G5") or n <= 4096)
+    P.roundtrip(c, data)
+
+
+def test_tiny_inputs_take_the_cheapest_block_type(c):
+    P.tiny_inputs_take_the_cheapest_block_type(c)
 
 
 def test_batch_of_small_buffers_shares_sorts(c):

@@ -60,9 +60,9 @@ def test_adler_kats_and_sizes(c):
 def test_deflate_model_table(c, row):
     name, n = row[0], row[1]
     data = T.gen(name, n)
-    # the 3 % size bound is checked where a 32 KiB block header is not the bulk of the output (DESIGN.md "Size")
-    degenerate = name in ("G1", "G2", "G4") and n > 4096
-    P.roundtrip(c, data, check_size=not degenerate)
+    # the 3 % size bound holds on every row: a chunk whose four blocks' headers cost more than they save is written as one
+    # block (k_huff_merge), tiny inputs with the fixed code (k_huff)
+    P.roundtrip(c, data)
 
 
 @pytest.mark.parametrize("n", [0, 1, 131073, 262145])
@@ -101,7 +101,7 @@ def test_long_matches_between_text(c):
         parts.append(T.gen("G5", int(rng.integers(1, 3000))))
         parts.append(bytes(int(rng.integers(1, 40000))) if rng.integers(0, 3) else b"ab" * int(rng.integers(1, 9000)))
     data = b"".join(parts)
-    P.roundtrip(c, data, check_size=False)
+    P.roundtrip(c, data)
     P.inflate_matches_oracle(c, zlib.compress(data, 6))
 
 
@@ -132,7 +132,11 @@ def test_window_modes(c):
 
 def test_long_matches_and_overlaps(c):
     for d in (bytes(300000), b"a" * 70000, b"ab" * 50000, b"abc" * 40000, T.repeat_input() * 40, bytes(range(256)) * 600):
-        P.roundtrip(c, d, check_size=False)
+        P.roundtrip(c, d)
+
+
+def test_tiny_inputs_take_the_cheapest_block_type(c):
+    P.tiny_inputs_take_the_cheapest_block_type(c)
 
 
 def test_incompressible(c):
@@ -152,7 +156,7 @@ def test_skewed_histograms_deep_trees(c):
     syms = np.repeat(np.arange(24, dtype=np.uint8) * 7 + 3, fib)
     for size in (32768, 100000):
         d = rng.permutation(np.resize(syms, size)).tobytes()
-        P.roundtrip(c, d, check_size=False)
+        P.roundtrip(c, d)
 
 
 def test_inflate_reference_streams(c):

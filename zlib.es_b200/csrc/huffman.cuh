@@ -21,6 +21,9 @@ constexpr int HUF_WARPS = 4;
 constexpr int HUF_THREADS = HUF_WARPS * 32;
 constexpr u32 HDR_BYTES = 576;  // >= ceil((14 + 19*3 + 316*14) / 8) = 562
 constexpr u32 HUF_STORED = 0xffffffffu;  // BlockCodes::hdr_nbits of a block that is smaller stored (BTYPE=0) than coded
+constexpr u32 HUF_FIXED = 0xfffffffeu;   // ... of a block that is smallest with the fixed code (BTYPE=1): no header, ll/d hold the fixed codes
+// code length of literal/length symbol s in the fixed code (RFC 1951 3.2.6; /root/reference/src/huffman.ts:41-53)
+__host__ __device__ __forceinline__ u32 fixed_ll_len(u32 s) { return s < 144 ? 8u : s < 256 ? 9u : s < 280 ? 7u : 8u; }
 // bytes a block of `bits` bits takes in the stream: padded to a byte when it ends the stream, else followed by the empty
 // stored block that makes the next block start on a byte (3 bits + pad, LEN, NLEN); bit 31 set: `bits` holds the bytes already
 __host__ __device__ __forceinline__ u32 seg_bytes_of(u32 bits, bool final_block) {
@@ -298,24 +301,42 @@ __global__ void __launch_bounds__(HUF_THREADS) k_huff(const u32 *__restrict__ hi
   for (u32 i = lane; i < 320; i += 32) S->freq[i] = hist[(size_t)b * 320 + i];
   u32 hbits, bits;
   huf_block(S, hbits, bits);
+  // The same symbols under the fixed code (BTYPE=1: no header at all).  The reference never writes it (src/deflate.ts:28);
+  // it wins on inputs of a few hundred bytes, where the dynamic header is most of the block.
+  u32 fbits = 0;
+  for (u32 i = lane; i < 320; i += 32) {
+    u32 e = 0, l = 5;
+    if (i < 288) l = fixed_ll_len(i);
+    if (i >= 257 && i < 286) e = c_len_extra[i - 257];
+    else if (i >= 288 && i < 318) e = c_dist_extra[i - 288];
+    fbits += S->freq[i] * (l + e);
+  }
+  fbits = __reduce_add_sync(ZLES_FULL, fbits);
+  const u32 own_len = table ? table[b].own_len : (u32)umin64((u64)SUB, n - (u64)b * SUB);
+  // The reference always emits BTYPE=2 (src/deflate.ts:28) and so expands incompressible data; a stored block
+  // (3 header bits + pad, LEN, NLEN, the bytes: RFC 1951 3.2.4) is taken when it is smaller.  Blocks start on a
+  // byte boundary, so a stored block costs exactly 5 + own_len bytes.
+  const u32 coded = 3 + hbits + bits, fixed = 3 + fbits, stored = 8 * (5 + own_len);
+  const u32 best = umin(coded, fixed);
+  const bool use_stored = stored < ((best + 7) & ~7u), use_fixed = !use_stored && fixed < coded;
   BlockCodes *C = codes + b;
-  for (u32 i = lane; i < 288; i += 32) C->ll[i] = S->code[i];
-  C->d[lane] = S->code[288 + lane];
-  for (u32 i = lane; i < HDR_BYTES / 4; i += 32) reinterpret_cast<u32 *>(C->hdr)[i] = S->hdr[i];
-  if (lane == 0) {
-    // The reference always emits BTYPE=2 (src/deflate.ts:28) and so expands incompressible data; a stored block
-    // (3 header bits + pad, LEN, NLEN, the bytes: RFC 1951 3.2.4) is taken when it is smaller.  Blocks start on a
-    // byte boundary, so a stored block costs exactly 5 + own_len bytes.
-    const u32 own_len = table ? table[b].own_len : (u32)umin64((u64)SUB, n - (u64)b * SUB);
-    const u32 coded = 3 + hbits + bits;
-    const u32 stored = 8 * (5 + own_len);
-    if (stored < ((coded + 7) & ~7u)) {
-      C->hdr_nbits = HUF_STORED;
-      blk_bits[b] = stored;
-    } else {
-      C->hdr_nbits = hbits;
-      blk_bits[b] = coded;
+  if (use_fixed) {
+    // canonical fixed codes, bit-reversed like huf_codes': 8-bit 0x30.. for 0-143, 9-bit 0x190.. for 144-255,
+    // 7-bit 0 .. for 256-279, 8-bit 0xC0.. for 280-287; distances are their own 5-bit numbers
+    for (u32 i = lane; i < 288; i += 32) {
+      const u32 l = fixed_ll_len(i);
+      const u32 code = i < 144 ? 0x30 + i : i < 256 ? 0x190 + (i - 144) : i < 280 ? i - 256 : 0xC0 + (i - 280);
+      C->ll[i] = ((__brev(code) >> (32 - l)) << 8) | l;
     }
+    C->d[lane] = ((__brev(lane) >> 27) << 8) | 5;
+  } else {
+    for (u32 i = lane; i < 288; i += 32) C->ll[i] = S->code[i];
+    C->d[lane] = S->code[288 + lane];
+    for (u32 i = lane; i < HDR_BYTES / 4; i += 32) reinterpret_cast<u32 *>(C->hdr)[i] = S->hdr[i];
+  }
+  if (lane == 0) {
+    C->hdr_nbits = use_stored ? HUF_STORED : use_fixed ? HUF_FIXED : hbits;
+    blk_bits[b] = use_stored ? stored : use_fixed ? fixed : coded;
   }
 }
 

@@ -57,6 +57,8 @@ constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 2324
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (at most)
 constexpr u32 LZ_BGROUP = 16;                               // batch mode: blocks per group (one sort when all are small)
 constexpr u32 LZ_BSLOT = (2 * SUB) / LZ_BGROUP;              // 4096: the most a block of a packed group holds
+constexpr u32 LZ_DENSE_SHIFT = 4;                            // blocks {0,1} of a chunk in fewer than 1/16 token per byte: blocks 2 and 3
+                                                            // are then matched one at a time, block 2 WITH its window (pair mode)
 constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
 // per-warp candidate ring: 64 entries of 4 bytes (lz_tag), stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
@@ -76,7 +78,9 @@ struct LzParams {
   u32 min_checks;     // reserved (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
   u32 good_len;       // reserved (reference: FAST_REPEAT_LENGTH = 8, src/lz77.ts:9)
   u32 lazy;           // 1: defer a match by one literal when the next position has a longer one
-  u32 *unit_ctr = nullptr;  // zeroed before the launch: units are handed out from it, the two-block ones first
+  u32 *unit_ctr = nullptr;  // zeroed before the launch: units are handed out from it, the two-block ones first;
+                            // stream mode: followed by one word per chunk of the launch (0 = blocks {0,1} not matched yet,
+                            // 1 = matched, 2 = matched and they are almost all matches: see LZ_DENSE_SHIFT)
   u32 pair_mode = 1;  // 1: two sorts per chunk — blocks {0,1} and {2,3}: block 2 has no window (the default);
                       // 0: three — {0,1}, then {2} and {3} each with the block before as window (smaller output, slower)
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
@@ -378,7 +382,30 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
       }
       packed = __syncthreads_and(small) != 0 && gcnt > 1;
     }
-    const u32 nrep = (TABLE && !packed) ? gcnt : 1u;
+    // stream mode: which chunk, which of its units.  Pair mode gives block 2 no window — on input that is all long matches
+    // (a period of 256 bytes costs 256 literals again, a third of such a chunk's output) that is not "within 3 %": the
+    // {2,3} unit waits for the chunk's {0,1} unit (handed out earlier, so it is finished or running on a resident CTA that
+    // waits for nothing) and, when that one came out in very few tokens, matches 2 and 3 one block at a time with windows.
+    u32 s_chunk = 0, s_k = 0;
+    bool split = false;
+    if (!TABLE) {
+      u32 v;  // chunk * upc + unit within the chunk
+      if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
+      else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
+      s_chunk = v / upc; s_k = v % upc;
+      if (P.pair_mode && s_k == 1 && s_chunk * SUBS_PER_CHUNK + 2 < P.nblocks) {
+        if (tid == 0) {
+          volatile u32 *flag = P.unit_ctr + 1 + (s_chunk - c_begin);
+          u32 f;
+          while ((f = *flag) == 0) __nanosleep(200);
+          *slice_ctr = f;
+        }
+        __syncthreads();
+        split = *slice_ctr == 2;
+        __syncthreads();
+      }
+    }
+    const u32 nrep = (TABLE && !packed) ? gcnt : split ? 2u : 1u;
     for (u32 rep = 0; rep < nrep; rep++) {
     u64 own_off = 0;
     u32 own_len, hist_len, bfirst;
@@ -390,12 +417,10 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
         own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len; bfirst = gfirst + rep;
       }
     } else {
-      u32 v;  // chunk * upc + unit within the chunk
-      if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
-      else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
-      const u32 chunk = v / upc, k = v % upc;
+      const u32 chunk = s_chunk, k = s_k;
       u32 sb0, nsb;
       if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
+      else if (split) { sb0 = 2 + rep; nsb = 1; hist_len = SUB; }
       else if (P.pair_mode) { sb0 = 2; nsb = 2; hist_len = 0; }
       else { sb0 = k + 1; nsb = 1; hist_len = SUB; }  // window = previous SUB of the same chunk
       bfirst = chunk * SUBS_PER_CHUNK + sb0;
@@ -840,6 +865,12 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
     __syncthreads();
     }  // blocks of the unit
     __syncthreads();
+    if (!TABLE && P.pair_mode && s_k == 0 && tid == 0) {  // the chunk's {2,3} unit may go ahead (P.ntok: thread 0's own stores)
+      u32 nt = 0;
+      for (u32 sbi = 0; sbi < nsub; sbi++) nt += P.ntok[bfirst + sbi];
+      __threadfence();
+      atomicExch(P.unit_ctr + 1 + (s_chunk - c_begin), (nt << LZ_DENSE_SHIFT) < unit_own ? 2u : 1u);
+    }
     LZ_CLK(scratch, 11);
     }  // blocks of an unpacked group
   }

@@ -247,7 +247,8 @@ __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *
       __syncthreads();
     }
     // block header: BFINAL, BTYPE=2 (src/deflate.ts:21-28), then the code-length header in 32-bit pieces
-    const u32 hbits = C->hdr_nbits;
+    const bool fixed = C->hdr_nbits == HUF_FIXED;  // BTYPE=1: the three bits are the whole header (k_huff)
+    const u32 hbits = fixed ? 0u : C->hdr_nbits;
     const u32 hwords = (merged && b != b0) ? 0xffffffffu : (hbits + 31) >> 5;  // (no header inside a merged chunk)
     const u32 bfinal = (final_chunk && (merged || b + 1 == b1)) ? 1u : 0u;
     for (u32 base = 0; hwords != 0xffffffffu && base < hwords + 1; base += PACK_TILE) {
@@ -255,7 +256,7 @@ __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *
       for (int k = 0; k < PACK_ITEMS; k++) {
         const u32 i = base + tid * PACK_ITEMS + k;
         bits[k] = 0; nb[k] = 0;
-        if (i == 0) { bits[k] = bfinal | (2u << 1); nb[k] = 3; }
+        if (i == 0) { bits[k] = bfinal | ((fixed ? 1u : 2u) << 1); nb[k] = 3; }
         else if (i <= hwords) {
           bits[k] = reinterpret_cast<const u32 *>(C->hdr)[i - 1];
           nb[k] = umin(32u, hbits - (i - 1) * 32);

@@ -560,7 +560,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
   lp.pair_mode = c->pair_mode;
-  RET(c->unit_ctr.reserve(4));
+  RET(c->unit_ctr.reserve(4 + 4 * (((size_t)nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK)));  // the counter, then a flag per chunk
   lp.unit_ctr = c->unit_ctr.as<u32>();
   // Host input arrives slab by slab: one wave of CTAs first (the matcher starts as soon as 4.6 MiB are on the device),
   // then 2, then 4 waves per slab (a multiple of the SM count keeps the tail of every launch short); whole chunks.
@@ -626,7 +626,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     }
     lp.first_block = b0;
     lp.nblocks = b1;
-    CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
+    CK(zrt_memset(lp.unit_ctr, 0, 4 + 4 * (size_t)((b1 - b0 + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK), c->stream));
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
            c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);

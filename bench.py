@@ -415,6 +415,8 @@ def run_ours(args):
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
     launches = c.launches - launches0
+    free_b, total_b = torch.cuda.mem_get_info(local)  # the codec's workspaces only grow: what is in use now is the step's peak
+    dev_mem_gib = round((total_b - free_b) / (1 << 30), 2)
     with torch.cuda.stream(stream):
         assert torch.equal(src, back), "round trip mismatch after the timed steps"
     kt = {k: c.kernel_time(k) for k in ("k_lz", "k_huff", "k_pack", "k_inf_tokens", "k_inf_tokens4", "k_inf_resolve", "k_piece_sym", "k_chunk_final",
@@ -507,7 +509,7 @@ def run_ours(args):
         dist.barrier(group=host_group)  # the other ranks wait on the host: their GPUs belong to rank 0's multi-GPU context meanwhile
 
     # ---- max over ranks --------------------------------------------------------------------------
-    vals = torch.tensor([td / args.steps, ti / args.steps, float(launches), lz_ms / max(1, lz_n), tok_ms / max(1, args.steps), res_ms / max(1, args.steps)],
+    vals = torch.tensor([td / args.steps, ti / args.steps, float(launches), lz_ms / max(1, args.steps), tok_ms / max(1, args.steps), res_ms / max(1, args.steps), lz_n / max(1, args.steps)],
                         dtype=torch.float64, device=dev)
     if multi:
         mx = vals.clone()
@@ -518,7 +520,9 @@ def run_ours(args):
         mx, sm = vals, vals
     d_ms, i_ms = float(mx[0]), float(mx[1])
     launches_total = int(float(sm[2]))
-    lz_avg_ms = float(mx[3])
+    lz_step_ms = float(mx[3])                    # k_lz per step on the slowest rank: all its launches (one per slab of the shard)
+    lz_launches = max(1, round(float(mx[6])))
+    lz_avg_ms = lz_step_ms / lz_launches
 
     cpu = None
     if rank == 0 and not multi and not args.no_cpu:
@@ -534,9 +538,10 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         shard = TOTAL / world
-        algo = shard + (clen - 6) / world  # deflate = U read + C written, per launch of the matcher over one shard
+        algo_shard = shard + (clen - 6) / world  # deflate = U read + C written by the matcher's pass over one shard
+        algo = algo_shard / lz_launches         # ... per launch: a long resident shard is matched in slabs of 1 GiB, one launch each
         achieved = algo / (lz_avg_ms * 1e-3) / 1e9 if lz_avg_ms > 0 else 0.0
-        tr = ncu_traffic("k_lz", shard)
+        tr = ncu_traffic("k_lz", shard / lz_launches)
         inf_ms = (float(mx[4]) + float(mx[5]))
         line = {
             "metric": METRIC, "value": round(TOTAL / ((d_ms + i_ms) * 1e-3) / 1e9, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -548,13 +553,17 @@ def run_ours(args):
             "ratio": round(TOTAL / clen, 4), "compressed_bytes": int(clen), "wall_s_timed_region": round(wall, 3),
             "e2e": e2e, "e2e_pageable": pageable,
             "gpu_launches": launches_total,
+            "device_mem_gib": {"rank0_in_use_after_the_timed_steps": dev_mem_gib,
+                               "of_which_bench_tensors": round((2 * n + cap + (cap if multi else 0)) / (1 << 30), 2),
+                               "note": "the rest is the codec's workspace (token slots: 4 B per input byte of one 1 GiB slab when one GPU "
+                                       "deflates a long resident input; of the whole shard in the two-phase sharded form)"},
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in kt.items() if v[1]},
             "roofline": {"bound": "hbm", "kernel": "k_lz", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": tr["traffic"] if tr else None, "traffic_source": tr, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(algo), "launch_ms": round(lz_avg_ms, 4)},
+                         "algorithmic_bytes_per_launch": int(algo), "launch_ms": round(lz_avg_ms, 4), "launches_per_step": lz_launches},
             "roofline_inflate": {"bound": "hbm", "kernels": "phase A (k_inf_tokens | k_inf_tokens4) + phase B (k_inf_resolve | k_piece_sym + k_chunk_final)",
-                                 "achieved": round(algo / (inf_ms * 1e-3) / 1e9, 2) if inf_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
-                                 "frac": round(algo / (inf_ms * 1e-3) / 1e9 / peak, 5) if inf_ms > 0 else 0.0, "algorithmic_bytes_per_launch": int(algo)},
+                                 "achieved": round(algo_shard / (inf_ms * 1e-3) / 1e9, 2) if inf_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
+                                 "frac": round(algo_shard / (inf_ms * 1e-3) / 1e9 / peak, 5) if inf_ms > 0 else 0.0, "algorithmic_bytes_per_launch": int(algo_shard)},
             "clocks": clocks,
         }
         if cpu:

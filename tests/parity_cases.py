@@ -65,6 +65,27 @@ def tiny_inputs_take_the_cheapest_block_type(c):
     assert seen == {0, 1, 2}, seen  # all three block types were chosen somewhere
 
 
+def batch_token_rows(c):
+    """A batch's token scratch has one row per block, as long as the batch's longest block (not 32 Ki slots: 262,144
+    buffers of 4 KiB would take 32 GiB): batches whose longest buffer is 1, 17, 1,003 and 5,000 bytes, and one with a
+    buffer of several blocks, give every buffer the bytes it gets on its own."""
+    import numpy as np
+    rng = np.random.default_rng(21)
+    src = T.fixture_raw() + T.gen("G5", 100000)
+    for longest, count in ((1, 5), (17, 40), (1003, 70), (5000, 40), (70000, 6)):
+        lens = [longest] + [int(x) for x in rng.integers(0, longest + 1, size=count - 1)]
+        bufs = []
+        for n in lens:
+            o = int(rng.integers(0, len(src) - n))
+            bufs.append(src[o:o + n])
+        zs = c.deflate_batch(bufs)
+        for b, z in zip(bufs, zs):
+            assert zlib.decompress(z) == b
+        for i in (0, 1, count // 2, count - 1):
+            assert zs[i] == c.deflate(bufs[i]), (longest, i)
+        assert c.inflate_batch(zs) == bufs
+
+
 def inflate_matches_oracle(c, stream: bytes):
     """Same bytes or the same error as the reference's inflate."""
     try:

@@ -45,6 +45,10 @@ def test_deflate_roundtrip(c, name, n):
     P.roundtrip(c, data)
 
 
+def test_batch_token_rows_follow_the_longest_block(c):
+    P.batch_token_rows(c)
+
+
 def test_tiny_inputs_take_the_cheapest_block_type(c):
     P.tiny_inputs_take_the_cheapest_block_type(c)
 

@@ -123,3 +123,25 @@ def test_config3_batch_of_4KiB_buffers(c):
 
 def test_config4_1GiB_mixed_stream(c):
     _device_round_trip(c, KINDS["mixed"], 1 << 30)
+
+
+def test_long_device_input_is_deflated_in_slabs(c):
+    # zles_dev_deflate cuts an input of 2 GiB or more into slabs of 1 GiB that are matched and packed one after the other
+    # (the token scratch is then a slab's, 4 GiB, not 4 bytes per byte of the whole input): same stream, byte for byte,
+    # as without slabs (ZLES_NO_DEV_SLABS), and as with a buffer too small for the worst case (two-phase path)
+    import os
+    import torch
+    import zles
+    n = (2 << 30) + (3 << 20) + 12345
+    src, comp, clen = _device_round_trip(c, KINDS["mixed"], n)
+    os.environ["ZLES_NO_DEV_SLABS"] = "1"
+    try:
+        c2 = zles.Codec(0)
+    finally:
+        del os.environ["ZLES_NO_DEV_SLABS"]
+    comp2 = torch.empty(clen, dtype=torch.uint8, device="cuda")  # exactly the size needed: below the bound
+    assert c2.dev_deflate(src.data_ptr(), n, comp2.data_ptr(), clen) == clen
+    assert torch.equal(comp[:clen], comp2)
+    comp2.zero_()
+    assert c.dev_deflate(src.data_ptr(), n, comp2.data_ptr(), clen) == clen  # the slabbed codec, no room for the bound
+    assert torch.equal(comp[:clen], comp2)

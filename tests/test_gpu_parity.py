@@ -235,6 +235,10 @@ def test_batch(c):
     assert res[0] == bufs[0] and str(res[1]) == "Not compressed by deflate" and str(res[2]) == "Not supported BTYPE : 3"
 
 
+def test_batch_token_rows_follow_the_longest_block(c):
+    P.batch_token_rows(c)
+
+
 def test_sharded_phases_match_single_call(c):
     import torch
     import zles

@@ -84,6 +84,8 @@ struct LzParams {
   u32 pair_mode = 1;  // 1: two sorts per chunk — blocks {0,1} and {2,3}: block 2 has no window (the default);
                       // 0: three — {0,1}, then {2} and {3} each with the block before as window (smaller output, slower)
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
+  u32 tok_stride = SUB;  // token slots per block: SUB, or less when no block of a batch is that long (a batch of 262,144
+                         // buffers of 4 KiB then takes 4 GiB of token scratch instead of 32)
 };
 
 // Per-stage cycle counters (tools/lz_stages.py builds with -DZLES_STAGE_CLOCKS; off in the product build):
@@ -348,6 +350,7 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
   if (tid == 0) mbar_init(mbar, 1);
   __syncthreads();
 #endif
+  if (tid == 0) seg_len[0] = seg_len[1] = 0;  // stream mode: [0] the flag this unit sets when done, [1] a pending single-block unit, [2] the flag read
   u32 *Y = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // sort pass buffer, 2 * SUB entries
   u32 *R = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // then the match results, SUB entries
 
@@ -359,12 +362,17 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
   const u32 c_begin = P.first_block / SUBS_PER_CHUNK, c_end = (P.nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
   const u32 nunits = TABLE ? (P.nblocks - P.first_block + LZ_BGROUP - 1) / LZ_BGROUP : (c_end - c_begin) * upc;
   for (;;) {
-    // units come from a counter (their cost differs: two blocks or one); all two-block units are handed out first
+    // units come from a counter (their cost differs: two blocks or one); all two-block units are handed out first.
+    // Bit 31 set: not a unit of the counter but block (ui & 0x7fffffff) on its own, with the block before it as window — the
+    // second half of a {2,3} unit that this CTA split (see below), waiting in seg_len[1].
     __syncthreads();
-    if (tid == 0) *slice_ctr = atomicAdd(P.unit_ctr, 1u);
+    if (tid == 0) {
+      if (!TABLE && seg_len[1]) { *slice_ctr = seg_len[1]; seg_len[1] = 0; }
+      else *slice_ctr = atomicAdd(P.unit_ctr, 1u);
+    }
     __syncthreads();
     const u32 ui = *slice_ctr;
-    if (ui >= nunits) break;
+    if (!(ui & 0x80000000u) && ui >= nunits) break;
     // batch mode: is the group one packed unit, or `gcnt` units of one block each?
     u32 gfirst = 0, gcnt = 1;
     bool packed = false;
@@ -382,30 +390,7 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
       }
       packed = __syncthreads_and(small) != 0 && gcnt > 1;
     }
-    // stream mode: which chunk, which of its units.  Pair mode gives block 2 no window — on input that is all long matches
-    // (a period of 256 bytes costs 256 literals again, a third of such a chunk's output) that is not "within 3 %": the
-    // {2,3} unit waits for the chunk's {0,1} unit (handed out earlier, so it is finished or running on a resident CTA that
-    // waits for nothing) and, when that one came out in very few tokens, matches 2 and 3 one block at a time with windows.
-    u32 s_chunk = 0, s_k = 0;
-    bool split = false;
-    if (!TABLE) {
-      u32 v;  // chunk * upc + unit within the chunk
-      if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
-      else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
-      s_chunk = v / upc; s_k = v % upc;
-      if (P.pair_mode && s_k == 1 && s_chunk * SUBS_PER_CHUNK + 2 < P.nblocks) {
-        if (tid == 0) {
-          volatile u32 *flag = P.unit_ctr + 1 + (s_chunk - c_begin);
-          u32 f;
-          while ((f = *flag) == 0) __nanosleep(200);
-          *slice_ctr = f;
-        }
-        __syncthreads();
-        split = *slice_ctr == 2;
-        __syncthreads();
-      }
-    }
-    const u32 nrep = (TABLE && !packed) ? gcnt : split ? 2u : 1u;
+    const u32 nrep = (TABLE && !packed) ? gcnt : 1u;
     for (u32 rep = 0; rep < nrep; rep++) {
     u64 own_off = 0;
     u32 own_len, hist_len, bfirst;
@@ -417,11 +402,33 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
         own_off = t.in_off; own_len = t.own_len; hist_len = t.hist_len; bfirst = gfirst + rep;
       }
     } else {
-      const u32 chunk = s_chunk, k = s_k;
+      u32 v;  // chunk * upc + unit within the chunk
+      if (ui & 0x80000000u) v = ((ui & 0x7fffffffu) / SUBS_PER_CHUNK) * upc + 1;
+      else if (ui < c_end - c_begin) v = (c_begin + ui) * upc;
+      else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
+      const u32 chunk = v / upc, k = v % upc;
       u32 sb0, nsb;
-      if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
-      else if (split) { sb0 = 2 + rep; nsb = 1; hist_len = SUB; }
-      else if (P.pair_mode) { sb0 = 2; nsb = 2; hist_len = 0; }
+      if (tid == 0) seg_len[0] = (P.pair_mode && k == 0) ? 1u + (chunk - c_begin) : 0u;  // the flag this unit sets when it is done
+      if (ui & 0x80000000u) { sb0 = (ui & 0x7fffffffu) % SUBS_PER_CHUNK; nsb = 1; hist_len = SUB; }
+      else if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
+      else if (P.pair_mode) {
+        // Pair mode gives block 2 no window — on input that is all long matches (a period of 256 bytes costs 256 literals
+        // again, a third of such a chunk's output) that is not "within 3 %".  The {2,3} unit therefore waits for the chunk's
+        // {0,1} unit (handed out earlier, so it is finished or running on a resident CTA that waits for nothing) and, when
+        // that one came out in very few tokens, matches block 2 now and block 3 next, each with the block before as window.
+        sb0 = 2; nsb = 2; hist_len = 0;
+        if (chunk * SUBS_PER_CHUNK + 2 < P.nblocks) {
+          if (tid == 0) {
+            volatile u32 *flag = P.unit_ctr + 1 + (chunk - c_begin);
+            u32 f;
+            while ((f = *flag) == 0) __nanosleep(200);
+            seg_len[2] = f;  // (not through *slice_ctr: other warps may not have read this unit's index from it yet)
+            if (f == 2 && chunk * SUBS_PER_CHUNK + 3 < P.nblocks) seg_len[1] = 0x80000000u | (chunk * SUBS_PER_CHUNK + 3);
+          }
+          __syncthreads();
+          if (seg_len[2] == 2) { nsb = 1; hist_len = SUB; }  // (rewritten a unit later at the earliest: many barriers from here)
+        }
+      }
       else { sb0 = k + 1; nsb = 1; hist_len = SUB; }  // window = previous SUB of the same chunk
       bfirst = chunk * SUBS_PER_CHUNK + sb0;
       if (bfirst >= P.nblocks) continue;  // the stream's last chunk is short (uniform over the CTA)
@@ -729,7 +736,7 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
           const u32 bcur = bfirst + h * SPH + sl;
           const u32 send2 = sl * LZ_BSLOT + (sl < nsl ? seg_len[h * SPH + sl] : 0u);
           u32 o = oex - pref[tid & ~127u];
-          u32 *tok = P.tokens + (size_t)bcur * SUB;
+          u32 *tok = P.tokens + (size_t)bcur * P.tok_stride;
           u32 *hc = hcopies + sl * LZ_NSYM;
           while (word) {
             const u32 bit = (u32)(__ffs((int)word) - 1);
@@ -832,7 +839,7 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
       u32 word = bm[tid];
       u32 total;
       u32 o = block_exscan((u32)__popc(word), scratch, &total);
-      u32 *tok = P.tokens + (size_t)bcur * SUB;
+      u32 *tok = P.tokens + (size_t)bcur * P.tok_stride;
       u32 *hc = hcopies + (w % LZ_HCOPIES) * LZ_NSYM;
       while (word) {
         const u32 bit = (u32)(__ffs((int)word) - 1);
@@ -865,11 +872,12 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
     __syncthreads();
     }  // blocks of the unit
     __syncthreads();
-    if (!TABLE && P.pair_mode && s_k == 0 && tid == 0) {  // the chunk's {2,3} unit may go ahead (P.ntok: thread 0's own stores)
+    if (!TABLE && tid == 0 && seg_len[0]) {  // the chunk's {2,3} unit may go ahead (P.ntok: thread 0's own stores)
       u32 nt = 0;
       for (u32 sbi = 0; sbi < nsub; sbi++) nt += P.ntok[bfirst + sbi];
       __threadfence();
-      atomicExch(P.unit_ctr + 1 + (s_chunk - c_begin), (nt << LZ_DENSE_SHIFT) < unit_own ? 2u : 1u);
+      atomicExch(P.unit_ctr + seg_len[0], (nt << LZ_DENSE_SHIFT) < unit_own ? 2u : 1u);
+
     }
     LZ_CLK(scratch, 11);
     }  // blocks of an unpacked group

@@ -212,7 +212,8 @@ __device__ __forceinline__ void pack_finish(PackState &st) {
 // merged: the blocks are written as ONE block — the header and code of block b0, the tokens of all, one end-of-block code
 // (k_huff_merge).
 __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *tokens, const u32 *ntok, const BlockCodes *codes,
-                                           u32 b0, u32 b1, bool final_chunk, const u8 *raw, u32 raw_len, bool merged = false) {
+                                           u32 b0, u32 b1, bool final_chunk, const u8 *raw, u32 raw_len, bool merged = false,
+                                           u32 tok_stride = SUB) {
   const u32 tid = threadIdx.x;
   u64 bits[PACK_ITEMS];
   u32 nb[PACK_ITEMS];
@@ -266,7 +267,7 @@ __device__ __forceinline__ void pack_chunk(PackState &st, u32 *ctab, const u32 *
     }
     // tokens, src/deflate.ts:183-220
     const u32 nt = ntok[b];
-    const u32 *tok = tokens + (size_t)b * SUB;
+    const u32 *tok = tokens + (size_t)b * tok_stride;
     for (u32 base = 0; base < nt; base += PACK_TILE) {
 #pragma unroll
       for (int k = 0; k < PACK_ITEMS; k++) {
@@ -341,11 +342,13 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack(const PackParams P) {
 // ---- batches of independent buffers: every buffer is a complete zlib stream ---------------
 // (header 78 9C, its chunks, Adler-32 trailer: /root/reference/src/zlib.ts:25-49 per buffer)
 
-// blk_first[i] = index of buffer i's first deflate block; blk_first[count] = total.  Single CTA.
+// blk_first[i] = index of buffer i's first deflate block; blk_first[count] = total; blk_first[count + 1] = the longest
+// block of the batch in bytes (= the token slots a block can need).  Single CTA.
 __global__ void __launch_bounds__(1024) k_batch_count(const u64 *__restrict__ in_off, u32 count, u64 *blk_first) {
   ZLES_SMEM_DECL(smem_raw);
   u32 *scratch = reinterpret_cast<u32 *>(smem_raw);
   u64 carry = 0;
+  u32 longest = 0;
   for (u32 base = 0; base < count; base += 1024) {
     const u32 i = base + threadIdx.x;
     u32 nb = 0;
@@ -353,13 +356,19 @@ __global__ void __launch_bounds__(1024) k_batch_count(const u64 *__restrict__ in
       const u64 len = in_off[i + 1] - in_off[i];
       nb = (u32)((len + SUB - 1) / SUB);
       if (nb == 0) nb = 1;
+      longest = umax(longest, (u32)umin64(len, (u64)SUB));
     }
     u32 total;
     const u32 ex = block_exscan(nb, scratch, &total);
     if (i < count) blk_first[i] = carry + ex;
     carry += total;
   }
-  if (threadIdx.x == 0) blk_first[count] = carry;
+  __syncthreads();
+  if (threadIdx.x == 0) { blk_first[count] = carry; scratch[0] = 0; }
+  __syncthreads();
+  atomicMax(scratch, longest);
+  __syncthreads();
+  if (threadIdx.x == 0) blk_first[count + 1] = scratch[0];
 }
 
 // pair_mode: the window policy of LzParams (1: a chunk's third block has no window), so that a buffer of a batch
@@ -431,6 +440,7 @@ struct BatchPackParams {
   u64 *out_len;            // [count]
   int32_t *status;         // [count]
   u32 *first_err;          // lowest non-zero status of the batch (0 if none)
+  u32 tok_stride = SUB;    // token slots per block (LzParams::tok_stride)
 };
 
 // one CTA per buffer
@@ -485,7 +495,7 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_batch(const BatchPackPara
   if (tid == 0) { bits[0] = 0x9C78u; nb[0] = 16; }  // CMF = 78, FLG = 9C (src/zlib.ts:28-34)
   pack_emit(st, bits, nb);
   for (u32 b = b0; b < b1; b++)
-    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, b + 1 == b1, P.in + P.table[b].in_off, P.table[b].own_len);
+    pack_chunk(st, ctab, P.tokens, P.ntok, P.codes, b, b + 1, b + 1 == b1, P.in + P.table[b].in_off, P.table[b].own_len, false, P.tok_stride);
   nb[0] = 0;
   if (tid == 0) {  // big-endian Adler-32 (src/zlib.ts:36-40)
     bits[0] = ((adler >> 24) & 0xff) | ((adler >> 8) & 0xff00) | ((adler << 8) & 0xff0000) | (adler << 24);

@@ -117,6 +117,7 @@ struct zles_ctx {
   // encoder search depth (see zles_ctx_set_level)
   u32 max_checks = 32, min_checks = 1, good_len = 8, lazy = 1;
   u32 pair_mode = 1;  // zles_ctx_set_window_mode
+  bool no_dev_slabs = false;  // ZLES_NO_DEV_SLABS=1: zles_dev_deflate never cuts a long input into slabs (a measuring aid)
   bool merge_chunks = true;  // k_huff_merge (ZLES_NO_MERGE=1 in the environment turns it off: a debugging aid)
   size_t inf_stream_min = (size_t)96 << 20;  // host-buffer inflate: streams at least this long are copied in pieces, scanned and decoded as they land
   u32 inf_slab_blocks = 0;  // host-buffer inflate of our own streams: blocks per slab (inflate_slabs_to_host); 0 = automatic
@@ -301,6 +302,7 @@ extern "C" int zles_ctx_create(int device, zles_ctx **out) {
   if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); delete c; return cuda_fail(e, "cudaStreamCreate"); }
   c->sm_count = zrt_sm_count(device);
   { const char *e = getenv("ZLES_NO_MERGE"); if (e && *e && *e != '0') c->merge_chunks = false; }
+  { const char *e = getenv("ZLES_NO_DEV_SLABS"); if (e && *e && *e != '0') c->no_dev_slabs = true; }
   void *m = nullptr;
   e = zrt_host_alloc(&m, sizeof(HostMail));
   if (e != ZRT_OK) { zrt_stream_destroy(c->stream); zrt_stream_destroy(c->copy_stream); zrt_stream_destroy(c->out_stream); delete c; return cuda_fail(e, "cudaMallocHost"); }
@@ -512,8 +514,16 @@ struct DeflatePipe {
   Drainer *drain = nullptr;  // the caller's buffer is pageable: copies to it go through the pinned staging ring
   bool defer = false;  // pack slab by slab into d_out but leave the copy to the host to the caller (multi-GPU: a shard's
                        // place in the stream is only known once every shard before it has been laid out)
+  bool dev = false;    // the input is already on the device and d_out is where the stream goes (zles_dev_deflate on a long
+                       // input): slabs of DEV_SLAB_BLOCKS blocks, so that the token scratch is a slab's and not the input's
   bool done = false, overflow = false;
 };
+
+#ifdef ZLES_EMU
+constexpr u32 DEV_SLAB_BLOCKS = 8;      // (the emulator tests run the slab logic on small inputs)
+#else
+constexpr u32 DEV_SLAB_BLOCKS = 32768;  // 1 GiB of input per slab of a device-resident deflate (4 GiB of token slots)
+#endif
 
 static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zles_shard_info *info, const u8 *h_src = nullptr,
                           DeflatePipe *pipe = nullptr) {
@@ -536,7 +546,6 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   const u32 nchunks = (nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK;
   const u32 grid_lz = (u32)umin64((u64)nblocks, (u64)c->sm_count);
 
-  RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
   RET(c->ntok.reserve((size_t)nblocks * 4));
   RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
   RET(c->scratch.reserve((size_t)grid_lz * 2 * SUB * 4));
@@ -550,7 +559,6 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.in = d_in;
   lp.n = n;
   lp.nblocks = nblocks;
-  lp.tokens = c->tokens.as<u32>();
   lp.ntok = c->ntok.as<u32>();
   lp.hist = c->hist.as<u32>();
   lp.scratch = c->scratch.as<u32>();
@@ -567,7 +575,11 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   std::vector<u32> slab_begin;  // first block of every slab, and nblocks at the end
   {
     const u32 wave = ((u32)c->sm_count / SUBS_PER_CHUNK) * SUBS_PER_CHUNK;
-    if (!h_src || wave == 0 || nblocks < 4 * wave) {
+    if (!h_src && pipe && pipe->dev && nblocks >= 2 * DEV_SLAB_BLOCKS) {
+      for (u32 b = 0; b < nblocks; b += DEV_SLAB_BLOCKS) slab_begin.push_back(b);
+      if (nblocks - slab_begin.back() < DEV_SLAB_BLOCKS / 2) slab_begin.pop_back();
+      slab_begin.push_back(nblocks);
+    } else if (!h_src || wave == 0 || nblocks < 4 * wave) {
       slab_begin = {0, nblocks};
     } else {
       // slabs double from one wave up to an eighth of the input (at least 4, at most 64 waves): a long input gets slabs
@@ -586,7 +598,17 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     }
   }
   const u32 nslabs = (u32)slab_begin.size() - 1;
-  const bool piped = pipe && h_src && nslabs > 1;
+  const bool piped = pipe && (h_src || pipe->dev) && nslabs > 1;
+  // Token slots: 4 bytes per input byte of whatever is between the matcher and the packer at one time — the whole input
+  // when the packer runs afterwards (sharded form: a shard's place in the stream is known only after the exchange), ONE
+  // SLAB when every slab is packed before the next is matched (same stream: k_pack of slab s precedes k_lz of slab s + 1).
+  // Block b's row is then at (b - slab's first block): the kernels index by absolute block, so they get a shifted base.
+  u32 tok_blocks = nblocks;
+  if (piped) {
+    tok_blocks = 0;
+    for (u32 si = 0; si < nslabs; si++) tok_blocks = std::max(tok_blocks, slab_begin[si + 1] - slab_begin[si]);
+  }
+  RET(c->tokens.reserve((size_t)tok_blocks * SUB * 4));
   // a large pageable source is staged through pinned memory by helper threads (stager.inl), slab by slab
   Feeder feeder;
   bool staged = false;
@@ -626,6 +648,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     }
     lp.first_block = b0;
     lp.nblocks = b1;
+    lp.tokens = c->tokens.as<u32>() - (piped ? (size_t)b0 * SUB : 0);
     CK(zrt_memset(lp.unit_ctr, 0, 4 + 4 * (size_t)((b1 - b0 + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK), c->stream));
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
@@ -639,7 +662,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
       LAUNCH(c, k_layout_slab, 1, 1024, LAYOUT_SMEM, (const u32 *)c->blk_bits.as<u32>(), b0, b1, nblocks, is_last ? 1u : 0u,
              c->summary.as<u64>() + 4, c->blk_off.as<u64>(), c->summary.as<u64>() + 5);
       PackParams pp;
-      pp.tokens = c->tokens.as<u32>();
+      pp.tokens = c->tokens.as<u32>() - (size_t)b0 * SUB;
       pp.ntok = c->ntok.as<u32>();
       pp.codes = c->codes.as<BlockCodes>();
       pp.blk_bits = c->blk_bits.as<u32>();
@@ -696,7 +719,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
 
   CK(zrt_mail(c->mail->summary, c->summary.p, 24, c->stream));
   CK(zrt_sync(c->stream));
-  c->p1_valid = true;
+  c->p1_valid = !piped;  // (slab by slab: the stream has been written, the tokens are gone — there is no phase 2)
   c->p1_in = d_in;
   c->p1_n = n;
   c->p1_nblocks = nblocks;
@@ -782,11 +805,15 @@ extern "C" int zles_dev_deflate(zles_ctx *c, const uint8_t *d_in, size_t n, uint
   if ((!d_in && n) || !out_len) return ZLES_E_ARG;
   RET(resolve_ctx(c));
   zles_shard_info info;
-  RET(deflate_phase1(c, d_in, n, 1, &info));
+  DeflatePipe pipe;  // a long input with room for the worst case: packed slab by slab straight into d_out
+  pipe.dev = pipe.defer = true;
+  pipe.d_out = d_out + 2;
+  const bool slabs = d_out && cap >= zles_deflate_bound(n) && !c->no_dev_slabs;
+  RET(deflate_phase1(c, d_in, n, 1, &info, nullptr, slabs ? &pipe : nullptr));
   const size_t need = (size_t)info.comp_bytes + 6;
   *out_len = need;
   if (!d_out || cap < need) return ZLES_E_OUTPUT_FULL;
-  RET(deflate_phase2(c, d_out + 2));
+  if (!pipe.done) RET(deflate_phase2(c, d_out + 2));
   put_zlib_header(c->mail->head);
   put_be32(c->mail->head + 2, zles_adler32_combine_shards(&info, 1));
   CK(zrt_h2d(d_out, c->mail->head, 2, c->stream));
@@ -1990,19 +2017,21 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   InfCtl *ctl = c->ctl.as<InfCtl>();
   CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
   // per-buffer block counts -> block table
-  RET(c->seg_pos.reserve(((size_t)count + 1) * 8));
-  u64 *d_blk_first = c->seg_pos.as<u64>();  // [count + 1] first block index of each buffer
+  RET(c->seg_pos.reserve(((size_t)count + 2) * 8));
+  u64 *d_blk_first = c->seg_pos.as<u64>();  // [count + 1] first block index of each buffer, then the longest block's bytes
   LAUNCH(c, k_batch_count, 1, 1024, 64 * 4, d_in_off, count, d_blk_first);
   CK(zrt_last_error());
-  CK(zrt_mail(&c->mail->total, d_blk_first + count, 8, c->stream));
+  CK(zrt_mail(c->mail->summary, d_blk_first + count, 16, c->stream));
   CK(zrt_sync(c->stream));
-  const u64 nb64 = c->mail->total;
+  const u64 nb64 = c->mail->summary[0];
+  // token slots per block: a block of b bytes has at most b tokens (16-slot granularity keeps rows 64-byte aligned)
+  const u32 tok_stride = (u32)std::max<u64>(16, (umin64(c->mail->summary[1], (u64)SUB) + 15) & ~15ull);
   if (nb64 > 0x7fffffffull / LZ_NSYM) return ZLES_E_ARG;
   const u32 nblocks = (u32)nb64;
   const u32 grid_lz = (u32)umin64((u64)nblocks, (u64)c->sm_count);
   RET(c->seg_off.reserve((size_t)nblocks * sizeof(BatchBlk)));
   BatchBlk *d_tab = c->seg_off.as<BatchBlk>();
-  RET(c->tokens.reserve((size_t)nblocks * SUB * 4));
+  RET(c->tokens.reserve((size_t)nblocks * tok_stride * 4));
   RET(c->ntok.reserve((size_t)nblocks * 4));
   RET(c->hist.reserve((size_t)nblocks * LZ_NSYM * 4));
   RET(c->scratch.reserve((size_t)grid_lz * 2 * SUB * 4));
@@ -2026,6 +2055,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
   lp.table = d_tab;
+  lp.tok_stride = tok_stride;
   RET(c->unit_ctr.reserve(4));
   lp.unit_ctr = c->unit_ctr.as<u32>();
   CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
@@ -2048,6 +2078,7 @@ static int dev_deflate_batch(zles_ctx *c, const u8 *d_in, const u64 *d_in_off, c
   bp.out_len = d_out_len;
   bp.status = d_status;
   bp.first_err = &ctl->ok;
+  bp.tok_stride = tok_stride;
   LAUNCH(c, k_pack_batch, count, PACK_THREADS, PACK_SMEM, bp);
   CK(zrt_last_error());
   CK(zrt_mail(&c->mail->ok, &ctl->ok, 4, c->stream));

@@ -543,22 +543,32 @@ __host__ __device__ __forceinline__ u64 seg_stored_src(u64 end_pos, u64 out_len,
 //   bits 8-23 literal value / length base / distance base | bit 24 length | bit 25 end of block | bit 26 invalid
 constexpr u32 TK_LEN = 1u << 24, TK_EOB = 1u << 25, TK_INV = 1u << 26;
 
-// What a token decoder keeps per warp besides its two 32-bit LUTs.  (No 16-bit LUTs as in InfWarpSmem: the 32-bit ones
-// are filled straight from the canonical arrays — 2.5 KB less per warp is two more CTAs per SM for k_inf_tokens.)
+// What a token decoder keeps per warp besides its two 32-bit LUTs: the canonical arrays (the slow path for codes longer
+// than the root tables).  What only lives while a header is parsed and the tables are built shares the LUTs' room —
+// the code-length code's LUT and lengths sit where lut_ll is filled afterwards, the literal/length and distance code
+// lengths where lut_d is filled last (tk_build_tables reads them before that): 6,112 bytes per warp instead of 6,752,
+// which is what lets NINE four-warp CTAs of k_inf_tokens share an SM's 228 KiB instead of eight.
 struct TokCore {
-  u16 lut_d[1 << CL_ROOT];  // the code-length code's LUT while a header is parsed
   u16 sorted_ll[288];
   u16 sorted_d[64];
   InfTab tab_ll, tab_d;
   u16 cur[16];
-  u8 lens[352];  // [0,288) literal/length code lengths, [288,352) distance code lengths
-  u8 cl_lens[32];
 };
 struct TokWarpSmem {
-  u32 lut_ll[1 << LL_ROOT];
-  u32 lut_d[1 << D_ROOT];
+  union {
+    u32 lut_ll[1 << LL_ROOT];
+    struct {
+      u16 cl_lut[1 << CL_ROOT];  // the code-length code's LUT while a header is parsed
+      u8 cl_lens[32];
+    };
+  };
+  union {
+    u32 lut_d[1 << D_ROOT];
+    u8 lens[352];  // [0,288) literal/length code lengths, [288,352) distance code lengths
+  };
   TokCore w;
 };
+static_assert(sizeof(TokWarpSmem) == 4096 + 1024 + sizeof(TokCore), "header-time members must fit inside the LUTs");
 constexpr int TOK_SMEM = (int)sizeof(TokWarpSmem) * INF_WARPS;
 
 __device__ __forceinline__ u32 tk_entry_ll(u32 sym, u32 l) {
@@ -576,13 +586,14 @@ __device__ __forceinline__ u32 tk_entry_d(u32 sym, u32 l) {
 // to the sequential decoder.
 __device__ __forceinline__ void tk_build_tables(TokWarpSmem *T) {
   TokCore *S = &T->w;
-  inf_canon(S->lens, 288, S->sorted_ll, &S->tab_ll, S->cur);
+  inf_canon(T->lens, 288, S->sorted_ll, &S->tab_ll, S->cur);
   for (u32 i = lane_id(); i < (1u << LL_ROOT); i += 32) {
     const u32 e = inf_lut_entry(i, LL_ROOT, &S->tab_ll, S->sorted_ll);
     T->lut_ll[i] = ((e & 15) && (e >> 4) < 286) ? tk_entry_ll(e >> 4, e & 15) : 0;
   }
   __syncwarp();
-  inf_canon(S->lens + 288, 32, S->sorted_d, &S->tab_d, S->cur);
+  inf_canon(T->lens + 288, 32, S->sorted_d, &S->tab_d, S->cur);
+  __syncwarp();  // the lengths have been read: lut_d takes their room
   for (u32 i = lane_id(); i < (1u << D_ROOT); i += 32) {
     const u32 e = inf_lut_entry(i, D_ROOT, &S->tab_d, S->sorted_d);
     T->lut_d[i] = ((e & 15) && (e >> 4) < 30) ? tk_entry_d(e >> 4, e & 15) : 0;
@@ -703,27 +714,28 @@ struct SpecReader : TokReader {
 };
 
 // dynamic block header for phase A (same as inf_read_dynamic_header, on the TokReader)
-__device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, TokCore *S, u32 &status) {
+__device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, TokWarpSmem *T, u32 &status) {
+  TokCore *S = &T->w;
   const u32 lane = lane_id();
   const u32 HLIT = r.take(5) + 257;
   const u32 HDIST = r.take(5) + 1;
   const u32 HCLEN = r.take(4) + 4;
-  S->cl_lens[lane] = 0;
-  for (u32 i = lane; i < 352; i += 32) S->lens[i] = 0;
+  T->cl_lens[lane] = 0;
+  for (u32 i = lane; i < 352; i += 32) T->lens[i] = 0;
   __syncwarp();
   for (u32 i = 0; i < HCLEN; i++) {
     r.refill();
     const u32 v = r.take(3);
-    if (lane == 0) S->cl_lens[c_cl_order[i]] = (u8)v;
+    if (lane == 0) T->cl_lens[c_cl_order[i]] = (u8)v;
   }
   __syncwarp();
-  inf_build(S->cl_lens, 32, CL_ROOT, S->lut_d, S->sorted_d, &S->tab_d, S->cur);
+  inf_build(T->cl_lens, 32, CL_ROOT, T->cl_lut, S->sorted_d, &S->tab_d, S->cur);
   const u32 total = HLIT + HDIST;
   u32 prev = 0;
   for (u32 i = 0; i < total;) {
     r.refill();
     if (r.past_end()) { status = SEG_E_LACK; return false; }
-    u32 e = S->lut_d[r.peek(CL_ROOT)], l = e & 15, sym = e >> 4;
+    u32 e = T->cl_lut[r.peek(CL_ROOT)], l = e & 15, sym = e >> 4;
     if (l == 0 && !inf_slow(r.bits64(), &S->tab_d, S->sorted_d, sym, l)) { status = SEG_E_CORRUPT; return false; }
     r.skip(l);
     u32 rep = 1, val = sym;
@@ -734,8 +746,8 @@ __device__ __forceinline__ bool tk_read_dynamic_header(TokReader &r, TokCore *S,
     if (val) {
       for (u32 k = lane; k < rep; k += 32) {
         const u32 j = i + k;
-        if (j < HLIT) { if (j < 288) S->lens[j] = (u8)val; }
-        else if (j - HLIT < 32) S->lens[288 + j - HLIT] = (u8)val;
+        if (j < HLIT) { if (j < 288) T->lens[j] = (u8)val; }
+        else if (j - HLIT < 32) T->lens[288 + j - HLIT] = (u8)val;
       }
       // a run that gives distance symbols 32.. a length (it spills past HDIST = 32): the reference keeps those codes
       // (src/inflate.ts:187-200); the parallel tiers do not model them — such a block is left to the sequential decoder
@@ -828,10 +840,10 @@ __device__ __forceinline__ void inf_segment_tokens(TokWarpSmem *T, const u8 *in,
     }
     if (flags & SEGF_STORED) { status = SEG_E_CORRUPT; break; }  // a coded block after stored data: not one of ours
     if (btype == 1) {
-      for (u32 i = lane; i < 320; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
+      for (u32 i = lane; i < 320; i += 32) T->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : 5);
       __syncwarp();
     } else {
-      if (!tk_read_dynamic_header(r, S, status)) break;
+      if (!tk_read_dynamic_header(r, T, status)) break;
     }
     tk_build_tables(T);
     // symbol loop (/root/reference/src/inflate.ts:237-291 without the copy).  It cannot run away: every

@@ -469,9 +469,9 @@ k_fblk_head(const u8 *__restrict__ in, u64 n, const FbJob *__restrict__ jobs, u3
     u32 status = 0;
     bool ok = false;
     if (btype == 2) {
-      ok = tk_read_dynamic_header(r, S, status);
+      ok = tk_read_dynamic_header(r, T, status);
     } else if (btype == 1) {  // the fixed code, /root/reference/src/huffman.ts:41-53
-      for (u32 i = lane; i < 352; i += 32) S->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : i < 320 ? 5 : 0);
+      for (u32 i = lane; i < 352; i += 32) T->lens[i] = (u8)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : i < 288 ? 8 : i < 320 ? 5 : 0);
       __syncwarp();
       ok = true;
       m.fixed = m.bfinal ? 0 : 1;  // (a final block is followed by nothing)

@@ -230,7 +230,7 @@ k_inf_tokens4(const u8 *__restrict__ in, u64 n, const u64 *__restrict__ seg_pos,
         bfinal = r.take(1);
         const u32 btype = r.take(2);
         u32 status = 0;
-        if (btype == 2 && tk_read_dynamic_header(r, S, status)) {
+        if (btype == 2 && tk_read_dynamic_header(r, T, status)) {
           tk_build_tables(T);
           const u64 bp = r.bitpos();
           if (seg_end > in_pos && (seg_end << 3) > bp && (seg_end - in_pos) < (1u << 19)) {

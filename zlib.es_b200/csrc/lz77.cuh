@@ -57,8 +57,8 @@ constexpr u32 LZ_SMEM = LZ_OFF_MISC + 2048;                 // 231808 B (of 2324
 constexpr u32 LZ_SCAN = 32;                                 // candidates compared per position (at most)
 constexpr u32 LZ_BGROUP = 16;                               // batch mode: blocks per group (one sort when all are small)
 constexpr u32 LZ_BSLOT = (2 * SUB) / LZ_BGROUP;              // 4096: the most a block of a packed group holds
-constexpr u32 LZ_DENSE_SHIFT = 4;                            // blocks {0,1} of a chunk in fewer than 1/16 token per byte: blocks 2 and 3
-                                                            // are then matched one at a time, block 2 WITH its window (pair mode)
+constexpr u32 LZ_REDO_SLACK = 64;                            // pair mode: block 2 is matched again with its window when it took more than
+                                                            // 4/3 of block 3's tokens plus this many (see the end of a unit)
 constexpr u32 LZ_SLICE = 256;                               // sorted entries per dynamically scheduled slice (multiple of 32)
 // per-warp candidate ring: 64 entries of 4 bytes (lz_tag), stored twice (slot i and i + 64) so that "entry k - r"
 // is a constant offset from a per-lane base and needs no wrap-around arithmetic
@@ -78,9 +78,7 @@ struct LzParams {
   u32 min_checks;     // reserved (reference: FAST_INDEX_CHECK_MIN = 16, src/lz77.ts:8)
   u32 good_len;       // reserved (reference: FAST_REPEAT_LENGTH = 8, src/lz77.ts:9)
   u32 lazy;           // 1: defer a match by one literal when the next position has a longer one
-  u32 *unit_ctr = nullptr;  // zeroed before the launch: units are handed out from it, the two-block ones first;
-                            // stream mode: followed by one word per chunk of the launch (0 = blocks {0,1} not matched yet,
-                            // 1 = matched, 2 = matched and they are almost all matches: see LZ_DENSE_SHIFT)
+  u32 *unit_ctr = nullptr;  // zeroed before the launch: units are handed out from it, the two-block ones first
   u32 pair_mode = 1;  // 1: two sorts per chunk — blocks {0,1} and {2,3}: block 2 has no window (the default);
                       // 0: three — {0,1}, then {2} and {3} each with the block before as window (smaller output, slower)
   const BatchBlk *table = nullptr;  // batch mode: block b is table[b] (in/n describe one stream otherwise)
@@ -350,7 +348,7 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
   if (tid == 0) mbar_init(mbar, 1);
   __syncthreads();
 #endif
-  if (tid == 0) seg_len[0] = seg_len[1] = 0;  // stream mode: [0] the flag this unit sets when done, [1] a pending single-block unit, [2] the flag read
+  if (tid == 0) seg_len[0] = seg_len[1] = 0;  // stream mode: [0] 1 + the block 2 this unit is judged by, [1] a pending single-block unit
   u32 *Y = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // sort pass buffer, 2 * SUB entries
   u32 *R = P.scratch + (size_t)blockIdx.x * 2 * SUB;  // then the match results, SUB entries
 
@@ -363,8 +361,8 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
   const u32 nunits = TABLE ? (P.nblocks - P.first_block + LZ_BGROUP - 1) / LZ_BGROUP : (c_end - c_begin) * upc;
   for (;;) {
     // units come from a counter (their cost differs: two blocks or one); all two-block units are handed out first.
-    // Bit 31 set: not a unit of the counter but block (ui & 0x7fffffff) on its own, with the block before it as window — the
-    // second half of a {2,3} unit that this CTA split (see below), waiting in seg_len[1].
+    // Bit 31 set: not a unit of the counter but block (ui & 0x7fffffff) on its own, with the block before it as window — a
+    // block 2 that this CTA matches a second time (see the end of a unit), waiting in seg_len[1].
     __syncthreads();
     if (tid == 0) {
       if (!TABLE && seg_len[1]) { *slice_ctr = seg_len[1]; seg_len[1] = 0; }
@@ -408,28 +406,18 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
       else { const u32 r = ui - (c_end - c_begin); v = (c_begin + r / (upc - 1)) * upc + 1 + r % (upc - 1); }
       const u32 chunk = v / upc, k = v % upc;
       u32 sb0, nsb;
-      if (tid == 0) seg_len[0] = (P.pair_mode && k == 0) ? 1u + (chunk - c_begin) : 0u;  // the flag this unit sets when it is done
       if (ui & 0x80000000u) { sb0 = (ui & 0x7fffffffu) % SUBS_PER_CHUNK; nsb = 1; hist_len = SUB; }
       else if (k == 0) { sb0 = 0; nsb = 2; hist_len = 0; }
       else if (P.pair_mode) {
-        // Pair mode gives block 2 no window — on input that is all long matches (a period of 256 bytes costs 256 literals
-        // again, a third of such a chunk's output) that is not "within 3 %".  The {2,3} unit therefore waits for the chunk's
-        // {0,1} unit (handed out earlier, so it is finished or running on a resident CTA that waits for nothing) and, when
-        // that one came out in very few tokens, matches block 2 now and block 3 next, each with the block before as window.
-        sb0 = 2; nsb = 2; hist_len = 0;
-        if (chunk * SUBS_PER_CHUNK + 2 < P.nblocks) {
-          if (tid == 0) {
-            volatile u32 *flag = P.unit_ctr + 1 + (chunk - c_begin);
-            u32 f;
-            while ((f = *flag) == 0) __nanosleep(200);
-            seg_len[2] = f;  // (not through *slice_ctr: other warps may not have read this unit's index from it yet)
-            if (f == 2 && chunk * SUBS_PER_CHUNK + 3 < P.nblocks) seg_len[1] = 0x80000000u | (chunk * SUBS_PER_CHUNK + 3);
-          }
-          __syncthreads();
-          if (seg_len[2] == 2) { nsb = 1; hist_len = SUB; }  // (rewritten a unit later at the earliest: many barriers from here)
-        }
+        // blocks {2,3} share a sort, block 2 without a window — or, when the chunk ends with block 2, that block alone
+        // WITH its window (nothing to share the sort with, and no block 3 to judge the missing window by: see below)
+        const bool has3 = chunk * SUBS_PER_CHUNK + 3 < P.nblocks;
+        sb0 = 2; nsb = has3 ? 2u : 1u; hist_len = has3 ? 0u : SUB;
       }
       else { sb0 = k + 1; nsb = 1; hist_len = SUB; }  // window = previous SUB of the same chunk
+      // (remembered in shared memory, not in registers — the kernel sits at its 64-register cap: 1 + the block 2 that is
+      // judged at the end of this unit, 0 for every other kind of unit)
+      if (tid == 0) seg_len[0] = (!(ui & 0x80000000u) && k == 1 && P.pair_mode && nsb == 2) ? chunk * SUBS_PER_CHUNK + 3 : 0u;
       bfirst = chunk * SUBS_PER_CHUNK + sb0;
       if (bfirst >= P.nblocks) continue;  // the stream's last chunk is short (uniform over the CTA)
       own_off = (u64)bfirst * SUB;
@@ -872,12 +860,14 @@ __device__ __forceinline__ void lz_body(const LzParams &P) {
     __syncthreads();
     }  // blocks of the unit
     __syncthreads();
-    if (!TABLE && tid == 0 && seg_len[0]) {  // the chunk's {2,3} unit may go ahead (P.ntok: thread 0's own stores)
-      u32 nt = 0;
-      for (u32 sbi = 0; sbi < nsub; sbi++) nt += P.ntok[bfirst + sbi];
-      __threadfence();
-      atomicExch(P.unit_ctr + seg_len[0], (nt << LZ_DENSE_SHIFT) < unit_own ? 2u : 1u);
-
+    // Pair mode gave block 2 no window.  What that cost is judged by block 3, which had one (block 2): when block 2 came out
+    // in a third more tokens than block 3 — a period longer than a few hundred bytes costs its literals again, a patchwork
+    // repeats what block 1 held — block 2 is matched again, alone, with block 1 as window (this CTA's next unit).  Text
+    // and binary data stay at 1.05–1.15 (tools/gpu_size_sweep.py), zeros at 1.0: no second pass.
+    if (!TABLE && tid == 0 && seg_len[0]) {
+      const u32 b2 = seg_len[0] - 1;
+      const u32 nt2 = P.ntok[b2], nt3 = P.ntok[b2 + 1];  // (thread 0's own stores)
+      if (3 * nt2 > 4 * nt3 + LZ_REDO_SLACK) seg_len[1] = 0x80000000u | b2;
     }
     LZ_CLK(scratch, 11);
     }  // blocks of an unpacked group

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_
     t.in_off = beg + k * SUB;
     t.own_len = (u32)umin64((u64)SUB, len - k * SUB);
     const u32 kc = (u32)(k % SUBS_PER_CHUNK);
-    t.hist_len = (kc == 0 || (pair_mode && kc == 2)) ? 0 : SUB;
+    t.hist_len = (kc == 0 || (pair_mode && kc == 2 && k + 1 < nb)) ? 0 : SUB;  // (a chunk that ends with block 2: window, as in k_lz)
     table[b0 + k] = t;
   }
 }

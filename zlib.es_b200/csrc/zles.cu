@@ -278,6 +278,8 @@ static int set_kernel_attrs(int device) {
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_piece_sym)");
   e = zrt_set_smem(k_inf_tokens4, SPEC_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens4)");
+  e = zrt_prefer_smem(k_inf_tokens);  // nine CTAs of 24,448 + 1,024 bytes per SM need all 228 KiB as shared memory
+  if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens, carveout)");
   e = zrt_set_smem(k_inf_tokens, TOK_SMEM);
   if (e != ZRT_OK) return cuda_fail(e, "cudaFuncSetAttribute(k_inf_tokens)");
   e = zrt_set_smem(k_inflate_batch, INF_SMEM);
@@ -568,7 +570,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
   lp.good_len = c->good_len;
   lp.lazy = c->lazy;
   lp.pair_mode = c->pair_mode;
-  RET(c->unit_ctr.reserve(4 + 4 * (((size_t)nblocks + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK)));  // the counter, then a flag per chunk
+  RET(c->unit_ctr.reserve(4));
   lp.unit_ctr = c->unit_ctr.as<u32>();
   // Host input arrives slab by slab: one wave of CTAs first (the matcher starts as soon as 4.6 MiB are on the device),
   // then 2, then 4 waves per slab (a multiple of the SM count keeps the tail of every launch short); whole chunks.
@@ -649,7 +651,7 @@ static int deflate_phase1(zles_ctx *c, const u8 *d_in, size_t n, int is_last, zl
     lp.first_block = b0;
     lp.nblocks = b1;
     lp.tokens = c->tokens.as<u32>() - (piped ? (size_t)b0 * SUB : 0);
-    CK(zrt_memset(lp.unit_ctr, 0, 4 + 4 * (size_t)((b1 - b0 + SUBS_PER_CHUNK - 1) / SUBS_PER_CHUNK), c->stream));
+    CK(zrt_memset(lp.unit_ctr, 0, 4, c->stream));
     LAUNCH(c, k_lz, (u32)umin64((u64)(b1 - b0), (u64)c->sm_count), LZ_THREADS, LZ_SMEM, lp);
     LAUNCH(c, k_huff, (b1 - b0 + HUF_WARPS - 1) / HUF_WARPS, HUF_THREADS, HUF_SMEM, (const u32 *)c->hist.as<u32>(), b0, b1,
            c->codes.as<BlockCodes>(), c->blk_bits.as<u32>(), (u64)n, (const BatchBlk *)nullptr);

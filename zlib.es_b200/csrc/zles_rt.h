@@ -32,6 +32,8 @@ static inline zrt_err_t zrt_last_error() { return 0; }
 static inline const char *zrt_err_str(zrt_err_t) { return "emulator"; }
 template <typename K>
 static inline zrt_err_t zrt_set_smem(K, int) { return 0; }
+template <typename K>
+static inline zrt_err_t zrt_prefer_smem(K) { return 0; }
 static inline int zrt_sm_count(int) { return 4; }
 typedef int zrt_event_t;
 static inline zrt_err_t zrt_event_create(zrt_event_t *e) { *e = 0; return 0; }
@@ -82,6 +84,11 @@ static inline const char *zrt_err_str(zrt_err_t e) { return cudaGetErrorString(e
 template <typename K>
 static inline zrt_err_t zrt_set_smem(K kern, int bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+// all of the SM's L1/shared array as shared memory: for kernels whose residency is bound by shared memory per CTA
+template <typename K>
+static inline zrt_err_t zrt_prefer_smem(K kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 typedef cudaEvent_t zrt_event_t;
 static inline zrt_err_t zrt_event_create(zrt_event_t *e) { return cudaEventCreate(e); }

@@ -555,8 +555,10 @@ def run_ours(args):
             "gpu_launches": launches_total,
             "device_mem_gib": {"rank0_in_use_after_the_timed_steps": dev_mem_gib,
                                "of_which_bench_tensors": round((2 * n + cap + (cap if multi else 0)) / (1 << 30), 2),
-                               "note": "the rest is the codec's workspace (token slots: 4 B per input byte of one 1 GiB slab when one GPU "
-                                       "deflates a long resident input; of the whole shard in the two-phase sharded form)"},
+                               "note": "the rest is the codec's workspace: inflate keeps token rows for every block of the stream it decodes (4 B per output "
+                                       "byte: 32 GiB for 8 GiB) plus 16-bit symbols for one group of 8,192 blocks; deflate keeps token rows for one "
+                                       "1 GiB slab of a long resident input (4 GiB; the whole shard in the two-phase sharded form), histograms and "
+                                       "codes per block; buffers are over-allocated by 1/8 and never shrink"},
             "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in kt.items() if v[1]},
             "roofline": {"bound": "hbm", "kernel": "k_lz", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": tr["traffic"] if tr else None, "traffic_source": tr, "peak_source": peak_src,

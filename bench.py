@@ -80,6 +80,24 @@ def ncu_traffic(kernel: str, launch_input_bytes: float):
         return None
 
 
+def issue_roofline(kernel: str, launch_input_bytes: float, launch_ms: float, sm_mhz: float, sms: int):
+    """The bound that actually holds for the byte-granular integer kernels (DRAM is 1 % busy): warp instructions issued per
+    second against the SMs' issue rate (4 schedulers per SM, one warp instruction per cycle each).  The instruction count
+    per input byte comes from the committed ncu capture (smsp__inst_executed.sum), the time is this run's."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        k = j[kernel]
+        inst = k["warp_inst"] / k["input_bytes_per_launch"] * launch_input_bytes
+        peak = sms * 4 * sm_mhz * 1e6
+        ach = inst / (launch_ms * 1e-3)
+        return {"bound": "issue", "kernel": kernel, "achieved": round(ach / 1e9, 1), "peak": round(peak / 1e9, 1), "unit": "G warp-instructions/s",
+                "frac": round(ach / peak, 4), "warp_instructions_per_input_byte": round(k["warp_inst"] / k["input_bytes_per_launch"], 2),
+                "peak_source": "%d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)" % (sms, sm_mhz),
+                "profile_git": j.get("_meta", {}).get("git")}
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle on all host cores, one worker per core over independent 128 KiB-aligned pieces
 # ---------------------------------------------------------------------------------------------
@@ -563,6 +581,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_lz", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 5), "traffic": tr["traffic"] if tr else None, "traffic_source": tr, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo), "launch_ms": round(lz_avg_ms, 4), "launches_per_step": lz_launches},
+            "roofline_issue": issue_roofline("k_lz", shard / lz_launches, lz_avg_ms, float((clocks or {}).get("sm_mhz") or 1965.0),
+                                             torch.cuda.get_device_properties(local).multi_processor_count),
             "roofline_inflate": {"bound": "hbm", "kernels": "phase A (k_inf_tokens | k_inf_tokens4) + phase B (k_inf_resolve | k_piece_sym + k_chunk_final)",
                                  "achieved": round(algo_shard / (inf_ms * 1e-3) / 1e9, 2) if inf_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
                                  "frac": round(algo_shard / (inf_ms * 1e-3) / 1e9 / peak, 5) if inf_ms > 0 else 0.0, "algorithmic_bytes_per_launch": int(algo_shard)},

@@ -131,7 +131,9 @@ uint32_t zles_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
  * the per-buffer code.  Host pointers.  Returns 0 when every buffer succeeded, ZLES_E_CUDA / ZLES_E_ARG / ZLES_E_NOMEM when
  * the call as a whole failed (status[] is then untouched), otherwise the LARGEST per-buffer status — e.g. OUTPUT_FULL (16)
  * hides CORRUPTED (4): inspect status[], do not branch on the return value alone.  For inflate, out_len[i] of a buffer
- * with status OUTPUT_FULL holds the size it needs; only the bytes actually produced are copied back to the host. */
+ * with status OUTPUT_FULL holds the size it needs; only the bytes actually produced are copied back to the host.
+ * deflate: a buffer of at most 64 KiB compresses to exactly the bytes zles_deflate gives it on its own; a longer one may
+ * come out a little smaller (every block but a chunk's first sees its 32 KiB window in a batch). */
 int zles_deflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,
                        const uint64_t *out_off, uint64_t *out_len, int32_t *status);
 int zles_inflate_batch(zles_ctx *ctx, const uint8_t *in, const uint64_t *in_off, uint32_t count, uint8_t *out,

@@ -225,7 +225,10 @@ def test_batch(c):
     assert len(zs) == len(bufs)
     for b, z in zip(bufs[:20], zs[:20]):
         assert zlib.decompress(z) == b and O.inflate(z) == b
-        assert z == c.deflate(b)
+        if len(b) <= 65536:
+            assert z == c.deflate(b)          # the same bytes alone and in a batch
+        else:
+            assert len(z) <= len(c.deflate(b))  # a long buffer's third blocks get their windows in a batch: never larger
     for b, z in zip(bufs, zs):
         assert zlib.decompress(z) == b
     assert c.inflate_batch(zs) == bufs

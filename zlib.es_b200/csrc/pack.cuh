@@ -371,8 +371,11 @@ __global__ void __launch_bounds__(1024) k_batch_count(const u64 *__restrict__ in
   if (threadIdx.x == 0) blk_first[count + 1] = scratch[0];
 }
 
-// pair_mode: the window policy of LzParams (1: a chunk's third block has no window), so that a buffer of a batch
-// compresses to the same bytes as on its own
+// A buffer of more than one block: every block but a chunk's first gets the 32 KiB before it as window.  (The stream form
+// leaves a chunk's third block without one so that blocks {2,3} share a sort — LzParams::pair_mode — and repairs the cases
+// where that costs size with a second pass; a batch matches the blocks of a long buffer one at a time anyway, so the
+// window is free.  A buffer of at most 64 KiB compresses to the same bytes alone and in a batch; a longer one may come out
+// smaller in a batch.)  pair_mode is accepted and ignored.
 __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_off, u32 count, const u64 *__restrict__ blk_first,
                                                      BatchBlk *table, u32 pair_mode) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__(256) k_batch_table(const u64 *__restrict__ in_
     t.in_off = beg + k * SUB;
     t.own_len = (u32)umin64((u64)SUB, len - k * SUB);
     const u32 kc = (u32)(k % SUBS_PER_CHUNK);
-    t.hist_len = (kc == 0 || (pair_mode && kc == 2 && k + 1 < nb)) ? 0 : SUB;  // (a chunk that ends with block 2: window, as in k_lz)
+    t.hist_len = kc == 0 ? 0 : SUB;
+    (void)pair_mode;
     table[b0 + k] = t;
   }
 }

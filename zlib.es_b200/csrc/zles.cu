@@ -141,6 +141,8 @@ struct zles_ctx {
   StageRing ring_in, ring_out;  // pinned staging of large pageable host buffers (stager.inl)
   u64 *cand_mail = nullptr;  // pinned: block starts read back by scan_block_starts
   size_t cand_mail_cap = 0;
+  u64 *slab_cand = nullptr;  // pinned: the block starts of one slab on their way back to the device (inflate_known_starts)
+  size_t slab_cand_cap = 0;
   CorpusTable *d_corpus = nullptr;
   CrcTables *d_crc = nullptr;  // CRC-32 tables (gzip), uploaded on first use
   DevBuf crc_part;
@@ -329,6 +331,8 @@ extern "C" void zles_ctx_destroy(zles_ctx *c) {
   c->slab_mail = nullptr;
   if (c->cand_mail) zrt_host_free(c->cand_mail);
   c->cand_mail = nullptr;
+  if (c->slab_cand) zrt_host_free(c->slab_cand);
+  c->slab_cand = nullptr;
   if (c->batch_stage) zrt_host_free(c->batch_stage);
   c->batch_stage = nullptr;
   c->ring_in.release();
@@ -1445,6 +1449,36 @@ constexpr size_t INF_SLAB_MIN_STREAM = 1u << 16;  // shorter streams are not wor
 constexpr u32 INF_SLAB_BLOCKS = 16384;  // 512 MiB of output per slab: enough blocks for one warp per block to fill the GPU
 static int scan_block_starts(zles_ctx *c, const u8 *d_in, size_t n, u64 first, std::vector<u64> &starts);
 
+// inflate_body for a run of our blocks whose starts the host already knows (h_starts[0 .. ncand), `rebase` is subtracted:
+// they become offsets into d_in): the marker scan — two kernels and a wait per slab — is skipped, the list goes to the
+// device with the launches.  Our blocks only (anything else: ZLES_E_CORRUPTED, the caller takes the general path).
+static int inflate_known_starts(zles_ctx *c, const u8 *d_in, size_t n, const u64 *h_starts, u32 ncand, u64 rebase, u8 *d_out, size_t cap,
+                                size_t *out_len, bool has_final) {
+  RET(c->ctl.reserve(sizeof(InfCtl)));
+  InfCtl *ctl = c->ctl.as<InfCtl>();
+  const u64 cand_cap64 = (u64)n / 32 + 64;
+  if (cand_cap64 > 0x7fffffffull) return ZLES_E_ARG;
+  if (ncand == 0 || ncand > cand_cap64) return ZLES_E_CORRUPTED;
+  RET(c->cand.reserve((size_t)cand_cap64 * 8));
+  if (c->slab_cand_cap < (size_t)ncand + 1) {
+    if (c->slab_cand) zrt_host_free(c->slab_cand);
+    c->slab_cand = nullptr;
+    c->slab_cand_cap = 0;
+    const size_t want = (size_t)ncand + ((size_t)ncand >> 2) + 64;
+    CK(zrt_host_alloc(reinterpret_cast<void **>(&c->slab_cand), want * 8));
+    c->slab_cand_cap = want;
+  }
+  for (u32 j = 0; j < ncand; j++) c->slab_cand[j] = h_starts[j] - rebase;
+  c->slab_cand[ncand] = ncand;  // (its low word is what goes into ctl->ncand)
+  CK(zrt_memset(ctl, 0, sizeof(InfCtl), c->stream));
+  // read from the pinned list by a kernel: a copy would queue behind the bulk host-to-device copies of the stream's pieces
+  // (measured: 55 ms per 8 GiB lost that way)
+  CK(zrt_mail(c->cand.p, c->slab_cand, (size_t)ncand * 8, c->stream));
+  CK(zrt_mail(&ctl->ncand, c->slab_cand + ncand, 4, c->stream));
+  // (the pinned list is rewritten for the next slab only after inflate_decode has waited for this one's result)
+  return inflate_decode(c, d_in, n, c->slab_cand[0], ncand, (u32)cand_cap64, d_out, cap, out_len, has_final, /*ours_only=*/true);
+}
+
 // One slab after the other: decode(b0, b1) decodes blocks [b0, b1) of the run into one of two device buffers and queues
 // its copy to the host on the output stream; finish() waits for the copies.
 struct SlabDecoder {
@@ -1482,7 +1516,7 @@ struct SlabDecoder {
     if (copied_valid[k & 1]) CK(zrt_stream_wait_event(c->stream, copied[k & 1]));  // the copy out of this buffer (slab k - 2) is done
     size_t olen = 0;
     TRACE("slab %u: blocks [%zu, %zu) begin", k, b0, b1);
-    int rc = inflate_body(c, d_in + in0, (size_t)(end - in0), al, d_slab, cap, &olen, has_final && last, /*ours_only=*/true);
+    int rc = inflate_known_starts(c, d_in + in0, (size_t)(end - in0), starts.data() + b0, (u32)(b1 - b0), in0, d_slab, cap, &olen, has_final && last);
     TRACE("slab %u: decoded rc=%d olen=%zu", k, rc, olen);
     if (rc == ZLES_E_OUTPUT_FULL) { total = off + olen; return rc; }
     if (rc == ZLES_E_CUDA) return rc;

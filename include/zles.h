@@ -65,7 +65,9 @@ int zles_ctx_set_stream(zles_ctx *ctx, void *cuda_stream);
 int zles_ctx_set_level(zles_ctx *ctx, uint32_t max_checks, uint32_t min_checks, uint32_t good_len, uint32_t lazy);
 /* Which window the third 32 KiB block of a 128 KiB chunk sees (/root/reference/src/lz77.ts:49 gives every position the
  * 32 KiB before it inside its chunk).  1 (default): none, like block 0 — blocks {0,1} and {2,3} each share one match-finder
- * pass.  0: the block before it, like blocks 1 and 3 — three passes per chunk, ~25 % slower, output ~1.4 % smaller on text.
+ * pass; a third block that took a third more tokens than the fourth (periodic or repeated material: what the window is
+ * for) is matched again with its window.  0: the block before it, like blocks 1 and 3 — three passes per chunk, ~25 %
+ * slower, output ~1.4 % smaller on text.
  * Either way the stream stays within 3 % of the reference's size on the benchmark corpora ("Size"). */
 int zles_ctx_set_window_mode(zles_ctx *ctx, uint32_t mode);
 /* Host-buffer inflate of our own streams runs slab by slab (finished slabs are copied to the host while the next one is

@@ -323,6 +323,29 @@ def slabbed_host_inflate(c, n):
             c.set_slab_blocks(0)
 
 
+def spurious_markers_in_slabs(c):
+    """Incompressible data that contains the marker bytes 00 00 FF FF: its blocks are stored, so the pattern appears
+    verbatim in the stream and the marker scan reports block starts that are none.  The slab-by-slab host inflate (which
+    decodes from the list of starts the host holds) must notice and hand the stream to the general path: same bytes for
+    every slab size, with and without the piece-wise copy in."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    a = bytearray(rng.integers(0, 256, size=600000, dtype=np.uint8).tobytes())
+    for o in range(1000, len(a) - 10, 7001):
+        a[o:o + 4] = b"\x00\x00\xff\xff"
+    d = bytes(a) + T.gen("G5", 200000)
+    z = c.deflate(d)
+    assert zlib.decompress(z) == d
+    try:
+        for smin, slab in ((1 << 40, 0), (1 << 40, 4), (1 << 40, 8), (200000, 4), (300000, 8)):
+            c.set_stream_min(smin)
+            c.set_slab_blocks(slab)
+            assert c.inflate(z) == d, (smin, slab)
+    finally:
+        c.set_stream_min(96 << 20)
+        c.set_slab_blocks(0)
+
+
 def wire_format_siblings(c, n):
     """raw deflate data (the reference's cores, /root/reference/src/deflate.ts:14 and src/inflate.ts:16 with its
     `offset` parameter) and gzip (RFC 1952, CRC-32) behind the same kernels — against system zlib / Python gzip / the oracle."""

@@ -238,5 +238,9 @@ def test_raw_deflate_and_gzip(c):
     P.wire_format_siblings(c, 300001)
 
 
+def test_spurious_markers_in_slabs(c):
+    P.spurious_markers_in_slabs(c)
+
+
 def test_host_batch_in_slabs(c):
     P.batch_in_slabs(c, 40)

@@ -286,6 +286,10 @@ def test_host_inflate_in_slabs(c):
     P.slabbed_host_inflate(c, 40 << 20)
 
 
+def test_spurious_markers_in_slabs(c):
+    P.spurious_markers_in_slabs(c)
+
+
 def test_raw_deflate_and_gzip(c):
     P.wire_format_siblings(c, 20971527)
 

@@ -440,6 +440,20 @@ def run_ours(args):
     kt = {k: c.kernel_time(k) for k in ("k_lz", "k_huff", "k_pack", "k_inf_tokens", "k_inf_tokens4", "k_inf_resolve", "k_piece_sym", "k_chunk_final",
                                         "k_mark_count", "k_mark_emit")}
     c.set_timing(False)
+    # the one pure streaming kernel of the path on its own: Adler-32 of this rank's shard (standalone K8; in deflate the sums are
+    # fused into k_lz's load), against the same HBM peak
+    adler = None
+    try:
+        c.dev_adler32(src.data_ptr(), n)
+        c.set_timing(True)
+        for _ in range(3):
+            c.dev_adler32(src.data_ptr(), n)
+        a_ms, a_n = c.kernel_time("k_adler_partial")
+        c.set_timing(False)
+        if a_n:
+            adler = {"kernel": "k_adler_partial", "bytes": n, "launch_ms": round(a_ms / a_n, 4), "gbs": round(n / (a_ms / a_n * 1e-3) / 1e9, 1)}
+    except Exception as e:  # never let the side measurement break the line
+        adler = {"error": str(e)}
     lz_ms, lz_n = kt["k_lz"]
     tok_ms = kt["k_inf_tokens"][0] + kt["k_inf_tokens4"][0]
     tok_n = kt["k_inf_tokens"][1] + kt["k_inf_tokens4"][1]
@@ -583,6 +597,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": int(algo), "launch_ms": round(lz_avg_ms, 4), "launches_per_step": lz_launches},
             "roofline_issue": issue_roofline("k_lz", shard / lz_launches, lz_avg_ms, float((clocks or {}).get("sm_mhz") or 1965.0),
                                              torch.cuda.get_device_properties(local).multi_processor_count),
+            "roofline_adler": dict(adler, bound="hbm", peak=peak, unit="GB/s", frac=round(adler["gbs"] / peak, 4),
+                                   note="a read-only stream; the peak is a measured COPY bandwidth, so a pure read can exceed it") if adler and "gbs" in adler else adler,
             "roofline_inflate": {"bound": "hbm", "kernels": "phase A (k_inf_tokens | k_inf_tokens4) + phase B (k_inf_resolve | k_piece_sym + k_chunk_final)",
                                  "achieved": round(algo_shard / (inf_ms * 1e-3) / 1e9, 2) if inf_ms > 0 else 0.0, "peak": peak, "unit": "GB/s",
                                  "frac": round(algo_shard / (inf_ms * 1e-3) / 1e9 / peak, 5) if inf_ms > 0 else 0.0, "algorithmic_bytes_per_launch": int(algo_shard)},

@@ -471,8 +471,8 @@ static int dev_adler32(zles_ctx *c, const u8 *d_in, size_t n, uint32_t *adler) {
   CK(zrt_memset(acc, 0, 16, c->stream));
   if (n) {
     u64 nvec = (n >> 4) + 1;
-    u64 want = (nvec + ADLER_THREADS * 4 - 1) / (ADLER_THREADS * 4);
-    u32 grid = (u32)umin64(want, (u64)c->sm_count * 8);
+    u64 want = (nvec + ADLER_TILE_VECS - 1) / ADLER_TILE_VECS;  // tiles of 32 KiB, handed out grid-stride
+    u32 grid = (u32)umin64(want, (u64)c->sm_count * 4);          // four resident CTAs per SM (64 registers x 256 threads)
     if (grid == 0) grid = 1;
     LAUNCH(c, k_adler_partial, grid, ADLER_THREADS, ADLER_SMEM, d_in, (u64)n, acc);
   }
